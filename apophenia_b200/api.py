@@ -1,0 +1,218 @@
+"""Host-side mirror of the reference's operators for this path.
+
+Names follow the reference: `log_likelihood(d, m)` is apop_log_likelihood
+(apop_model.m4.c:257), `score(d, m)` is apop_score (:290), `pin` / `unpin` /
+`invalidate` manage HBM residency.  Everything computes on the B200 through the
+C-ABI in include/apop_b200.h.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import abi
+from .abi import (B200Error, Data, Model, PROBIT, LOGIT, POISSON, NORMAL, OLS, POISSON_REG,  # noqa: F401
+                  MAP_IDENTITY, MAP_DEV, MAP_DEV2, MAP_POISSON, MAP_LOG, MAP_EXP)
+
+__all__ = ["init", "finalize", "pin", "unpin", "invalidate", "is_pinned", "log_likelihood", "score",
+           "ll_score", "map_sum", "synth", "SynthData", "launch_count", "last_pass_ms", "pass_timer_reset",
+           "pass_timer", "probit_model", "logit_model", "vector_model", "Data", "Model", "B200Error",
+           "PROBIT", "LOGIT", "POISSON", "NORMAL", "OLS", "POISSON_REG", "comm_init_from_torch",
+           "comm_finalize", "set_auto_pin", "last_error", "information", "ols_gram"]
+
+_dp = C.POINTER(C.c_double)
+
+
+def _lib():
+    return abi.load_library()
+
+
+def init(device=-1):
+    """Bind this process to one B200 (LOCAL_RANK if device < 0)."""
+    abi.check(_lib().apop_b200_init(int(device)), "apop_b200_init")
+
+
+def finalize():
+    _lib().apop_b200_finalize()
+
+
+def last_error():
+    return abi.last_error()
+
+
+def set_auto_pin(on):
+    _lib().apop_b200_set_auto_pin(int(bool(on)))
+
+
+def pin(d: Data):
+    abi.check(_lib().apop_b200_pin(d.ptr), "apop_b200_pin")
+    return d
+
+
+def unpin(d):
+    return _lib().apop_b200_unpin(d.ptr)
+
+
+def invalidate(d):
+    return _lib().apop_b200_invalidate(d.ptr)
+
+
+def is_pinned(d):
+    return bool(_lib().apop_b200_is_pinned(d.ptr))
+
+
+def launch_count():
+    return int(_lib().apop_b200_launch_count())
+
+
+def last_pass_ms():
+    return float(_lib().apop_b200_last_pass_ms())
+
+
+def pass_timer_reset():
+    _lib().apop_b200_pass_timer_reset()
+
+
+def pass_timer():
+    n = C.c_ulonglong(0)
+    ms = _lib().apop_b200_pass_timer_total_ms(C.byref(n))
+    return float(ms), int(n.value)
+
+
+_LL = {PROBIT: "apop_b200_probit_ll", LOGIT: "apop_b200_logit_ll", POISSON: "apop_b200_poisson_ll",
+       NORMAL: "apop_b200_normal_ll", OLS: "apop_b200_ols_ll", POISSON_REG: "apop_b200_poisson_reg_ll"}
+_SC = {PROBIT: "apop_b200_probit_score", LOGIT: "apop_b200_logit_score", POISSON: "apop_b200_poisson_score",
+       NORMAL: "apop_b200_normal_score", OLS: "apop_b200_ols_score",
+       POISSON_REG: "apop_b200_poisson_reg_score"}
+
+
+def _ptr(obj):
+    return obj.ptr if obj is not None else None
+
+
+def log_likelihood(family, d, m):
+    """model->log_likelihood(d, m) on the device; NaN on error (reference convention)."""
+    return float(getattr(_lib(), _LL[family])(_ptr(d), _ptr(m)))
+
+
+def score(family, d, m, size=None):
+    """the apop_score vtable entry: fills a caller-allocated gsl_vector in pack order"""
+    if size is None:
+        p = m.parameters
+        size = (p.vector.size if p.vector is not None else 0) + (p.matrix.size if p.matrix is not None else 0)
+    out = np.zeros(size)
+    g, keep = abi.make_vector(out)
+    getattr(_lib(), _SC[family])(_ptr(d), C.byref(g), _ptr(m))
+    return out
+
+
+def ll_score(family, d, beta, want_score=True):
+    beta = np.ascontiguousarray(beta, dtype=np.float64).ravel()
+    g = np.zeros(beta.size) if want_score else None
+    ll = _lib().apop_b200_ll_score(int(family), _ptr(d), beta.ctypes.data_as(_dp), beta.size,
+                                   g.ctypes.data_as(_dp) if want_score else None)
+    return float(ll), g
+
+
+def information(family, d, beta):
+    beta = np.ascontiguousarray(beta, dtype=np.float64).ravel()
+    H = np.zeros((beta.size, beta.size))
+    abi.check(_lib().apop_b200_information(int(family), _ptr(d), beta.ctypes.data_as(_dp), beta.size,
+                                           H.ctypes.data_as(_dp)), "apop_b200_information")
+    return H
+
+
+def ols_gram(d):
+    k = d.matrix.shape[1] if getattr(d, "matrix", None) is not None else d.k
+    A = np.zeros((k, k)); b = np.zeros(k)
+    abi.check(_lib().apop_b200_ols_gram(_ptr(d), A.ctypes.data_as(_dp), b.ctypes.data_as(_dp)), "apop_b200_ols_gram")
+    return A, b
+
+
+def map_sum(d, fn, p0=0.0, part="a"):
+    return float(_lib().apop_b200_map_sum(_ptr(d), int(fn), float(p0), part.encode()))
+
+
+# ---- parameter containers shaped like the reference's --------------------------
+def probit_model(beta, data=None, name="Probit"):
+    """parameters = k x 1 matrix, as probit_prep allocates them (model/apop_probit.c:49)"""
+    b = np.ascontiguousarray(beta, dtype=np.float64).reshape(-1, 1)
+    return Model(name, Data(matrix=b), data)
+
+
+def logit_model(B, data=None, name="Logit"):
+    """parameters = k x (C-1) matrix"""
+    B = np.ascontiguousarray(B, dtype=np.float64)
+    if B.ndim == 1:
+        B = B.reshape(-1, 1)
+    return Model(name, Data(matrix=B), data)
+
+
+def vector_model(params, data=None, name="model"):
+    """parameters in the vector: Poisson (lambda), Normal (mu, sigma), OLS (beta)"""
+    return Model(name, Data(vector=np.ascontiguousarray(params, dtype=np.float64)), data)
+
+
+# ---- device-generated synthetic data -----------------------------------------------
+class SynthData:
+    """A resident, device-generated data set; `.ptr` is the apop_data* header."""
+
+    def __init__(self, family, n_rows, k, beta_true, ncat=2, seed=8, row_offset=0):
+        beta_true = np.ascontiguousarray(beta_true, dtype=np.float64).ravel()
+        self.family, self.n_rows, self.k, self.ncat = family, int(n_rows), int(k), int(ncat)
+        self.has_y = family not in (POISSON, NORMAL)
+        self._p = _lib().apop_b200_synth(int(family), self.n_rows, self.k, self.ncat,
+                                         beta_true.ctypes.data_as(_dp), int(seed), int(row_offset))
+        if not self._p:
+            raise B200Error("apop_b200_synth failed: " + abi.last_error())
+
+    @property
+    def ptr(self):
+        return self._p
+
+    def download(self):
+        """(X row-major, y) back on the host, in the reference's layout"""
+        X = np.zeros((self.n_rows, self.k))
+        y = np.zeros(self.n_rows) if self.has_y else None
+        abi.check(_lib().apop_b200_download(self._p, X.ctypes.data_as(_dp),
+                                            y.ctypes.data_as(_dp) if y is not None else None, None),
+                  "apop_b200_download")
+        return X, y
+
+    def free(self):
+        if self._p:
+            _lib().apop_b200_synth_free(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def synth(family, n_rows, k, beta_true, ncat=2, seed=8, row_offset=0):
+    return SynthData(family, n_rows, k, beta_true, ncat, seed, row_offset)
+
+
+# ---- multi-GPU plumbing: torch.distributed carries the NCCL id ----------------------
+def comm_init_from_torch():
+    """Create the library's NCCL communicator over the ranks of the default
+    torch.distributed process group (one process per GPU)."""
+    import torch
+    import torch.distributed as dist
+    lib = _lib()
+    rank, world = dist.get_rank(), dist.get_world_size()
+    buf = (C.c_char * 128)()
+    if rank == 0:
+        abi.check(lib.apop_b200_comm_unique_id(C.cast(buf, C.c_void_p)), "apop_b200_comm_unique_id")
+    t = torch.tensor(list(bytes(buf)), dtype=torch.uint8)
+    if dist.get_backend() == "nccl":
+        t = t.cuda()
+    dist.broadcast(t, src=0)
+    raw = bytes(t.cpu().tolist())
+    buf2 = (C.c_char * 128).from_buffer_copy(raw)
+    abi.check(lib.apop_b200_comm_init(world, rank, C.cast(buf2, C.c_void_p)), "apop_b200_comm_init")
+
+
+def comm_finalize():
+    _lib().apop_b200_comm_finalize()

@@ -1,0 +1,125 @@
+// cells.cu -- apop_map_sum / apop_matrix_sum shaped reductions over every cell
+// of a resident data set (apop_mapply.m4.c:485-517, apop_stats.m4.c:15,310).
+//
+// One pass returns, separately for the matrix cells and the vector cells,
+//   s0 = sum f0(x)   s1 = sum f1(x)   and a count of cells mapped to -inf,
+// which is what the iid models need: Normal wants sum (x-mu) and sum (x-mu)^2
+// (model/apop_normal.c:38-50,108-118), Poisson wants sum x and sum lgamma(x+1)
+// with its validity test (model/apop_poisson.c:14-28,66-73).
+// Bound: HBM (8 bytes per cell, read once).
+#include "cells.cuh"
+
+namespace apb {
+
+template <int MODE>
+__device__ __forceinline__ void cell_eval(double x, double p0, double& f0, double& f1, int& bad) {
+    if (MODE == CELLS_NORMAL) {
+        const double d = x - p0;
+        f0 = d;
+        f1 = d * d;
+    } else if (MODE == CELLS_POISSON) {
+        // apply_me: -inf for negative or non-integer cells (fractional part > 1e-4)
+        const bool invalid = (x < 0.0) || ((x - (double)(int)x) > 1e-4);
+        bad += invalid ? 1 : 0;
+        f0 = x;                                   // ln(lambda) * x summed as ln(lambda) * sum x
+        f1 = (x == 0.0 || invalid) ? 0.0 : lgamma(x + 1.0);
+    } else if (MODE == CELLS_IDENTITY) {
+        f0 = x; f1 = 0.0;
+    } else if (MODE == CELLS_LOG) {
+        f0 = log(x); f1 = 0.0;
+    } else {  // CELLS_EXP
+        f0 = exp(x); f1 = 0.0;
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(CELLS_THREADS)
+cells_kernel(const double* __restrict__ tiles, unsigned long long n_rows, unsigned long long n_tiles,
+             int k, int ycol, int cols, double p0, double* __restrict__ partials,
+             unsigned int* __restrict__ ticket, double* __restrict__ out) {
+    constexpr int WARPS = CELLS_THREADS / 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned long long gwarp = (unsigned long long)blockIdx.x * WARPS + warp;
+    const unsigned long long nwarps = (unsigned long long)gridDim.x * WARPS;
+    KSum m0, m1, v0, v1;
+    int bad = 0;
+    for (unsigned long long t = gwarp; t < n_tiles; t += nwarps) {
+        const double* base = tiles + t * (unsigned long long)cols * TILE_ROWS + lane;
+        const bool valid = t * TILE_ROWS + lane < n_rows;
+        int j = 0;
+        for (; j + 8 <= k; j += 8) {
+            double x[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) x[u] = ld_stream(base + (j + u) * TILE_ROWS);
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                double f0, f1; int b = 0;
+                cell_eval<MODE>(x[u], p0, f0, f1, b);
+                if (valid) { m0.add(f0); m1.add(f1); bad += b; }
+            }
+        }
+        for (; j < k; j++) {
+            double f0, f1; int b = 0;
+            cell_eval<MODE>(ld_stream(base + j * TILE_ROWS), p0, f0, f1, b);
+            if (valid) { m0.add(f0); m1.add(f1); bad += b; }
+        }
+        if (ycol >= 0) {
+            double f0, f1; int b = 0;
+            cell_eval<MODE>(ld_stream(base + ycol * TILE_ROWS), p0, f0, f1, b);
+            if (valid) { v0.add(f0); v1.add(f1); bad += b; }
+        }
+    }
+    __shared__ double red[WARPS][CELLS_NOUT];
+    double vals[CELLS_NOUT] = {m0.value(), m1.value(), v0.value(), v1.value(), (double)bad};
+#pragma unroll
+    for (int a = 0; a < CELLS_NOUT; a++) {
+        const double v = warp_sum(vals[a]);
+        if (lane == 0) red[warp][a] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < CELLS_NOUT) {
+        double s = 0.0;
+#pragma unroll
+        for (int wv = 0; wv < WARPS; wv++) s += red[wv][threadIdx.x];
+        partials[(size_t)blockIdx.x * CELLS_NOUT + threadIdx.x] = s;
+    }
+    __shared__ unsigned int is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if (threadIdx.x < CELLS_NOUT) {
+        double s = 0.0, c = 0.0;
+        for (unsigned b = 0; b < gridDim.x; b++) {
+            double e;
+            two_sum(s, __ldcg(partials + (size_t)b * CELLS_NOUT + threadIdx.x), s, e);
+            c += e;
+        }
+        out[threadIdx.x] = s + c;
+    }
+    if (threadIdx.x == 0) *ticket = 0;
+}
+
+cudaError_t cells_launch(int mode, const double* tiles, size_t n_rows, size_t n_tiles, int k,
+                         int ycol, int cols, double p0, double* partials, unsigned int* ticket,
+                         double* out, int grid, cudaStream_t st) {
+#define APB_CELLS(M)                                                                          \
+    case M:                                                                                   \
+        cells_kernel<M><<<grid, CELLS_THREADS, 0, st>>>(tiles, n_rows, n_tiles, k, ycol,         \
+                                                        cols, p0, partials, ticket, out);     \
+        break;
+    switch (mode) {
+        APB_CELLS(CELLS_IDENTITY)
+        APB_CELLS(CELLS_NORMAL)
+        APB_CELLS(CELLS_POISSON)
+        APB_CELLS(CELLS_LOG)
+        APB_CELLS(CELLS_EXP)
+    default: return cudaErrorInvalidValue;
+    }
+#undef APB_CELLS
+    return cudaGetLastError();
+}
+
+}  // namespace apb

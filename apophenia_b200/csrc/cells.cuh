@@ -1,0 +1,13 @@
+// cells.cuh -- per-cell map/sum reductions (see cells.cu)
+#pragma once
+#include "common.cuh"
+#include <stddef.h>
+
+namespace apb {
+enum CellsMode { CELLS_IDENTITY = 0, CELLS_NORMAL = 1, CELLS_POISSON = 2, CELLS_LOG = 3, CELLS_EXP = 4 };
+constexpr int CELLS_THREADS = 256;
+constexpr int CELLS_NOUT = 5;  // matrix s0, s1; vector s0, s1; count of -inf cells
+cudaError_t cells_launch(int mode, const double* tiles, size_t n_rows, size_t n_tiles, int k,
+                         int ycol, int cols, double p0, double* partials, unsigned int* ticket,
+                         double* out, int grid, cudaStream_t st);
+}  // namespace apb

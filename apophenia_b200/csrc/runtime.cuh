@@ -1,0 +1,80 @@
+// runtime.cuh -- per-process device context of libapop_b200 (one process per GPU).
+#pragma once
+#include <cuda_runtime.h>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+#include "../../include/apop_b200.h"
+#include "glm_kernel.cuh"
+#include "cells.cuh"
+#include "layout.cuh"
+
+namespace apb {
+
+// A data set kept in HBM between optimizer iterations.
+struct Resident {
+    size_t n_rows = 0;
+    int k = 0;
+    bool has_y = false, has_w = false;
+    int cols = 0;           // k + has_y + has_w
+    size_t n_tiles = 0;
+    double* tiles = nullptr;
+    bool synthetic = false;
+    bool dirty = false;      // host copy changed: re-upload before next use
+    bool transient = false;  // uploaded for one call only
+    // beta-independent constants, computed on first use
+    bool have_lgamma_y = false;
+    double lgamma_y = 0.0;   // sum_i lgamma(y_i + 1)
+    bool have_poisson = false;
+    double pois[CELLS_NOUT];
+    // last evaluation (f then df at the same beta costs one pass)
+    bool memo_valid = false;
+    int memo_fam = -1;
+    std::vector<double> memo_beta, memo_out;
+    // resample multiplicities for the batched path
+    unsigned char* counts = nullptr;
+    size_t counts_m = 0;
+};
+
+struct NcclApi {
+    void* handle = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, struct NcclId, int) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+struct NcclId { char internal[128]; };
+
+struct Runtime {
+    bool ready = false;
+    int device = -1;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double* d_partials = nullptr;
+    size_t partials_cap = 0;  // doubles
+    unsigned int* d_ticket = nullptr;
+    double* d_out = nullptr;  // OUT_CAP doubles
+    double* h_out = nullptr;  // pinned
+    bool auto_pin = false;
+    std::unordered_map<const apop_data*, Resident*> reg;
+    // stats
+    unsigned long long launches = 0, n_passes = 0;
+    double last_ms = 0.0, total_ms = 0.0;
+    // multi-GPU
+    NcclApi nccl;
+    void* comm = nullptr;
+    int nranks = 1, rank = 0;
+    std::string err;
+};
+constexpr size_t OUT_CAP = 4096;
+
+Runtime& rt();
+std::recursive_mutex& rt_mutex();
+bool set_error(const char* fmt, ...);
+bool cuda_ok(cudaError_t e, const char* what);
+bool ensure_partials(size_t doubles);
+
+}  // namespace apb

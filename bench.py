@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""bench.py -- likelihood+score rows/s of the fused probit pass (FP64, % of HBM roofline).
+
+Contract: `python bench.py --gpus N --steps K --warmup W` prints ONE JSON line.
+A step is one fused log-likelihood + score pass over the resident data set (one
+optimizer evaluation: beta in, [LL | score] out, allreduced over ranks).
+
+  value   rows/s with X, y resident in HBM (the design point named by
+          BASELINE.json: the matrix stays resident between optimizer iterations)
+  e2e     the same pass driven through the reference-signature C-ABI entry
+          points (model->log_likelihood + the apop_score vtable entry) on a HOST
+          apop_data: beta goes host->device and [LL | score] device->host inside
+          the timed region every step; `e2e.cold` also reports the one-off pin
+          (full host->device copy of X and y + tiling) for the same data set.
+  roofline  algorithmic bytes N*(k+1)*8 per launch / CUDA-event kernel time,
+          against MEASURED_PEAKS.json hbm_gbs.
+  cpu_baseline  the restated reference CPU path (oracle/, structure-faithful:
+          materialised dgemm, OpenMP row map, serial long double sum, serial
+          score) timed on this box's host cores on a bounded row sample.
+
+`--impl reference` times that CPU path alone as the reference arm.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "probit likelihood+score rows/sec (FP64)"
+UNIT = "rows/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--rows", type=int, default=100_000_000, help="rows per GPU (weak scaling)")
+    ap.add_argument("--k", type=int, default=32)
+    ap.add_argument("--family", default="probit", choices=["probit", "logit", "poisson_reg", "ols"])
+    ap.add_argument("--cpu-rows", type=int, default=3_000_000, help="row sample of the CPU baseline")
+    ap.add_argument("--e2e-rows", type=int, default=0, help="rows of the host data set for e2e (0 = auto)")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons during the timed region"""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+FAM = {"probit": 0, "logit": 1, "poisson_reg": 5, "ols": 4}
+
+
+def cpu_reference_pass(o, X, y, beta, threads):
+    r = o.time_probit_ll_score(X, y, beta, threads)
+    return r
+
+
+def run_reference(args):
+    """the reference arm: restated CPU path, all host threads, bounded sample per step"""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as o
+    n, k = args.cpu_rows, args.k
+    rng = np.random.default_rng(8)
+    X = rng.uniform(-1, 1, (n, k)); X[:, 0] = 1.0
+    beta = rng.uniform(-1, 1, k)
+    y = (rng.standard_normal(n) > -(X @ beta)).astype(np.float64)
+    threads = o.max_threads()
+    for _ in range(max(args.warmup, 1)):
+        cpu_reference_pass(o, X[: n // 8], y[: n // 8], beta, threads)
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        cpu_reference_pass(o, X, y, beta * (1 + 1e-9 * s), threads)
+    dt = time.perf_counter() - t0
+    val = n * args.steps / dt
+    sample = f"{n} rows x {k} cols per step (probit, restated reference CPU path, gcc -O3 -fopenmp)"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": workload_config(args, args.gpus),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_config(args, world):
+    return {"workload": f"{args.family} fused LL+score pass, {args.rows} rows x {args.k} cols per GPU "
+                        f"(target 100M x 32 probit MLE of BASELINE.json north_star)",
+            "rows_per_gpu": args.rows, "k": args.k, "global_rows": args.rows * world,
+            "parallelism": f"row-sharded dp{world}, one NCCL allreduce of [LL|score] per pass",
+            "l2": "inputs (>= 26 GB per pass) far exceed the 126 MB L2; no flush needed"}
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import apophenia_b200 as ab
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ab.init(local)
+    if world > 1:
+        ab.comm_init_from_torch()
+
+    fam = FAM[args.family]
+    n, k = args.rows, args.k
+    rng = np.random.default_rng(8)
+    beta_true = rng.uniform(-1, 1, k)
+    if args.family == "poisson_reg":
+        beta_true /= np.sqrt(k)
+    data = ab.synth(fam, n, k, beta_true, seed=8, row_offset=rank * n)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(i):
+        # a new beta every step (an optimizer never evaluates the same point twice)
+        b = beta_true * (1.0 + 1e-6 * (i + 1))
+        return ab.ll_score(fam, data, b)
+
+    for i in range(args.warmup):
+        step(-i - 2)
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    ab.pass_timer_reset()
+    launches0 = ab.launch_count()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        ll, g = step(i)
+    barrier()
+    dt = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    kern_ms, n_pass = ab.pass_timer()
+    launches = ab.launch_count() - launches0
+    assert np.isfinite(ll) and np.all(np.isfinite(g)), "non-finite result"
+    if dist is not None:
+        t = torch.tensor([dt, kern_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt, kern_ms = float(t[0]), float(t[1])
+    value = n * world * args.steps / dt
+
+    # ---- roofline of the dominant kernel (the fused pass), CUDA events on its stream
+    peak, peak_src = measured_peak()
+    bytes_per_launch = n * (k + 1) * 8
+    kern_ms_avg = kern_ms / max(n_pass, 1)
+    achieved = bytes_per_launch / (kern_ms_avg * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "kernel": "glm_fused_kernel",
+                "kernel_ms": kern_ms_avg, "algorithmic_bytes_per_launch": bytes_per_launch,
+                "frac_of_nominal_8TBs": achieved / 8000.0}
+    prof = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(prof):
+        try:
+            tj = json.load(open(prof))
+            if tj.get("rows") == n and tj.get("k") == k:
+                roofline["traffic"] = tj.get("dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    # ---- e2e through the reference-signature entry points on a HOST apop_data
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(ab, args, fam, beta_true, world, rank, barrier, dist, torch)
+
+    # ---- CPU baseline on rank 0
+    cpu = None
+    if rank == 0 and not args.no_cpu and args.family == "probit":
+        cpu = run_cpu_baseline(ab, args, fam, beta_true)
+
+    if rank == 0:
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+               "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+               "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic (device Philox, seed 8)",
+               "config": workload_config(args, world), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+               "gpu_launches": launches, "clocks": clocks, "impl": "b200"}
+        print(json.dumps(out))
+    data.free()
+    if dist is not None:
+        ab.comm_finalize()
+        dist.destroy_process_group()
+
+
+def run_e2e(ab, args, fam, beta_true, world, rank, barrier, dist, torch):
+    import psutil
+    k = args.k
+    n = args.e2e_rows or args.rows
+    need = n * (k + 1) * 8
+    avail = psutil.virtual_memory().available
+    if need * 2.5 > avail / max(world, 1):
+        n = int(avail / max(world, 1) / 2.5 / ((k + 1) * 8))
+    n = max(32, n // 32 * 32)
+    # host data set: the same synthetic recipe, generated on the device and copied back
+    src = ab.synth(fam, n, k, beta_true, seed=8, row_offset=rank * n)
+    X, y = src.download()
+    src.free()
+    d = ab.Data(matrix=X, vector=y)
+    barrier()
+    t0 = time.perf_counter()
+    ab.pin(d)                      # one-off: host->device copy of X, y + tiling
+    pin_s = time.perf_counter() - t0
+    mk = {0: ab.probit_model, 1: ab.logit_model}.get(fam, ab.vector_model)
+    for i in range(2):
+        m = mk(beta_true * (1 + 1e-7 * (i + 1)), d)
+        ab.log_likelihood(fam, d, m); ab.score(fam, d, m)
+    barrier()
+    steps = args.steps
+    t0 = time.perf_counter()
+    for i in range(steps):
+        m = mk(beta_true * (1.0 + 1e-6 * (i + 1)), d)
+        ll = ab.log_likelihood(fam, d, m)      # model->log_likelihood(d, m)
+        g = ab.score(fam, d, m)                # apop_score vtable entry (memo: same pass)
+    barrier()
+    dt = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([dt, pin_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt, pin_s = float(t[0]), float(t[1])
+    assert np.isfinite(ll) and np.all(np.isfinite(g))
+    ab.unpin(d)
+    return {"value": n * world * steps / dt, "unit": UNIT, "h2d_bytes_per_step": k * 8 + 32,
+            "d2h_bytes_per_step": (3 + k) * 8, "rows_per_gpu": n, "ms_per_step": 1e3 * dt / steps,
+            "api": "apop_b200_<family>_ll + apop_b200_<family>_score on a pinned host apop_data",
+            "cold": {"pin_seconds": pin_s, "h2d_bytes": n * (k + 1) * 8,
+                     "first_pass_rows_per_s": n * world / (pin_s + dt / steps)}}
+
+
+def run_cpu_baseline(ab, args, fam, beta_true):
+    from oracle import oracle as o
+    n, k = min(args.cpu_rows, args.rows), args.k
+    src = ab.synth(fam, n, k, beta_true, seed=8, row_offset=0)
+    X, y = src.download()
+    src.free()
+    threads = o.max_threads()
+    o.time_probit_ll_score(X[: n // 10], y[: n // 10], beta_true, threads)  # warm-up
+    best = None
+    t_total = 0.0
+    reps = 0
+    while reps < 3 and t_total < 30.0:
+        r = o.time_probit_ll_score(X, y, beta_true, threads)
+        t_total += r["seconds"]
+        reps += 1
+        if best is None or r["seconds"] < best["seconds"]:
+            best = r
+    return {"value": n / best["seconds"], "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{n} rows x {k} cols of the same synthetic recipe, best of {reps}; restated reference "
+                      f"CPU path (materialised dgemm, OpenMP row map, serial long double sum, serial score)",
+            "sec_ll": best["sec_ll"], "sec_score": best["sec_score"]}
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,234 @@
+/* apop_b200.h -- C-ABI of the B200-native likelihood/score hot path.
+ *
+ * This is the drop-in boundary: every entry point below has the exact signature
+ * the reference's own dispatch would bind for this path, so that a maintainer
+ * can install it into an unmodified libapophenia.
+ *
+ *   model->log_likelihood   long double (*)(apop_data*, apop_model*)      apop.m4.h:106
+ *   apop_score vtable entry void (*)(apop_data*, gsl_vector*, apop_model*) apop.m4.h:531
+ *
+ * No C++ or torch types cross this boundary: plain pointers and sizes only.
+ *
+ * When the real <apop.h> / GSL headers are available, compile with
+ * -DAPOP_B200_USE_SYSTEM_HEADERS and the structs come from there.  Otherwise
+ * the layouts are re-declared here bit-for-bit (public, ABI-stable layouts;
+ * apop.m4.h:61-115 and GSL's gsl_block/gsl_vector/gsl_matrix) and checked by
+ * static asserts in capi.cu.
+ */
+#ifndef APOP_B200_H
+#define APOP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifdef APOP_B200_USE_SYSTEM_HEADERS
+#include <apop.h>
+#else
+/* ---- GSL containers (gsl_block_double.h, gsl_vector_double.h, gsl_matrix_double.h) */
+typedef struct { size_t size; double *data; } gsl_block;
+typedef struct { size_t size; size_t stride; double *data; gsl_block *block; int owner; } gsl_vector;
+typedef struct { size_t size1; size_t size2; size_t tda; double *data; gsl_block *block; int owner; } gsl_matrix;
+typedef struct gsl_rng_s gsl_rng; /* opaque here */
+
+/* ---- apop_name (apop.m4.h:61-69) */
+typedef struct {
+    char *title;
+    char *vector;
+    char **col;
+    char **row;
+    char **text;
+    int colct, rowct, textct;
+    unsigned long *colhash, *rowhash, *texthash;
+} apop_name;
+
+/* ---- apop_data (apop.m4.h:72-81) */
+typedef struct apop_data {
+    gsl_vector *vector;
+    gsl_matrix *matrix;
+    apop_name *names;
+    char ***text;
+    size_t textsize[2];
+    gsl_vector *weights;
+    struct apop_data *more;
+    char error;
+} apop_data;
+
+/* ---- settings (apop.m4.h:85-91) */
+typedef struct {
+    char name[101];
+    unsigned long name_hash;
+    void *setting_group;
+    void *copy;
+    void *free;
+} apop_settings_type;
+
+/* ---- apop_model (apop.m4.h:94-115) */
+typedef struct apop_model apop_model;
+struct apop_model {
+    char name[101];
+    int vsize, msize1, msize2, dsize;
+    apop_data *data;
+    apop_data *parameters;
+    apop_data *info;
+    void (*estimate)(apop_data *data, apop_model *params);
+    long double (*p)(apop_data *d, apop_model *params);
+    long double (*log_likelihood)(apop_data *d, apop_model *params);
+    long double (*cdf)(apop_data *d, apop_model *params);
+    long double (*constraint)(apop_data *data, apop_model *params);
+    int (*draw)(double *out, gsl_rng *r, apop_model *params);
+    void (*prep)(apop_data *data, apop_model *params);
+    apop_settings_type *settings;
+    void *more;
+    size_t more_size;
+    char error;
+};
+
+/* vtable signature for the score (apop.m4.h:531-533) */
+typedef void (*apop_score_type)(apop_data *d, gsl_vector *gradient, apop_model *params);
+#define apop_score_hash(m1) ((size_t)((m1)->log_likelihood ? (m1)->log_likelihood : (m1)->p))
+#endif /* APOP_B200_USE_SYSTEM_HEADERS */
+
+/* ------------------------------------------------------------------ *
+ *  Model families served by this library
+ * ------------------------------------------------------------------ */
+typedef enum {
+    APOP_B200_PROBIT = 0,       /* binary probit            model/apop_probit.c:83-154  */
+    APOP_B200_LOGIT = 1,        /* multinomial logit        model/apop_probit.c:206-242 (+ analytic score, :244-289) */
+    APOP_B200_POISSON = 2,      /* iid Poisson(lambda)      model/apop_poisson.c:14-28,66-73 */
+    APOP_B200_NORMAL = 3,       /* iid Normal(mu,sigma)     model/apop_normal.c:38-50,108-118 */
+    APOP_B200_OLS = 4,          /* Gaussian-error OLS       model/apop_ols.c:129-205 */
+    APOP_B200_POISSON_REG = 5,  /* Poisson regression (new model, no reference counterpart) */
+    APOP_B200_MODEL_COUNT = 6
+} apop_b200_family;
+
+/* ------------------------------------------------------------------ *
+ *  Runtime
+ * ------------------------------------------------------------------ */
+/* Select the CUDA device this process drives (one process per GPU).  Returns 0
+ * on success; nonzero (and a message through apop_b200_last_error) if no
+ * sm_100 device is available.  There is no CPU fallback. */
+int apop_b200_init(int device);
+void apop_b200_finalize(void);
+const char *apop_b200_last_error(void);
+/* number of likelihood/score kernels launched since init (bench's gpu_launches) */
+unsigned long long apop_b200_launch_count(void);
+/* device milliseconds (CUDA events on the library stream) spent in the most
+ * recent fused pass, and the accumulated total and count since the last reset */
+double apop_b200_last_pass_ms(void);
+void apop_b200_pass_timer_reset(void);
+double apop_b200_pass_timer_total_ms(unsigned long long *n_passes);
+
+/* Multi-GPU: rows are sharded, one rank per process.  The 128-byte NCCL unique
+ * id is produced on rank 0 and carried to the other ranks by the host program
+ * (torch.distributed / MPI / a file); afterwards every ll/score call ends with
+ * one ncclAllReduce(sum, f64) of [LL | score] on the library stream.
+ * (No reference counterpart: the reference is single-process) */
+int apop_b200_comm_unique_id(void *id128);
+int apop_b200_comm_init(int nranks, int rank, const void *id128);
+int apop_b200_comm_finalize(void);
+int apop_b200_comm_size(void);
+
+/* ------------------------------------------------------------------ *
+ *  Residency: X, y (and weights) live in HBM between optimizer iterations
+ * ------------------------------------------------------------------ */
+/* Copy d->matrix / d->vector / d->weights to the device in the tiled layout
+ * described in DESIGN.md and remember it under the address of d.  Call after
+ * the model's prep (prep mutates the data: ols_shuffle, model/apop_ols.c:97). */
+int apop_b200_pin(apop_data *d);
+int apop_b200_unpin(apop_data *d);
+/* The host copy changed behind the same pointer (apop_bootstrap.m4.c:143-149):
+ * re-upload on next use. */
+int apop_b200_invalidate(apop_data *d);
+int apop_b200_is_pinned(const apop_data *d);
+/* unpinned data policy: 0 = upload per call and drop (always correct, default),
+ * 1 = pin on first sight and trust the caller to invalidate. */
+void apop_b200_set_auto_pin(int on);
+
+/* Synthetic, device-generated data sets in the resident layout (SURVEY 8(d),
+ * recipe of tests/test_apop.c:889-907).  The returned apop_data is a host
+ * header whose matrix/vector carry sizes but NULL data pointers; it is pinned.
+ * beta_true has k*(ncat-1) doubles in pack order.  Rows are numbered from
+ * row_offset so that shards of one global data set can be generated per rank.
+ * Free with apop_b200_synth_free. */
+apop_data *apop_b200_synth(apop_b200_family family, size_t n_rows, size_t k, int ncat,
+                           const double *beta_true, uint64_t seed, uint64_t row_offset);
+void apop_b200_synth_free(apop_data *d);
+/* Copy a resident data set back into caller-provided host buffers in the
+ * reference's layout (row-major X with tda = k; y; w may be NULL). */
+int apop_b200_download(const apop_data *d, double *X_rowmajor, double *y, double *w);
+
+/* ------------------------------------------------------------------ *
+ *  The path: log likelihood and score, reference signatures
+ * ------------------------------------------------------------------ */
+long double apop_b200_probit_ll(apop_data *d, apop_model *m);       /* replaces multiprobit_log_likelihood, model/apop_probit.c:104 */
+void apop_b200_probit_score(apop_data *d, gsl_vector *g, apop_model *m); /* replaces probit_dlog_likelihood, :130 */
+long double apop_b200_logit_ll(apop_data *d, apop_model *m);        /* replaces multilogit_log_likelihood, :231 */
+void apop_b200_logit_score(apop_data *d, gsl_vector *g, apop_model *m);  /* new (reference has it commented out, :244-289) */
+long double apop_b200_poisson_ll(apop_data *d, apop_model *m);      /* replaces poisson_log_likelihood, model/apop_poisson.c:21 */
+void apop_b200_poisson_score(apop_data *d, gsl_vector *g, apop_model *m); /* replaces poisson_dlog_likelihood, :66 */
+long double apop_b200_normal_ll(apop_data *d, apop_model *m);       /* replaces normal_log_likelihood, model/apop_normal.c:42 */
+void apop_b200_normal_score(apop_data *d, gsl_vector *g, apop_model *m);  /* replaces normal_dlog_likelihood, :108 */
+long double apop_b200_ols_ll(apop_data *d, apop_model *m);          /* replaces ols_log_likelihood, model/apop_ols.c:129 */
+void apop_b200_ols_score(apop_data *d, gsl_vector *g, apop_model *m);     /* replaces ols_score, :175 */
+long double apop_b200_poisson_reg_ll(apop_data *d, apop_model *m);  /* new model behind the same API */
+void apop_b200_poisson_reg_score(apop_data *d, gsl_vector *g, apop_model *m);
+
+/* Row reductions the models are built from (apop_map_sum / apop_matrix_sum,
+ * apop_mapply.m4.c:485, apop_stats.m4.c:15,310) over a resident data set:
+ * sum over every cell of vector+matrix of f(x; param). */
+typedef enum {
+    APOP_B200_MAP_IDENTITY = 0,    /* x                         (apop_matrix_sum)        */
+    APOP_B200_MAP_DEV = 1,         /* x - p0                    (normal apply_me)        */
+    APOP_B200_MAP_DEV2 = 2,        /* (x - p0)^2                (normal apply_me2)       */
+    APOP_B200_MAP_POISSON = 3,     /* x==0?0: p0*x - lgamma(x+1), -inf if invalid (poisson apply_me) */
+    APOP_B200_MAP_LOG = 4,         /* log(x)                                              */
+    APOP_B200_MAP_EXP = 5          /* exp(x)                                              */
+} apop_b200_map_fn;
+/* part: 'a' all (vector and matrix), 'v' vector only, 'm' matrix only */
+double apop_b200_map_sum(apop_data *d, apop_b200_map_fn fn, double p0, char part);
+
+/* OLS normal equations X'X (k*k, row-major) and X'y (k) in one pass
+ * (apop_estimate_OLS, model/apop_ols.c:333-334). */
+int apop_b200_ols_gram(apop_data *d, double *xtx, double *xty);
+
+/* Fused value+gradient in one call (what fdf_shell, apop_mle.m4.c:362, wants):
+ * beta in pack order (P doubles), score may be NULL. Returns LL. */
+double apop_b200_ll_score(apop_b200_family family, apop_data *d, const double *beta, size_t P,
+                          double *score);
+
+/* Observed information  -d2LL/dbeta dbeta' (P*P row-major) by one device pass
+ * (replaces the numeric Hessian, apop_mle.m4.c:187-223).  PROBIT, LOGIT(binary),
+ * POISSON_REG, OLS.  Returns 0 on success. */
+int apop_b200_information(apop_b200_family family, apop_data *d, const double *beta, size_t P,
+                          double *H);
+
+/* Batched parameter vectors (bootstrap replicates, parallel chains): B is
+ * P x m column-major-by-replicate (replicate r at B + r*P); counts is NULL or an
+ * n_rows x m row-major uint8 matrix of resample multiplicities already resident
+ * (see apop_b200_bootstrap_counts); ll has m, score has P*m (NULL to skip).
+ * (New entry; the unmodified callers are serial: apop_bootstrap.m4.c:143,
+ * apop_mcmc.m4.c:198.) */
+int apop_b200_ll_score_batched(apop_b200_family family, apop_data *d, const double *B, size_t P,
+                               size_t m, int use_counts, double *ll, double *score);
+/* draw m multinomial resamples of the rows into a resident n x m count matrix */
+int apop_b200_bootstrap_counts(apop_data *d, size_t m, uint64_t seed);
+
+/* ------------------------------------------------------------------ *
+ *  Installing into the reference's dispatch
+ * ------------------------------------------------------------------ */
+/* Sets model->log_likelihood to the device entry of `family` and registers the
+ * device score through apop_vtable_add("apop_score", fn, hash) -- the symbol is
+ * looked up in the running process (libapophenia, or this repo's host mirror).
+ * The model's own prep then finds the hash present and leaves it
+ * (apop_vtables.c:98). */
+int apop_b200_register(apop_model *model, apop_b200_family family);
+int apop_b200_unregister(apop_model *model);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

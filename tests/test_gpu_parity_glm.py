@@ -1,0 +1,219 @@
+"""Parity of the fused CUDA kernels with the oracle, through the C-ABI.
+
+Tolerances (BASELINE.json north_star): LL within 1e-12 relative of
+the oracle in exact (x87 long double) mode; score within 1e-12 * sum_i |X_ij d_i|
+per component.  The data cross the boundary as host `apop_data` structs.
+"""
+import numpy as np
+import pytest
+
+from conftest import gen_probit_logit_sample
+
+pytestmark = pytest.mark.gpu
+
+LL_RTOL = 1e-12
+SCORE_RTOL = 1e-12
+
+
+def _check_ll(got, want):
+    want = np.longdouble(want)
+    assert abs(np.longdouble(got) - want) <= LL_RTOL * abs(want) + 1e-300, (got, want)
+
+
+def _check_score(got, want, scale):
+    err = np.abs(np.asarray(got, dtype=np.longdouble) - want)
+    assert np.all(err <= SCORE_RTOL * scale + 1e-300), (err / scale).max()
+
+
+@pytest.mark.parametrize("n,k", [(80000, 8), (100003, 10), (31, 3), (32, 1), (33, 32), (50000, 32),
+                                 (20001, 16), (20000, 20), (20000, 24), (1, 5), (4097, 7)])
+def test_probit_ll_score(b200, oracle, n, k):
+    ab = b200
+    X, y, beta_true = gen_probit_logit_sample(n, k, seed=8 + n + k)
+    d = ab.pin(ab.Data(matrix=X, vector=y))
+    for beta in (beta_true, oracle.probit_start(X), np.zeros(k)):
+        m = ab.probit_model(beta, d)
+        launches = ab.launch_count()
+        ll = ab.log_likelihood(ab.PROBIT, d, m)
+        g = ab.score(ab.PROBIT, d, m)
+        assert ab.launch_count() == launches + 1  # f then df at the same beta: one fused pass
+        _check_ll(ll, oracle.probit_ll(X, y, beta, oracle.EXACT))
+        ge, scale = oracle.probit_score(X, y, beta, oracle.EXACT)
+        _check_score(g, ge, scale)
+        # and the gap to the reference's own operation order is the reference's rounding
+        gf, _ = oracle.probit_score(X, y, beta, oracle.FAITHFUL)
+        assert np.all(np.abs(g - gf) <= 1e-10 * scale + 1e-300)
+        assert abs(ll - float(oracle.probit_ll(X, y, beta, oracle.FAITHFUL))) <= 1e-11 * abs(ll) + 1e-300
+    ab.unpin(d)
+
+
+def test_probit_clamps_and_extremes(b200, oracle):
+    """rows that hit the 1e-10 clamps (model/apop_probit.c:85-86) and the cdf saturation"""
+    ab = b200
+    xb = np.array([-40.0, -38.0, -37.0, -20.0, -9.0, -8.3, -8.29, 0.0, 8.29, 8.3, 8.6, 9.0, 20.0, 37.0, 38.0, 40.0])
+    X = np.stack([np.ones(xb.size * 2), np.tile(xb, 2)], axis=1)
+    y = np.concatenate([np.zeros(xb.size), np.ones(xb.size)])
+    beta = np.array([0.0, 1.0])
+    d = ab.pin(ab.Data(matrix=X, vector=y))
+    m = ab.probit_model(beta, d)
+    ll = ab.log_likelihood(ab.PROBIT, d, m)
+    g = ab.score(ab.PROBIT, d, m)
+    want = oracle.probit_ll(X, y, beta, oracle.EXACT)
+    assert np.isfinite(ll)
+    assert abs(ll - float(want)) <= 1e-12 * abs(float(want))
+    ge, scale = oracle.probit_score(X, y, beta, oracle.EXACT)
+    _check_score(g, ge, scale)
+    ab.unpin(d)
+
+
+def test_probit_views_and_unpinned(b200, oracle):
+    """tda > size2 (matrix views), strided vector, unpinned upload-per-call, invalidate"""
+    ab = b200
+    X, y, beta = gen_probit_logit_sample(5000, 6, seed=3)
+    big = np.zeros((5000, 9)); big[:, 2:8] = X
+    ys = np.zeros(10000); ys[::2] = y
+    d = ab.Data(matrix=big[:, 2:8], vector=ys[::2])
+    assert d._m.tda == 9 and d._v.stride == 2
+    m = ab.probit_model(beta, d)
+    want = float(oracle.probit_ll(X, y, beta, oracle.EXACT))
+    assert not ab.is_pinned(d)
+    ll = ab.log_likelihood(ab.PROBIT, d, m)          # transient upload
+    assert abs(ll - want) <= 1e-12 * abs(want)
+    assert not ab.is_pinned(d)
+    ab.pin(d)
+    assert ab.is_pinned(d)
+    # the bootstrap hazard: same pointer, new contents
+    big[:, 2:8] = X[::-1]; ys[::2] = y[::-1]
+    ab.invalidate(d)
+    ll2 = ab.log_likelihood(ab.PROBIT, d, m)
+    want2 = float(oracle.probit_ll(X[::-1], y[::-1], beta, oracle.EXACT))
+    assert abs(ll2 - want2) <= 1e-12 * abs(want2)
+    ab.unpin(d)
+
+
+def test_error_conventions(b200):
+    """NaN from LL on NULL inputs, NaN-filled score, error char on the model"""
+    ab = b200
+    X, y, beta = gen_probit_logit_sample(100, 4, seed=5)
+    d = ab.Data(matrix=X, vector=y)
+    assert np.isnan(ab.log_likelihood(ab.PROBIT, None, ab.probit_model(beta)))
+    assert np.isnan(ab.log_likelihood(ab.PROBIT, d, None))
+    m_bad = ab.probit_model(np.ones(7), d)  # wrong parameter count
+    assert np.isnan(ab.log_likelihood(ab.PROBIT, d, m_bad))
+    assert m_bad.error == b"d"
+    assert np.all(np.isnan(ab.score(ab.PROBIT, d, m_bad)))
+    assert ab.last_error()
+
+
+@pytest.mark.parametrize("n,k", [(60000, 9), (1000, 2), (50001, 24)])
+def test_binary_logit(b200, oracle, n, k):
+    ab = b200
+    X, y, beta = gen_probit_logit_sample(n, k, seed=n + k, method="logit")
+    d = ab.pin(ab.Data(matrix=X, vector=y))
+    for b in (beta, 3 * beta, np.zeros(k)):
+        m = ab.logit_model(b, d)
+        _check_ll(ab.log_likelihood(ab.LOGIT, d, m), oracle.logit_ll(X, y, b, mode=oracle.EXACT))
+        ge, scale = oracle.logit_score(X, y, b, mode=oracle.EXACT)
+        _check_score(ab.score(ab.LOGIT, d, m), ge, scale)
+    ab.unpin(d)
+
+
+@pytest.mark.parametrize("n,k", [(40000, 16), (999, 3)])
+def test_poisson_regression(b200, oracle, n, k):
+    ab = b200
+    rng = np.random.default_rng(n)
+    X = rng.uniform(-1, 1, (n, k)); X[:, 0] = 1
+    beta = rng.uniform(-1, 1, k) / np.sqrt(k)
+    y = rng.poisson(np.exp(X @ beta)).astype(float)
+    d = ab.pin(ab.Data(matrix=X, vector=y))
+    for b in (beta, np.zeros(k)):
+        m = ab.vector_model(b, d)
+        _check_ll(ab.log_likelihood(ab.POISSON_REG, d, m), oracle.poisson_reg_ll(X, y, b, oracle.EXACT))
+        ge, scale = oracle.poisson_reg_score(X, y, b, oracle.EXACT)
+        _check_score(ab.score(ab.POISSON_REG, d, m), ge, scale)
+    ab.unpin(d)
+
+
+@pytest.mark.parametrize("weights", [False, True])
+def test_ols(b200, oracle, weights):
+    ab = b200
+    rng = np.random.default_rng(11)
+    n, k = 30007, 12
+    X = rng.uniform(-1, 1, (n, k)); X[:, 0] = 1
+    beta = rng.uniform(-1, 1, k)
+    y = X @ beta + rng.standard_normal(n)
+    w = rng.uniform(0.5, 2.0, n) if weights else None
+    d = ab.pin(ab.Data(matrix=X, vector=y, weights=w))
+    for b in (beta, beta + 0.1):
+        m = ab.vector_model(b, d)
+        want = oracle.ols_ll(X, y, b, w, oracle.EXACT)
+        _check_ll(ab.log_likelihood(ab.OLS, d, m), want)
+        ge, scale = oracle.ols_score(X, y, b, w, oracle.EXACT)
+        _check_score(ab.score(ab.OLS, d, m), ge, scale)
+        # the reference's own form (exp then log) agrees to its rounding
+        wf = float(oracle.ols_ll(X, y, b, w, oracle.FAITHFUL))
+        assert abs(float(want) - wf) <= 1e-10 * abs(wf)
+    ab.unpin(d)
+
+
+def test_iid_normal_and_poisson(b200, oracle):
+    ab = b200
+    rng = np.random.default_rng(5)
+    M = rng.normal(3.0, 2.0, (20011, 7)); v = rng.normal(3.0, 2.0, 20011)
+    for mat, vec in ((M, None), (None, v), (M, v)):
+        d = ab.pin(ab.Data(matrix=mat, vector=vec))
+        m = ab.vector_model([2.9, 2.1], d)
+        _check_ll(ab.log_likelihood(ab.NORMAL, d, m), oracle.normal_ll(vec, mat, 2.9, 2.1, oracle.EXACT))
+        g = ab.score(ab.NORMAL, d, m)
+        ge = oracle.normal_score(vec, mat, 2.9, 2.1, oracle.EXACT)
+        assert np.all(np.abs(g - ge) <= 1e-12 * np.maximum(np.abs(ge), 1e3))
+        ab.unpin(d)
+    P = rng.poisson(3.1, (30001, 5)).astype(float); pv = rng.poisson(3.1, 30001).astype(float)
+    for mat, vec in ((P, None), (P, pv)):
+        d = ab.pin(ab.Data(matrix=mat, vector=vec))
+        m = ab.vector_model([3.05], d)
+        _check_ll(ab.log_likelihood(ab.POISSON, d, m), oracle.poisson_ll(vec, mat, 3.05, oracle.EXACT))
+        _check_ll(ab.log_likelihood(ab.POISSON, d, m), oracle.poisson_ll(vec, mat, 3.05, oracle.FAITHFUL) * (1 + 0))
+        g = ab.score(ab.POISSON, d, m)
+        ge = oracle.poisson_score(vec, mat, 3.05, oracle.EXACT)
+        assert abs(g[0] - float(ge[0])) <= 1e-12 * abs(float(ge[0])) + 1e-6
+        ab.unpin(d)
+    # invalid cells give -inf ("look elsewhere", model/apop_poisson.c:15-16)
+    bad = P.copy(); bad[17, 2] = 2.5
+    d = ab.pin(ab.Data(matrix=bad))
+    assert ab.log_likelihood(ab.POISSON, d, ab.vector_model([3.0], d)) == -np.inf
+    ab.unpin(d)
+
+
+def test_map_sum(b200, oracle):
+    """apop_map_sum small exact cases (tests/test_apop.c:1037-1044 style) and big ones"""
+    ab = b200
+    M = np.arange(1.0, 13.0).reshape(4, 3); v = np.array([1.0, 2.0, 3.0, 4.0])
+    d = ab.pin(ab.Data(matrix=M, vector=v))
+    assert ab.map_sum(d, ab.MAP_IDENTITY) == 78 + 10
+    assert ab.map_sum(d, ab.MAP_IDENTITY, part="m") == 78
+    assert ab.map_sum(d, ab.MAP_IDENTITY, part="v") == 10
+    assert ab.map_sum(d, ab.MAP_DEV2, 1.0, part="v") == 0 + 1 + 4 + 9
+    assert abs(ab.map_sum(d, ab.MAP_LOG) - float(oracle.map_sum(v, M, 4))) < 1e-12
+    assert abs(ab.map_sum(d, ab.MAP_EXP) - float(oracle.map_sum(v, M, 5))) < 1e-12 * float(oracle.map_sum(v, M, 5))
+    ab.unpin(d)
+
+
+def test_synth_download_roundtrip_and_parity(b200, oracle):
+    """device-generated data (bench input) read back equals what the kernels saw"""
+    ab = b200
+    k = 10
+    beta = np.linspace(-0.9, 0.9, k)
+    s = ab.synth(ab.PROBIT, 100003, k, beta, seed=8)
+    X, y = s.download()
+    assert np.all(X[:, 0] == 1.0) and np.all(np.abs(X[:, 1:]) < 1) and set(np.unique(y)) <= {0.0, 1.0}
+    assert abs(X[:, 1:].mean()) < 0.01 and 0.2 < y.mean() < 0.8
+    ll, g = ab.ll_score(ab.PROBIT, s, beta)
+    _check_ll(ll, oracle.probit_ll(X, y, beta, oracle.EXACT))
+    ge, scale = oracle.probit_score(X, y, beta, oracle.EXACT)
+    _check_score(g, ge, scale)
+    # sharded generation reproduces the same global data set
+    s2 = ab.synth(ab.PROBIT, 50003, k, beta, seed=8, row_offset=50000)
+    X2, y2 = s2.download()
+    assert np.array_equal(X2, X[50000:]) and np.array_equal(y2, y[50000:])
+    s.free(); s2.free()
