@@ -4,6 +4,7 @@
 // There is no CPU fallback anywhere in this file: without a B200 every entry
 // point fails loudly (NaN + apop_b200_last_error).
 #include "runtime.cuh"
+#include "logit_kernel.cuh"
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -594,6 +595,48 @@ extern "C" void apop_b200_probit_score(apop_data* d, gsl_vector* g, apop_model* 
     release(e.r);
 }
 
+// One fused multinomial-logit pass; out = [LL | G in pack order (j*(C-1)+c)], all ranks summed.
+static bool eval_logit(Resident* r, const std::vector<double>& B, size_t C1, const std::vector<double>& cats,
+                       std::vector<double>& out) {
+    Runtime& R = rt();
+    const int K = r->k;
+    if (B.size() != (size_t)K * C1) return set_error("parameters are %zu doubles; the data has %d columns x %zu free categories", B.size(), K, C1);
+    if (K < 1 || K > MAX_K_REG) return set_error("k = %d columns: the fused kernels cover 1..%d", K, MAX_K_REG);
+    if (C1 < 2 || C1 > (size_t)LOGIT_MAX_C1) return set_error("%zu outcome categories: the multinomial kernel covers 3..%d", C1 + 1, LOGIT_MAX_C1 + 1);
+    if (!r->has_y || r->has_w) return set_error("logit needs an outcome vector and no weights column");
+    std::vector<double> key(B);
+    key.insert(key.end(), cats.begin(), cats.end());
+    if (r->memo_valid && r->memo_fam == 200 + (int)C1 && r->memo_beta.size() == key.size() &&
+        memcmp(r->memo_beta.data(), key.data(), key.size() * sizeof(double)) == 0) {
+        out = r->memo_out;
+        return true;
+    }
+    static int bps_cache[MAX_K_REG + 1][LOGIT_MAX_C1 + 1];
+    int& bps = bps_cache[K][C1];
+    if (!bps) bps = logit_blocks_per_sm(K, (int)C1);
+    if (bps <= 0) return set_error("multinomial logit kernel unavailable for k=%d, C=%zu", K, C1 + 1);
+    const int KB = logit_kb(K);
+    const int NOUT = 1 + KB * (int)C1;
+    LogitLaunch L;
+    L.tiles = r->tiles; L.n_rows = r->n_rows; L.n_tiles = r->n_tiles; L.k = K;
+    L.grid = grid_for(bps, r->n_tiles, LOGIT_THREADS / 32);
+    if (!ensure_partials((size_t)L.grid * NOUT)) return false;
+    L.partials = R.d_partials; L.ticket = R.d_ticket; L.out = R.d_out; L.stream = R.stream;
+    LogitParams prm;
+    memset(&prm, 0, sizeof prm);
+    memcpy(prm.B, B.data(), B.size() * sizeof(double));
+    for (size_t c = 0; c < C1 && c < 8; c++) prm.cats[c] = cats[c];
+    time_begin();
+    if (!cuda_ok(logit_launch((int)C1, L, prm), "logit kernel launch")) return false;
+    time_end_record();
+    R.launches++;
+    if (!reduce_and_fetch(NOUT)) return false;
+    time_collect();
+    out.assign(R.h_out, R.h_out + 1 + (size_t)K * C1);
+    r->memo_valid = true; r->memo_fam = 200 + (int)C1; r->memo_beta = key; r->memo_out = out;
+    return true;
+}
+
 static bool logit_categories(apop_data* d, apop_model* m, size_t C, std::vector<double>& cats) {
     const apop_data* pg = category_page(m && m->data ? m->data : d);
     if (!pg) pg = category_page(d);
@@ -617,9 +660,14 @@ extern "C" long double apop_b200_logit_ll(apop_data* d, apop_model* m) {
         release(e.r);
         return ll;
     }
-    set_error("multinomial logit kernel: C = %zu not built yet", C1 + 1);
-    m->error = 'd';
-    return NAN;
+    std::vector<double> B, out;
+    pack_parameters(m->parameters, B);
+    Resident* r = acquire(d);
+    if (!r) { d->error = 'a'; return NAN; }
+    const bool ok = eval_logit(r, B, C1, cats, out);
+    release(r);
+    if (!ok) { m->error = 'd'; return NAN; }
+    return (long double)out[0];
 }
 extern "C" void apop_b200_logit_score(apop_data* d, gsl_vector* g, apop_model* m) {
     LOCK;
@@ -636,8 +684,14 @@ extern "C" void apop_b200_logit_score(apop_data* d, gsl_vector* g, apop_model* m
         release(e.r);
         return;
     }
-    set_error("multinomial logit kernel: C = %zu not built yet", C1 + 1);
-    fill_nan(g);
+    std::vector<double> B, out;
+    pack_parameters(m->parameters, B);
+    Resident* r = acquire(d);
+    if (!r) { fill_nan(g); return; }
+    const bool ok = eval_logit(r, B, C1, cats, out);
+    release(r);
+    if (ok) store_score(g, out.data() + 1, B.size(), 1.0);
+    else { m->error = 'd'; fill_nan(g); }
 }
 
 // sum_i lgamma(y_i + 1): beta-independent, one pass per residency

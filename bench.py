@@ -40,8 +40,8 @@ UNIT = "rows/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--rows", type=int, default=100_000_000, help="rows per GPU (weak scaling)")
     ap.add_argument("--k", type=int, default=32)
@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--e2e-rows", type=int, default=0, help="rows of the host data set for e2e (0 = auto)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-fit", action="store_true")
     return ap.parse_args()
 
 
@@ -64,53 +65,46 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks and throttle reasons during the timed region"""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region (NVML in a thread,
+    every ~5 ms; the recipe's nvidia-smi line needs a process spawn per 100 ms sample)."""
 
     def __init__(self, index):
         self.index = index
-        self.proc = None
-        self.lines = []
+        self.sm, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self.t = None
+
+    def _run(self):
+        import pynvml as nv
+        try:
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            bits = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                    "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                    "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                    "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+            while not self._stop.is_set():
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for name, bit in bits.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                time.sleep(0.005)
+        except Exception as e:  # noqa: BLE001
+            self.reasons.add(f"nvml unavailable: {e}")
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 8:
-                continue
-            try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for nm, val in zip(names, f[4:8]):
-                if val.lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        self._stop.set()
+        if self.t:
+            self.t.join(timeout=2)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.sm)}
 
 
 FAM = {"probit": 0, "logit": 1, "poisson_reg": 5, "ols": 4}
@@ -200,7 +194,9 @@ def main():
 
     for i in range(args.warmup):
         step(-i - 2)
-    sampler = ClockSampler(local)
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    nvml_index = int(vis.split(",")[local]) if vis and vis.split(",")[local].isdigit() else local
+    sampler = ClockSampler(nvml_index)
     barrier()
     if rank == 0:
         sampler.start()
@@ -244,6 +240,11 @@ def main():
     if not args.no_e2e:
         e2e = run_e2e(ab, args, fam, beta_true, world, rank, barrier, dist, torch)
 
+    # ---- probit MLE time-to-fit on the resident data (same optimizer on every rank)
+    fit = None
+    if not args.no_fit and args.family == "probit":
+        fit = run_time_to_fit(ab, data, args, beta_true, barrier)
+
     # ---- CPU baseline on rank 0
     cpu = None
     if rank == 0 and not args.no_cpu and args.family == "probit":
@@ -254,7 +255,7 @@ def main():
                "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic (device Philox, seed 8)",
                "config": workload_config(args, world), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-               "gpu_launches": launches, "clocks": clocks, "impl": "b200"}
+               "gpu_launches": launches, "clocks": clocks, "impl": "b200", "time_to_fit": fit}
         print(json.dumps(out))
     data.free()
     if dist is not None:
@@ -304,6 +305,40 @@ def run_e2e(ab, args, fam, beta_true, world, rank, barrier, dist, torch):
             "api": "apop_b200_<family>_ll + apop_b200_<family>_score on a pinned host apop_data",
             "cold": {"pin_seconds": pin_s, "h2d_bytes": n * (k + 1) * 8,
                      "first_pass_rows_per_s": n * world / (pin_s + dt / steps)}}
+
+
+def run_time_to_fit(ab, data, args, beta_true, barrier):
+    """apop_maximum_likelihood (host mirror, csrc/mle.c) over the device entries installed by
+    apop_b200_register, from the probit_prep start point (exp(mean ln|x|): 1 for the ones
+    column, e^-1 for U(-1,1) columns), stop rule |gradient| < 1e-9 * |LL|."""
+    import ctypes as C
+    from apophenia_b200 import abi, host
+    h, lib = host.lib(), abi.load_library()
+    out = {}
+    k = args.k
+    start = np.full(k, np.exp(-1.0)); start[0] = 1.0
+    for method in ("BFGS cg", "Newton"):
+        m = h.apop_model_copy(host.model_object(abi.PROBIT))
+        abi.check(lib.apop_b200_register(m, abi.PROBIT), "apop_b200_register")
+        prm = h.apop_data_alloc(k, 1, 0)
+        m.contents.parameters = prm
+        m.contents.data = data.ptr
+        keep = []
+        host.mle_settings(m, method=method, tolerance=1e-9, relative_tolerance=True, max_iterations=200,
+                          starting_pt=start, keep=keep)
+        barrier()
+        t0 = time.perf_counter()
+        h.apop_maximum_likelihood(data.ptr, m)
+        barrier()
+        dt = time.perf_counter() - t0
+        rep = h.apop_mle_last_report()
+        est = host.parameters_of(m)
+        if rep.status != 0 and method == "Newton":
+            continue
+        out[method] = {"seconds": dt, "status": rep.status, "iterations": rep.iterations,
+                       "passes": rep.f_evals, "ll": rep.ll, "gradient_norm": rep.gradient_norm,
+                       "max_abs_err_vs_beta_true": float(np.max(np.abs(est - beta_true)))}
+    return out
 
 
 def run_cpu_baseline(ab, args, fam, beta_true):

@@ -1,0 +1,92 @@
+"""apop_estimate through the reference's own dispatch with the device entries registered:
+fitted parameters agree to 1e-8 relative with the same optimizer driven by the oracle
+(BASELINE.json north_star; SURVEY F9: compare two tight runs of one optimizer)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import gen_probit_logit_sample
+from test_host_mirror import _install_oracle_model, _np_vec
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def host():
+    from apophenia_b200 import host as h
+    h.lib()
+    return h
+
+
+def _fit_oracle(host, oracle, family, raw, **settings):
+    h = host.lib()
+    d = host.data_from_numpy(raw)
+    keep = []
+    m = _install_oracle_model(host, oracle, family, keep)
+    host.mle_settings(m, keep=keep, **settings)
+    est = h.apop_estimate(d, m)
+    rep = h.apop_mle_last_report()
+    out = host.parameters_of(est), rep.status, rep.iterations
+    h.apop_vtable_drop(b"apop_score", m.contents.log_likelihood)
+    return out
+
+
+@pytest.mark.parametrize("method", ["BFGS cg", "FR cg"])
+def test_probit_fit_matches_oracle_driven_fit(b200, host, oracle, method):
+    X, y, beta = gen_probit_logit_sample(60000, 6, seed=8)
+    raw = X.copy(); raw[:, 0] = y
+    settings = dict(method=method, tolerance=1e-7, max_iterations=500)
+    est, params, rep = host.estimate(b200.PROBIT, host.data_from_numpy(raw), **settings)
+    assert rep["status"] == 0
+    want, st, it = _fit_oracle(host, oracle, 0, raw, **settings)
+    assert st == 0
+    assert np.max(np.abs(params - want) / np.abs(want)) < 1e-8, (params, want)
+    assert np.linalg.norm(params - beta) < 0.07          # the reference's own recovery test
+    assert est.contents.info.contents.vector.contents.data[0] == 0
+
+
+def test_logit_fit_multinomial_and_newton(b200, host, oracle):
+    X, y, B = gen_probit_logit_sample(30000, 4, seed=3, method="logit", ncat=3)
+    raw = X.copy(); raw[:, 0] = y
+    settings = dict(method="BFGS cg", tolerance=1e-7, max_iterations=500)
+    est, params, rep = host.estimate(b200.LOGIT, host.data_from_numpy(raw), **settings)
+    assert rep["status"] == 0
+    want, st, it = _fit_oracle(host, oracle, 1, raw, **settings)
+    assert st == 0 and np.max(np.abs(params - want) / np.maximum(np.abs(want), 1e-3)) < 1e-7
+    assert np.linalg.norm(params.reshape(4, 2) - B) < 0.2
+
+
+def test_register_installs_and_restores(b200, host):
+    from apophenia_b200 import abi
+    h, lib = host.lib(), abi.load_library()
+    m = h.apop_model_copy(host.model_object(0))
+    assert not m.contents.log_likelihood
+    assert lib.apop_b200_register(m, 0) == 0
+    want = C.cast(lib.apop_b200_probit_ll, C.c_void_p).value
+    assert m.contents.log_likelihood == want
+    # the score is in the vtable under the new hash, and a second add is a no-op
+    assert h.apop_vtable_get(b"apop_score", want) == C.cast(lib.apop_b200_probit_score, C.c_void_p).value
+    h.apop_vtable_add(b"apop_score", C.c_void_p(0x1234), want)
+    assert h.apop_vtable_get(b"apop_score", want) != 0x1234
+    copy = h.apop_model_copy(m)                           # memcpy keeps fn pointers, hence the hash
+    assert copy.contents.log_likelihood == want
+    assert lib.apop_b200_unregister(m) == 0
+    assert not m.contents.log_likelihood
+    assert h.apop_vtable_get(b"apop_score", want) is None
+
+
+def test_metropolis_style_ll_only_calls(b200, oracle):
+    """apop_model_metropolis asks for one LL per step and never the score (apop_mcmc.m4.c:113)"""
+    ab = b200
+    X, y, beta = gen_probit_logit_sample(20000, 5, seed=7, method="logit")
+    d = ab.pin(ab.Data(matrix=X, vector=y))
+    rng = np.random.default_rng(0)
+    b = beta.copy()
+    for _ in range(5):
+        prop = b + 0.01 * rng.standard_normal(5)
+        ll = ab.log_likelihood(ab.LOGIT, d, ab.logit_model(prop, d))
+        want = float(oracle.logit_ll(X, y, prop, mode=oracle.EXACT))
+        assert abs(ll - want) <= 1e-12 * abs(want)
+        b = prop
+    ab.unpin(d)
