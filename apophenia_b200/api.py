@@ -17,7 +17,8 @@ __all__ = ["init", "finalize", "pin", "unpin", "invalidate", "is_pinned", "log_l
            "ll_score", "map_sum", "synth", "SynthData", "launch_count", "last_pass_ms", "pass_timer_reset",
            "pass_timer", "probit_model", "logit_model", "vector_model", "Data", "Model", "B200Error",
            "PROBIT", "LOGIT", "POISSON", "NORMAL", "OLS", "POISSON_REG", "comm_init_from_torch",
-           "comm_finalize", "set_auto_pin", "last_error", "information", "ols_gram"]
+           "comm_finalize", "set_auto_pin", "last_error", "information", "ols_gram",
+           "MAP_IDENTITY", "MAP_DEV", "MAP_DEV2", "MAP_POISSON", "MAP_LOG", "MAP_EXP"]
 
 _dp = C.POINTER(C.c_double)
 

@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--rows", type=int, default=100_000_000, help="rows per GPU (weak scaling)")
     ap.add_argument("--k", type=int, default=32)
     ap.add_argument("--family", default="probit", choices=["probit", "logit", "poisson_reg", "ols"])
+    ap.add_argument("--ncat", type=int, default=2, help="outcome categories (logit)")
     ap.add_argument("--cpu-rows", type=int, default=3_000_000, help="row sample of the CPU baseline")
     ap.add_argument("--e2e-rows", type=int, default=0, help="rows of the host data set for e2e (0 = auto)")
     ap.add_argument("--no-cpu", action="store_true")
@@ -146,7 +147,8 @@ def run_reference(args):
 
 
 def workload_config(args, world):
-    return {"workload": f"{args.family} fused LL+score pass, {args.rows} rows x {args.k} cols per GPU "
+    fam = args.family + (f" (C={args.ncat})" if args.family == "logit" else "")
+    return {"workload": f"{fam} fused LL+score pass, {args.rows} rows x {args.k} cols per GPU "
                         f"(target 100M x 32 probit MLE of BASELINE.json north_star)",
             "rows_per_gpu": args.rows, "k": args.k, "global_rows": args.rows * world,
             "parallelism": f"row-sharded dp{world}, one NCCL allreduce of [LL|score] per pass",
@@ -177,10 +179,10 @@ def main():
     fam = FAM[args.family]
     n, k = args.rows, args.k
     rng = np.random.default_rng(8)
-    beta_true = rng.uniform(-1, 1, k)
+    beta_true = rng.uniform(-1, 1, k * (args.ncat - 1) if args.family == "logit" else k)
     if args.family == "poisson_reg":
         beta_true /= np.sqrt(k)
-    data = ab.synth(fam, n, k, beta_true, seed=8, row_offset=rank * n)
+    data = ab.synth(fam, n, k, beta_true, ncat=args.ncat, seed=8, row_offset=rank * n)
 
     def barrier():
         if dist is not None:
@@ -223,7 +225,7 @@ def main():
     kern_ms_avg = kern_ms / max(n_pass, 1)
     achieved = bytes_per_launch / (kern_ms_avg * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "kernel": "glm_fused_kernel",
+                "traffic": None, "peak_source": peak_src, "kernel": "logit_fused_kernel" if (args.family == "logit" and args.ncat > 2) else "glm_fused_kernel",
                 "kernel_ms": kern_ms_avg, "algorithmic_bytes_per_launch": bytes_per_launch,
                 "frac_of_nominal_8TBs": achieved / 8000.0}
     prof = os.path.join(ROOT, "profiles", "traffic.json")
@@ -273,7 +275,7 @@ def run_e2e(ab, args, fam, beta_true, world, rank, barrier, dist, torch):
         n = int(avail / max(world, 1) / 2.5 / ((k + 1) * 8))
     n = max(32, n // 32 * 32)
     # host data set: the same synthetic recipe, generated on the device and copied back
-    src = ab.synth(fam, n, k, beta_true, seed=8, row_offset=rank * n)
+    src = ab.synth(fam, n, k, beta_true, ncat=args.ncat, seed=8, row_offset=rank * n)
     X, y = src.download()
     src.free()
     d = ab.Data(matrix=X, vector=y)
@@ -282,14 +284,15 @@ def run_e2e(ab, args, fam, beta_true, world, rank, barrier, dist, torch):
     ab.pin(d)                      # one-off: host->device copy of X, y + tiling
     pin_s = time.perf_counter() - t0
     mk = {0: ab.probit_model, 1: ab.logit_model}.get(fam, ab.vector_model)
+    shape = (lambda b: b.reshape(k, -1)) if fam == 1 else (lambda b: b)
     for i in range(2):
-        m = mk(beta_true * (1 + 1e-7 * (i + 1)), d)
+        m = mk(shape(beta_true * (1 + 1e-7 * (i + 1))), d)
         ab.log_likelihood(fam, d, m); ab.score(fam, d, m)
     barrier()
     steps = args.steps
     t0 = time.perf_counter()
     for i in range(steps):
-        m = mk(beta_true * (1.0 + 1e-6 * (i + 1)), d)
+        m = mk(shape(beta_true * (1.0 + 1e-6 * (i + 1))), d)
         ll = ab.log_likelihood(fam, d, m)      # model->log_likelihood(d, m)
         g = ab.score(fam, d, m)                # apop_score vtable entry (memo: same pass)
     barrier()
@@ -300,8 +303,8 @@ def run_e2e(ab, args, fam, beta_true, world, rank, barrier, dist, torch):
         dt, pin_s = float(t[0]), float(t[1])
     assert np.isfinite(ll) and np.all(np.isfinite(g))
     ab.unpin(d)
-    return {"value": n * world * steps / dt, "unit": UNIT, "h2d_bytes_per_step": k * 8 + 32,
-            "d2h_bytes_per_step": (3 + k) * 8, "rows_per_gpu": n, "ms_per_step": 1e3 * dt / steps,
+    return {"value": n * world * steps / dt, "unit": UNIT, "h2d_bytes_per_step": beta_true.size * 8 + 32,
+            "d2h_bytes_per_step": (3 + beta_true.size) * 8, "rows_per_gpu": n, "ms_per_step": 1e3 * dt / steps,
             "api": "apop_b200_<family>_ll + apop_b200_<family>_score on a pinned host apop_data",
             "cold": {"pin_seconds": pin_s, "h2d_bytes": n * (k + 1) * 8,
                      "first_pass_rows_per_s": n * world / (pin_s + dt / steps)}}
