@@ -18,6 +18,7 @@ __all__ = ["init", "finalize", "pin", "unpin", "invalidate", "is_pinned", "log_l
            "pass_timer", "probit_model", "logit_model", "vector_model", "Data", "Model", "B200Error",
            "PROBIT", "LOGIT", "POISSON", "NORMAL", "OLS", "POISSON_REG", "comm_init_from_torch",
            "comm_finalize", "set_auto_pin", "last_error", "information", "ols_gram",
+           "ll_score_batched", "bootstrap_counts", "counts_download",
            "MAP_IDENTITY", "MAP_DEV", "MAP_DEV2", "MAP_POISSON", "MAP_LOG", "MAP_EXP"]
 
 _dp = C.POINTER(C.c_double)
@@ -120,6 +121,32 @@ def information(family, d, beta):
     abi.check(_lib().apop_b200_information(int(family), _ptr(d), beta.ctypes.data_as(_dp), beta.size,
                                            H.ctypes.data_as(_dp)), "apop_b200_information")
     return H
+
+
+def ll_score_batched(family, d, B, use_counts=False, want_score=True):
+    """m parameter vectors in one pass (bootstrap replicates, parallel chains).
+    B is m x P (one parameter vector per row).  Returns (ll[m], score[m x P] or None)."""
+    B = np.ascontiguousarray(B, dtype=np.float64)
+    m, P = B.shape
+    ll = np.zeros(m)
+    g = np.zeros((m, P)) if want_score else None
+    abi.check(_lib().apop_b200_ll_score_batched(int(family), _ptr(d), B.ctypes.data_as(_dp), P, m, int(use_counts),
+                                                ll.ctypes.data_as(_dp),
+                                                g.ctypes.data_as(_dp) if want_score else None),
+              "apop_b200_ll_score_batched")
+    return ll, g
+
+
+def bootstrap_counts(d, m, seed=8):
+    """draw m multinomial resamples of the rows into a resident count matrix"""
+    abi.check(_lib().apop_b200_bootstrap_counts(_ptr(d), int(m), int(seed)), "apop_b200_bootstrap_counts")
+
+
+def counts_download(d, m, n_rows):
+    out = np.zeros((n_rows, m), dtype=np.uint8)
+    abi.check(_lib().apop_b200_counts_download(_ptr(d), int(m), out.ctypes.data_as(C.POINTER(C.c_ubyte))),
+              "apop_b200_counts_download")
+    return out
 
 
 def ols_gram(d):

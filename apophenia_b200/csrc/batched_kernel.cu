@@ -1,0 +1,254 @@
+// batched_kernel.cu -- many parameter vectors per pass (bootstrap replicates, parallel
+// MCMC chains): X.[beta_1 .. beta_m] is a real dense FP64 contraction and runs on the
+// tensor-core path, mma.sync.aligned.m8n8k4 f64 (SASS: DMMA.8x8x4; tcgen05 has no FP64 kind).
+//
+// For a 32-row tile and a group of 16 replicates per warp:
+//   stage 1  S^T[rep][row] = B^T[rep][j] . X^T[j][row]       (DMMA, K = columns)
+//            A fragments (B^T) are loop invariant and live in registers;
+//            B fragments (X^T) come straight from the resident tile: lane (g = lane/4,
+//            q = lane%4) of block (kb, nb) reads column kb*4+q, row nb*8+g.
+//   stage 2  per element: link/density and score multiplier of the family, times the
+//            resample multiplicity c[row][rep] (bootstrap) -- the FP64-pipe bulk of the
+//            kernel (N*m special-function evaluations);
+//   stage 3  G^T[rep][j] += D^T[rep][row] . X[row][j]          (DMMA, K = rows)
+//            The C fragment of stage 1 holds, per lane, rows nb*8 + 2q + {0,1} of replicate
+//            g: exactly an A fragment if the four contraction slots are taken to be rows
+//            {2q+e}, so the X operand is loaded with the same row permutation (one 16-byte
+//            load gives e = 0,1) and no shuffle or shared-memory transpose is needed.
+// All 8 warps of a CTA work on the same tile (L1-resident, 8(k+1)*32 bytes) for 8
+// different replicate groups, so X is re-read from L2/HBM only m/128 times per pass.
+// Reference: the serial loops this replaces are apop_bootstrap.m4.c:143-159 (resample
+// + full fit per replicate) and apop_mcmc.m4.c:198-210 (one LL per step, one chain).
+#include "batched_kernel.cuh"
+#include "families.cuh"
+
+namespace apb {
+
+__device__ __forceinline__ void dmma_8x8x4(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+
+// position of row r (0..31) of a tile inside a replicate's 32-byte count record:
+// lane q = (r%8)/2 owns bytes q*8 .. q*8+7, ordered (nb = r/8, e = r%2)
+__host__ __device__ __forceinline__ int count_pos(int r) { return ((r & 7) >> 1) * 8 + (r >> 3) * 2 + (r & 1); }
+
+template <int KB, class Fam, bool WANT_SCORE, bool USE_COUNTS>
+__global__ void __launch_bounds__(BATCH_THREADS, 1)
+batched_kernel(const double* __restrict__ tiles, const unsigned long long n_rows, const unsigned long long n_tiles,
+               const int K, const int cols, const double* __restrict__ Bmat, const int P, const int m,
+               const unsigned char* __restrict__ counts, const int m_pad, const double4 aux4,
+               const int n_rowgroups, double* __restrict__ partials) {
+    constexpr int WARPS = BATCH_THREADS / 32;
+    constexpr int MB = BATCH_RC / 8;   // replicate blocks of 8 per warp
+    constexpr int KS = KB / 4;         // stage-1 k-steps
+    constexpr int JB = KB / 8;         // stage-3 column blocks
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, q = lane & 3;
+    const int n_repgroups = (m + WARPS * BATCH_RC - 1) / (WARPS * BATCH_RC);
+    const int repgroup = blockIdx.x % n_repgroups;
+    const int rowgroup = blockIdx.x / n_repgroups;
+    if (rowgroup >= n_rowgroups) return;
+    const int rep0 = (repgroup * WARPS + warp) * BATCH_RC;   // first replicate of this warp
+    const double aux[4] = {aux4.x, aux4.y, aux4.z, aux4.w};
+
+    // loop-invariant A fragments of stage 1: B^T[rep0 + mb*8 + g][ks*4 + q]
+    double bfrag[MB][KS];
+#pragma unroll
+    for (int mb = 0; mb < MB; mb++)
+#pragma unroll
+        for (int ks = 0; ks < KS; ks++) {
+            const int rep = rep0 + mb * 8 + g, j = ks * 4 + q;
+            bfrag[mb][ks] = (rep < m && j < K) ? Bmat[(size_t)rep * P + j] : 0.0;
+        }
+
+    double G[MB][JB][2];   // G^T[rep = mb*8+g][j = jb*8 + 2q + {0,1}]
+#pragma unroll
+    for (int mb = 0; mb < MB; mb++)
+#pragma unroll
+        for (int jb = 0; jb < JB; jb++) G[mb][jb][0] = G[mb][jb][1] = 0.0;
+    KSum ll[MB];
+
+    for (unsigned long long t = rowgroup; t < n_tiles; t += n_rowgroups) {
+        const double* tile = tiles + t * (unsigned long long)(cols * TILE_ROWS);
+        // ---- stage 1: S^T = B^T X^T
+        double S[MB][4][2];
+#pragma unroll
+        for (int mb = 0; mb < MB; mb++)
+#pragma unroll
+            for (int nb = 0; nb < 4; nb++) S[mb][nb][0] = S[mb][nb][1] = 0.0;
+#pragma unroll
+        for (int ks = 0; ks < KS; ks++) {
+            const int j = ks * 4 + q;
+            double xf[4];
+#pragma unroll
+            for (int nb = 0; nb < 4; nb++) xf[nb] = (j < K) ? __ldg(tile + j * TILE_ROWS + nb * 8 + g) : 0.0;
+#pragma unroll
+            for (int mb = 0; mb < MB; mb++)
+#pragma unroll
+                for (int nb = 0; nb < 4; nb++) dmma_8x8x4(S[mb][nb][0], S[mb][nb][1], bfrag[mb][ks], xf[nb]);
+        }
+        // ---- stage 2: link/density per (row, replicate); this lane owns rows nb*8+2q+e, replicates mb*8+g
+        double yv[4][2];
+#pragma unroll
+        for (int nb = 0; nb < 4; nb++) {
+            const double2 y2 = __ldg(reinterpret_cast<const double2*>(tile + K * TILE_ROWS + nb * 8 + 2 * q));
+            yv[nb][0] = y2.x; yv[nb][1] = y2.y;
+        }
+#pragma unroll
+        for (int mb = 0; mb < MB; mb++) {
+            const int rep = rep0 + mb * 8 + g;
+            unsigned long long cbits = 0x0101010101010101ull;
+            if (USE_COUNTS)
+                cbits = (rep < m) ? __ldg(reinterpret_cast<const unsigned long long*>(
+                                        counts + (t * (unsigned long long)m_pad + rep) * TILE_ROWS + q * 8))
+                                  : 0ull;
+#pragma unroll
+            for (int nb = 0; nb < 4; nb++)
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const unsigned long long row = t * TILE_ROWS + nb * 8 + 2 * q + e;
+                    const double c = (row < n_rows) ? (double)((cbits >> (8 * (nb * 2 + e))) & 0xffull) : 0.0;
+                    const RowOut o = Fam::eval(S[mb][nb][e], yv[nb][e], 1.0, aux);
+                    ll[mb].add(c != 0.0 ? c * o.s[0] : 0.0);
+                    S[mb][nb][e] = c != 0.0 ? c * o.d : 0.0;   // S now holds D^T
+                }
+        }
+        // ---- stage 3: G^T += D^T X, contraction slots = rows nb*8 + 2q + e
+        if (WANT_SCORE) {
+#pragma unroll
+            for (int jb = 0; jb < JB; jb++) {
+                const int j = jb * 8 + g;
+#pragma unroll
+                for (int nb = 0; nb < 4; nb++) {
+                    double2 x2 = make_double2(0.0, 0.0);
+                    if (j < K) x2 = __ldg(reinterpret_cast<const double2*>(tile + j * TILE_ROWS + nb * 8 + 2 * q));
+#pragma unroll
+                    for (int mb = 0; mb < MB; mb++) {
+                        dmma_8x8x4(G[mb][jb][0], G[mb][jb][1], S[mb][nb][0], x2.x);
+                        dmma_8x8x4(G[mb][jb][0], G[mb][jb][1], S[mb][nb][1], x2.y);
+                    }
+                }
+            }
+        }
+    }
+
+    // ---- per-CTA partials: [rowgroup][rep][1 + KB]
+    const int NOUT = 1 + KB;
+#pragma unroll
+    for (int mb = 0; mb < MB; mb++) {
+        const int rep = rep0 + mb * 8 + g;
+        double v = ll[mb].value();
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        if (rep < m) {
+            double* dst = partials + ((size_t)rowgroup * m + rep) * NOUT;
+            if (q == 0) dst[0] = v;
+            if (WANT_SCORE) {
+#pragma unroll
+                for (int jb = 0; jb < JB; jb++) {
+                    dst[1 + jb * 8 + 2 * q] = G[mb][jb][0];
+                    dst[1 + jb * 8 + 2 * q + 1] = G[mb][jb][1];
+                }
+            }
+        }
+    }
+}
+
+// sum the row-group partials in fixed order: out[rep][0..KB] (compensated)
+__global__ void batched_reduce_kernel(const double* __restrict__ partials, int n_rowgroups, int m, int nout,
+                                      double* __restrict__ out) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)m * nout) return;
+    double s = 0.0, c = 0.0;
+    for (int rg = 0; rg < n_rowgroups; rg++) {
+        double e;
+        two_sum(s, partials[(size_t)rg * m * nout + idx], s, e);
+        c += e;
+    }
+    out[idx] = s + c;
+}
+
+// exact multinomial resampling: replicate r draws n_global rows with replacement
+// (apop_bootstrap.m4.c:144-147 draws gsl_rng_uniform_int(rng, N) per row); the count of
+// each resident row lands in the layout stage 2 reads.  One thread per draw.
+struct U4c { uint32_t x, y, z, w; };
+__device__ __forceinline__ U4c philox_c(U4c c, uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = U4c{hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0};
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return c;
+}
+__global__ void __launch_bounds__(256)
+bootstrap_counts_kernel(unsigned int* __restrict__ words, unsigned long long n_local, unsigned long long row_offset,
+                        unsigned long long n_global, int m, int m_pad, unsigned long long seed) {
+    const unsigned long long draw = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int r0 = blockIdx.y * 4;
+    if (draw >= n_global) return;
+    // 4 replicates per Philox call
+    const U4c u = philox_c(U4c{(uint32_t)draw, (uint32_t)(draw >> 32), (uint32_t)blockIdx.y, 0xB007u},
+                           (uint32_t)seed, (uint32_t)(seed >> 32));
+    const uint32_t rnd[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+        const int rep = r0 + e;
+        if (rep >= m) break;
+        // uniform row in [0, n_global): 32 random bits extended with the draw's low bits for n > 2^32
+        const unsigned long long wide = ((unsigned long long)rnd[e] << 32) | (rnd[(e + 1) & 3] ^ (uint32_t)draw * 0x9E3779B9u);
+        const unsigned long long row = (unsigned long long)(((unsigned __int128)wide * n_global) >> 64);
+        if (row < row_offset || row >= row_offset + n_local) continue;   // another rank's row
+        const unsigned long long lr = row - row_offset;
+        const unsigned long long byte = ((lr >> 5) * (unsigned long long)m_pad + rep) * TILE_ROWS + count_pos((int)(lr & 31));
+        atomicAdd(words + (byte >> 2), 1u << (8 * (byte & 3)));
+    }
+}
+
+template <int KB, class Fam>
+static cudaError_t launch_fam(const BatchedLaunch& L) {
+    const double4 aux = make_double4(L.aux[0], L.aux[1], L.aux[2], L.aux[3]);
+#define APB_GO(S, C)                                                                                          \
+    batched_kernel<KB, Fam, S, C><<<L.grid, BATCH_THREADS, 0, L.stream>>>(L.tiles, L.n_rows, L.n_tiles, L.k, L.cols, \
+        L.B, L.P, L.m, L.counts, L.m_pad, aux, L.n_rowgroups, L.partials)
+    if (L.want_score) { if (L.counts) APB_GO(true, true); else APB_GO(true, false); }
+    else { if (L.counts) APB_GO(false, true); else APB_GO(false, false); }
+#undef APB_GO
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    const int nout = 1 + KB;
+    const size_t total = (size_t)L.m * nout;
+    batched_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, L.stream>>>(L.partials, L.n_rowgroups, L.m, nout, L.out);
+    return cudaGetLastError();
+}
+template <int KB>
+static cudaError_t launch_kb(int fam, const BatchedLaunch& L) {
+    switch (fam) {
+    case GLM_PROBIT: return launch_fam<KB, FamProbit>(L);
+    case GLM_LOGIT2: return launch_fam<KB, FamLogit2>(L);
+    case GLM_POISSON_REG: return launch_fam<KB, FamPoissonReg>(L);
+    default: return cudaErrorInvalidValue;
+    }
+}
+int batched_kb(int k) { return k <= 8 ? 8 : k <= 16 ? 16 : k <= 24 ? 24 : 32; }
+cudaError_t batched_launch(int fam, const BatchedLaunch& L) {
+    switch (batched_kb(L.k)) {
+    case 8: return launch_kb<8>(fam, L);
+    case 16: return launch_kb<16>(fam, L);
+    case 24: return launch_kb<24>(fam, L);
+    case 32: return launch_kb<32>(fam, L);
+    }
+    return cudaErrorInvalidValue;
+}
+cudaError_t bootstrap_counts_launch(unsigned char* counts, size_t n_local, size_t row_offset, size_t n_global, int m,
+                                    int m_pad, unsigned long long seed, cudaStream_t st) {
+    if (!n_global || !m) return cudaSuccess;
+    dim3 grid((unsigned)((n_global + 255) / 256), (unsigned)((m + 3) / 4));
+    bootstrap_counts_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<unsigned int*>(counts), n_local, row_offset, n_global, m, m_pad, seed);
+    return cudaGetLastError();
+}
+
+}  // namespace apb

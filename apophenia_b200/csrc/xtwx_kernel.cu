@@ -1,0 +1,167 @@
+// xtwx_kernel.cu -- H = X' diag(w) [X | y]: the k x k observed information of the GLM
+// families (replacing the reference's numeric Hessian, apop_mle.m4.c:187-223, which costs
+// >= 4 P score passes) and the OLS normal equations X'X, X'y (model/apop_ols.c:333-334).
+//
+// Same two-phase tile scheme as the multinomial logit kernel: lane = row computes the
+// row weight and parks x (row-major, odd stride) and w*[x | y] (column-major) in the warp's
+// shared-memory slab; lane = column then accumulates its row of H with 16-byte broadcast
+// loads.  X and y are read from HBM once (8(k+1) bytes per row); per row the kernel issues
+// k (k+1) DFMA, so for k = 32 it is FP64-pipe bound (~1056 DFMA per lane per 32 rows).
+#include "xtwx_kernel.cuh"
+#include "families.cuh"
+
+namespace apb {
+
+template <int MODE>
+__device__ __forceinline__ double row_weight(double xb, double y, double w, const double* aux) {
+    if (MODE == XTWX_GRAM) return w;
+    if (MODE == XTWX_PROBIT) {
+        const RowOut o = FamProbit::eval(xb, y, w, aux);   // same clamps as the score
+        return o.d * (o.d + xb);
+    }
+    if (MODE == XTWX_LOGIT2) {
+        const double p = 1.0 / (1.0 + exp(-xb));
+        return p * (1.0 - p);
+    }
+    return exp(xb);
+}
+
+template <int KB, int MODE>
+__global__ void __launch_bounds__(XTWX_THREADS)
+xtwx_kernel(const double* __restrict__ tiles, const unsigned long long n_rows, const unsigned long long n_tiles,
+            const int K, const int cols, const int has_w, const __grid_constant__ XtwxParams prm,
+            double* __restrict__ partials, unsigned int* __restrict__ ticket, double* __restrict__ out) {
+    constexpr int WARPS = XTWX_THREADS / 32;
+    constexpr int XS = KB + 1;       // parked x rows: odd stride, conflict-free both ways
+    constexpr int NC = KB + 1;       // columns of [X | y]
+    constexpr int NOUT = KB * NC;
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* sx = smem + warp * (32 * XS + NC * 32);
+    double* sz = sx + 32 * XS;
+    const unsigned long long gwarp = (unsigned long long)blockIdx.x * WARPS + warp;
+    const unsigned long long nwarps = (unsigned long long)gridDim.x * WARPS;
+
+    double H[NC];
+#pragma unroll
+    for (int c = 0; c < NC; c++) H[c] = 0.0;
+
+    for (unsigned long long t = gwarp; t < n_tiles; t += nwarps) {
+        const double* base = tiles + t * (unsigned long long)(cols * TILE_ROWS) + lane;
+        double x[KB];
+#pragma unroll
+        for (int j = 0; j < KB; j++) x[j] = (j < K) ? ld_stream(base + j * TILE_ROWS) : 0.0;
+        const double y = ld_stream(base + K * TILE_ROWS);
+        const double w = has_w ? ld_stream(base + (K + 1) * TILE_ROWS) : 1.0;
+        double xb = 0.0;
+        if (MODE != XTWX_GRAM) {
+#pragma unroll
+            for (int j = 0; j < KB; j++) xb = fma(x[j], prm.beta[j], xb);
+        }
+        const bool valid = t * TILE_ROWS + lane < n_rows;
+        const double wgt = valid ? row_weight<MODE>(xb, y, w, prm.aux) : 0.0;
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < KB; j++) {
+            sx[lane * XS + j] = x[j];
+            sz[j * 32 + lane] = wgt * x[j];
+        }
+        sz[KB * 32 + lane] = wgt * y;
+        __syncwarp();
+#pragma unroll 2
+        for (int i = 0; i < 32; i += 2) {
+            const double xa = sx[i * XS + lane];
+            const double xc = sx[(i + 1) * XS + lane];
+#pragma unroll
+            for (int c = 0; c < NC; c++) {
+                const double2 r = *reinterpret_cast<const double2*>(sz + c * 32 + i);
+                H[c] = fma(xa, r.x, H[c]);
+                H[c] = fma(xc, r.y, H[c]);
+            }
+        }
+    }
+    __syncthreads();
+    double* red = smem;  // WARPS x NOUT doubles fits in the slabs (NOUT <= 32*XS + NC*32)
+    if (lane < KB) {
+#pragma unroll
+        for (int c = 0; c < NC; c++) red[warp * NOUT + lane * NC + c] = H[c];
+    }
+    __syncthreads();
+    for (int v = threadIdx.x; v < NOUT; v += XTWX_THREADS) {
+        double s = 0.0;
+#pragma unroll
+        for (int wv = 0; wv < WARPS; wv++) s += red[wv * NOUT + v];
+        partials[(size_t)blockIdx.x * NOUT + v] = s;
+    }
+    __shared__ unsigned int is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    for (int v = threadIdx.x; v < NOUT; v += XTWX_THREADS) {
+        double s = 0.0, c = 0.0;
+        for (unsigned b = 0; b < gridDim.x; b++) {
+            double er;
+            two_sum(s, __ldcg(partials + (size_t)b * NOUT + v), s, er);
+            c += er;
+        }
+        out[v] = s + c;
+    }
+    if (threadIdx.x == 0) *ticket = 0;
+}
+
+template <int KB>
+static size_t xtwx_smem() { return (size_t)(XTWX_THREADS / 32) * (32 * (KB + 1) + (KB + 1) * 32) * sizeof(double); }
+
+template <int KB, int MODE>
+static cudaError_t launch_one(const XtwxLaunch& L, const XtwxParams& prm) {
+    const size_t sm = xtwx_smem<KB>();
+    static bool done = false;
+    if (!done) { cudaFuncSetAttribute(xtwx_kernel<KB, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); done = true; }
+    xtwx_kernel<KB, MODE><<<L.grid, XTWX_THREADS, sm, L.stream>>>(L.tiles, L.n_rows, L.n_tiles, L.k, L.cols, L.has_w, prm,
+                                                                 L.partials, L.ticket, L.out);
+    return cudaGetLastError();
+}
+template <int KB, int MODE>
+static int bps_one() {
+    const size_t sm = xtwx_smem<KB>();
+    cudaFuncSetAttribute(xtwx_kernel<KB, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    int nb = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, xtwx_kernel<KB, MODE>, XTWX_THREADS, sm);
+    return nb;
+}
+int xtwx_kb(int k) { return k <= 8 ? 8 : k <= 16 ? 16 : k <= 24 ? 24 : 32; }
+
+#define APB_MODES(KB)                              \
+    switch (mode) {                                \
+    case XTWX_GRAM: return APB_OP(KB, XTWX_GRAM);  \
+    case XTWX_PROBIT: return APB_OP(KB, XTWX_PROBIT); \
+    case XTWX_LOGIT2: return APB_OP(KB, XTWX_LOGIT2); \
+    case XTWX_POISSON_REG: return APB_OP(KB, XTWX_POISSON_REG); \
+    default: break;                                \
+    }
+cudaError_t xtwx_launch(int mode, const XtwxLaunch& L, const XtwxParams& prm) {
+#define APB_OP(KB, M) launch_one<KB, M>(L, prm)
+    switch (xtwx_kb(L.k)) {
+    case 8: APB_MODES(8) break;
+    case 16: APB_MODES(16) break;
+    case 24: APB_MODES(24) break;
+    case 32: APB_MODES(32) break;
+    }
+#undef APB_OP
+    return cudaErrorInvalidValue;
+}
+int xtwx_blocks_per_sm(int mode, int k) {
+#define APB_OP(KB, M) bps_one<KB, M>()
+    switch (xtwx_kb(k)) {
+    case 8: APB_MODES(8) break;
+    case 16: APB_MODES(16) break;
+    case 24: APB_MODES(24) break;
+    case 32: APB_MODES(32) break;
+    }
+#undef APB_OP
+    return 0;
+}
+}  // namespace apb

@@ -216,6 +216,8 @@ int apop_b200_ll_score_batched(apop_b200_family family, apop_data *d, const doub
                                size_t m, int use_counts, double *ll, double *score);
 /* draw m multinomial resamples of the rows into a resident n x m count matrix */
 int apop_b200_bootstrap_counts(apop_data *d, size_t m, uint64_t seed);
+/* the resident counts as an n_rows x m row-major uint8 matrix (for checking and for host-side drivers) */
+int apop_b200_counts_download(const apop_data *d, size_t m, unsigned char *out);
 
 /* ------------------------------------------------------------------ *
  *  Installing into the reference's dispatch

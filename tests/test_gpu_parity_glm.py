@@ -276,3 +276,39 @@ def test_logit_category_page_and_overflow(b200, oracle):
         ge, scale = oracle.logit_score(Xo, yo, Bo, mode=oracle.EXACT)
         _check_score(ab.score(ab.LOGIT, d, m), ge, scale)
         ab.unpin(d)
+
+
+@pytest.mark.parametrize("n,k", [(30011, 32), (5000, 5), (20000, 20)])
+def test_information_and_gram(b200, oracle, n, k):
+    """observed information by one device pass (replaces the numeric Hessian,
+    apop_mle.m4.c:187-223) and the OLS normal equations (model/apop_ols.c:333-334)"""
+    ab = b200
+    X, y, beta = gen_probit_logit_sample(n, k, seed=n + k)
+    d = ab.pin(ab.Data(matrix=X, vector=y))
+    for fam, ofam in ((ab.PROBIT, 0), (ab.LOGIT, 1), (ab.POISSON_REG, 5)):
+        b = beta / (np.sqrt(k) if fam == ab.POISSON_REG else 1)
+        H = ab.information(fam, d, b)
+        want = oracle.information(ofam, X, y, b).astype(float)
+        scale = np.abs(want).max()
+        assert np.max(np.abs(H - want)) <= 1e-12 * scale * k, fam
+        assert np.allclose(H, H.T, rtol=0, atol=1e-13 * scale)
+    A, bvec = ab.ols_gram(d)
+    wa, wb = oracle.ols_gram(X, y, oracle.EXACT)
+    assert np.max(np.abs(A - wa.astype(float))) <= 1e-13 * np.abs(wa).max().astype(float) * 10
+    assert np.max(np.abs(bvec - wb.astype(float))) <= 1e-12 * (np.abs(X).T @ np.abs(y)).max()
+    ab.unpin(d)
+
+
+def test_nist_pontius_through_device_gram(b200):
+    """tests/nist_tests.c:20-35: certified OLS coefficients from the device X'X, X'y"""
+    import json, os
+    ab = b200
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "nist_strd.json")))["pontius"]
+    yx = np.array(g["y_x"]); y, x = yx[:, 0], yx[:, 1]
+    X = np.stack([np.ones_like(x), x, x * x], axis=1)
+    d = ab.pin(ab.Data(matrix=X, vector=y))
+    A, b = ab.ols_gram(d)
+    beta = np.linalg.solve(A, b)
+    for got, want, tol in zip(beta, g["certified_beta"], g["tolerances"]):
+        assert abs(got - want) < tol
+    ab.unpin(d)
