@@ -5,20 +5,25 @@
 // The formula shapes follow the reference (file:line under /root/reference) so
 // that clamps and branches trigger on the same rows; see SURVEY.md 8(a).
 #pragma once
+#include "fastmath.cuh"
+#ifdef __CUDACC__
 #include "common.cuh"
+#else
+namespace apb { constexpr int MAX_ACC = 3; }
+#endif
 
 namespace apb {
 
 // gsl_cdf_gaussian_P(x, 1): Phi(x) = erfc(-x/sqrt2)/2 with GSL's saturation
 // cut-offs (cdf/gauss.c GAUSS_XLOWER / GAUSS_XUPPER), as in oracle/oracle.c.
-__device__ __forceinline__ double gauss_cdf(double x) {
+APB_HD double gauss_cdf(double x) {
     double r = 0.5 * erfc(-x * 0.70710678118654752440);
     r = (x < -37.519) ? 0.0 : r;
     r = (x > 8.572) ? 1.0 : r;
     return r;
 }
 // gsl_ran_gaussian_pdf(x, 1)
-__device__ __forceinline__ double gauss_pdf1(double x) {
+APB_HD double gauss_pdf1(double x) {
     return 0.39894228040143267794 * exp(-0.5 * x * x);
 }
 
@@ -32,15 +37,30 @@ struct RowOut {
 struct FamProbit {
     static constexpr int NACC = 1;
     static constexpr bool USES_W = false;
-    __device__ __forceinline__ static RowOut eval(double xb, double y, double w, const double* aux) {
+    APB_HD static RowOut eval(double xb, double y, double w, const double* aux) {
         RowOut o;
+#ifdef APB_USE_LIBM_DEVICE
         double n = gauss_cdf(-xb);
+        const double pdf = gauss_pdf1(-xb);
+#else
+        // Phi(-|xb|) and phi(xb) from one exponential (fastmath.cuh); then the reference's
+        // own shape: n = Phi(-xb) as a rounded double, GSL's saturation, the two clamps.
+        double E, T;
+        fm_gauss_tail(fabs(xb), E, T);
+        double n = (xb >= 0.0) ? T : 1.0 - T;
+        n = (-xb < -37.519) ? 0.0 : n;
+        n = (-xb > 8.572) ? 1.0 : n;
+        const double pdf = 0.39894228040143267794 * E;
+#endif
         n = (n != 0.0) ? n : 1e-10;          // prevent -inf in the log
         n = (n < 1.0) ? n : 1.0 - 1e-10;
         const bool yes = (y != 0.0);
         const double arg = yes ? 1.0 - n : n;  // P(observed outcome)
+#ifdef APB_USE_LIBM_DEVICE
         o.s[0] = log(arg);
-        const double pdf = gauss_pdf1(-xb);
+#else
+        o.s[0] = fm_log(arg);
+#endif
         o.d = (yes ? pdf : -pdf) / arg;
         return o;
     }
@@ -52,14 +72,19 @@ struct FamProbit {
 struct FamLogit2 {
     static constexpr int NACC = 1;
     static constexpr bool USES_W = false;
-    __device__ __forceinline__ static RowOut eval(double xb, double y, double w, const double* aux) {
+    APB_HD static RowOut eval(double xb, double y, double w, const double* aux) {
         RowOut o;
         const bool chosen = (y != aux[0]);  // find_index: 0 = numeraire, else 1
         const double num = chosen ? xb : 0.0;
         // max + log(exp(xb-max) + exp(-max)) with max = xb:  xb + log(1 + exp(-xb));
         // when exp(-max) overflows the reference returns num - (max - max).
+#ifdef APB_USE_LIBM_DEVICE
         const double em = exp(-xb);
         const double lse = (xb < -700.0) ? 0.0 : xb + log(1.0 + em);
+#else
+        const double em = fm_exp(-xb);
+        const double lse = (xb < -700.0) ? 0.0 : xb + fm_log(1.0 + em);
+#endif
         o.s[0] = num - lse;
         const double p = 1.0 / (1.0 + em);   // P(category 1); em=inf -> 0
         o.d = (chosen ? 1.0 : 0.0) - p;
@@ -72,9 +97,13 @@ struct FamLogit2 {
 struct FamPoissonReg {
     static constexpr int NACC = 1;
     static constexpr bool USES_W = false;
-    __device__ __forceinline__ static RowOut eval(double xb, double y, double w, const double* aux) {
+    APB_HD static RowOut eval(double xb, double y, double w, const double* aux) {
         RowOut o;
+#ifdef APB_USE_LIBM_DEVICE
         const double mu = exp(xb);
+#else
+        const double mu = fm_exp(xb);
+#endif
         o.s[0] = y * xb - mu;
         o.d = y - mu;
         return o;
@@ -88,7 +117,7 @@ struct FamPoissonReg {
 struct FamOls {
     static constexpr int NACC = 3;
     static constexpr bool USES_W = true;
-    __device__ __forceinline__ static RowOut eval(double xb, double y, double w, const double* aux) {
+    APB_HD static RowOut eval(double xb, double y, double w, const double* aux) {
         RowOut o;
         const double e = xb - y;
         o.s[0] = e;

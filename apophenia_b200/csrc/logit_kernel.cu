@@ -17,6 +17,7 @@
 // kernel issues ~2 k (C-1) DFMA + (C-1) exp + 1 log, so at k = 32, C = 8 the
 // FP64 pipe is about level with HBM.
 #include "logit_kernel.cuh"
+#include "fastmath.cuh"
 
 namespace apb {
 
@@ -66,14 +67,14 @@ logit_fused_kernel(const double* __restrict__ tiles, const unsigned long long n_
         double e[C1], sum = 0.0, num = 0.0;
 #pragma unroll
         for (int c = 0; c < C1; c++) {
-            e[c] = exp(xb[c] - mx);
+            e[c] = fm_exp(xb[c] - mx);
             sum += e[c];
             num = (idx == c + 1) ? xb[c] : num;
         }
-        const double e0 = exp(-mx);  // the numeraire's exp(0 - max)
+        const double e0 = fm_exp(-mx);  // the numeraire's exp(0 - max)
         const bool valid = t * TILE_ROWS + lane < n_rows;
         // when exp(-max) overflows the reference takes log-sum-exp = max - max
-        const double lse = (mx < -700.0) ? 0.0 : mx + log(sum + e0);
+        const double lse = (mx < -700.0) ? 0.0 : mx + fm_log(sum + e0);
         ll.add(valid ? num - lse : 0.0);
         // probabilities for the score: overflow of e0 means p_c = 0 for every free category
         const double inv = (mx < -700.0) ? 0.0 : 1.0 / (sum + e0);

@@ -20,10 +20,10 @@ __device__ __forceinline__ double row_weight(double xb, double y, double w, cons
         return o.d * (o.d + xb);
     }
     if (MODE == XTWX_LOGIT2) {
-        const double p = 1.0 / (1.0 + exp(-xb));
+        const double p = 1.0 / (1.0 + fm_exp(-xb));
         return p * (1.0 - p);
     }
-    return exp(xb);
+    return fm_exp(xb);
 }
 
 template <int KB, int MODE>

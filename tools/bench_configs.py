@@ -1,0 +1,114 @@
+#!/usr/bin/env python
+"""Times the other BASELINE.json configurations on one GPU (bench.py carries the headline
+one).  Prints one JSON object per configuration.  Usage: python tools/bench_configs.py [names]"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import apophenia_b200 as ab  # noqa: E402
+
+
+def timed(fn, reps=5, warm=2):
+    for _ in range(warm):
+        fn()
+    ab.pass_timer_reset()
+    t0 = time.perf_counter()
+    for i in range(reps):
+        fn(i)
+    dt = (time.perf_counter() - t0) / reps
+    ms, n = ab.pass_timer()
+    return dt, ms / max(n, 1)
+
+
+def cfg_logit8(rows=20_000_000, k=32, C=8):
+    rng = np.random.default_rng(8)
+    B = rng.uniform(-1, 1, k * (C - 1))
+    s = ab.synth(ab.LOGIT, rows, k, B, ncat=C)
+    dt, kms = timed(lambda i=0: ab.ll_score(ab.LOGIT, s, B * (1 + 1e-6 * (i + 1))), reps=20)
+    s.free()
+    by = rows * (k + 1) * 8
+    return {"config": f"logit multinomial C={C}, {rows}x{k}, fused LL+score", "ms_per_pass": 1e3 * dt, "kernel_ms": kms,
+            "rows_per_s": rows / dt, "GBps": by / kms / 1e6, "flops_per_row": 4 * k * (C - 1)}
+
+
+def cfg_bootstrap(rows=5_000_000, k=20, m=1000, score=True):
+    rng = np.random.default_rng(8)
+    beta = rng.uniform(-1, 1, k)
+    s = ab.synth(ab.PROBIT, rows, k, beta)
+    t0 = time.perf_counter()
+    ab.bootstrap_counts(s, m, seed=8)
+    t_counts = time.perf_counter() - t0
+    B = beta[None, :] + 0.01 * rng.standard_normal((m, k))
+    dt, kms = timed(lambda i=0: ab.ll_score_batched(ab.PROBIT, s, B * (1 + 1e-6 * (i + 1)), use_counts=True, want_score=score), reps=3, warm=1)
+    # the unbatched alternative: m single-beta passes
+    dt1, kms1 = timed(lambda i=0: ab.ll_score(ab.PROBIT, s, B[0] * (1 + 1e-6 * (i + 1))), reps=20)
+    s.free()
+    return {"config": f"probit bootstrap batched, {rows}x{k}, m={m} replicates with resample counts, score={score}",
+            "ms_per_batched_pass": 1e3 * dt, "kernel_ms": kms, "row_replicates_per_s": rows * m / dt,
+            "dmma_flops": 4.0 * rows * k * m, "dmma_TFLOPs": 4.0 * rows * k * m / (kms * 1e-3) / 1e12,
+            "counts_seconds": t_counts, "single_beta_pass_ms": 1e3 * dt1, "m_single_passes_ms": 1e3 * dt1 * m,
+            "speedup_vs_m_single_passes": dt1 * m / dt}
+
+
+def cfg_chains(rows=50_000_000, k=24, m=256):
+    rng = np.random.default_rng(8)
+    beta = rng.uniform(-1, 1, k)
+    s = ab.synth(ab.LOGIT, rows, k, beta)
+    B = beta[None, :] + 0.01 * rng.standard_normal((m, k))
+    dt, kms = timed(lambda i=0: ab.ll_score_batched(ab.LOGIT, s, B * (1 + 1e-6 * (i + 1)), want_score=False), reps=3, warm=1)
+    dt1, kms1 = timed(lambda i=0: ab.ll_score(ab.LOGIT, s, B[0] * (1 + 1e-6 * (i + 1)), want_score=False), reps=20)
+    s.free()
+    return {"config": f"logit metropolis chains batched LL, {rows}x{k}, m={m} chains",
+            "ms_per_batched_step": 1e3 * dt, "kernel_ms": kms, "row_chains_per_s": rows * m / dt,
+            "single_chain_step_ms": 1e3 * dt1, "speedup_vs_m_single_steps": dt1 * m / dt}
+
+
+def cfg_poisson(rows=50_000_000, k=16):
+    rng = np.random.default_rng(8)
+    beta = rng.uniform(-1, 1, k) / np.sqrt(k)
+    s = ab.synth(ab.POISSON_REG, rows, k, beta)
+    dt, kms = timed(lambda i=0: ab.ll_score(ab.POISSON_REG, s, beta * (1 + 1e-6 * (i + 1))), reps=20)
+    s.free()
+    by = rows * (k + 1) * 8
+    out = {"config": f"poisson regression, {rows}x{k} (one GPU's shard of 400M x 16), fused LL+score",
+           "ms_per_pass": 1e3 * dt, "kernel_ms": kms, "rows_per_s": rows / dt, "GBps": by / kms / 1e6}
+    lam = np.array([3.1])
+    s = ab.synth(ab.POISSON, rows, k, lam)
+    m = ab.vector_model([3.0], None)
+    t0 = time.perf_counter(); ll0 = ab.log_likelihood(ab.POISSON, s, m); first = time.perf_counter() - t0
+    t0 = time.perf_counter(); ll1 = ab.log_likelihood(ab.POISSON, s, ab.vector_model([3.2], None)); later = time.perf_counter() - t0
+    s.free()
+    out["iid_poisson_reading"] = {"cells": rows * k, "first_pass_s": first, "later_call_s": later}
+    return out
+
+
+def cfg_newton(rows=100_000_000, k=32):
+    """information pass timing at the headline shape"""
+    rng = np.random.default_rng(8)
+    beta = rng.uniform(-1, 1, k)
+    s = ab.synth(ab.PROBIT, rows, k, beta)
+    dt, kms = timed(lambda i=0: ab.information(ab.PROBIT, s, beta * (1 + 1e-6 * (i + 1))), reps=5)
+    s.free()
+    return {"config": f"probit observed information (k x k), {rows}x{k}", "ms_per_pass": 1e3 * dt, "kernel_ms": kms,
+            "GBps": rows * (k + 1) * 8 / kms / 1e6, "dfma_TFLOPs": 2.0 * rows * k * (k + 1) / (kms * 1e-3) / 1e12}
+
+
+ALL = {"logit8": cfg_logit8, "bootstrap": cfg_bootstrap, "chains": cfg_chains, "poisson": cfg_poisson, "newton": cfg_newton}
+
+if __name__ == "__main__":
+    ab.init(0)
+    names = sys.argv[1:] or list(ALL)
+    for nm in names:
+        kw = {}
+        if "=" in nm:
+            nm, arg = nm.split(":", 1) if ":" in nm else (nm, "")
+        if ":" in nm:
+            nm, arg = nm.split(":", 1)
+            kw = {a.split("=")[0]: int(a.split("=")[1]) for a in arg.split(",")}
+        print(json.dumps({nm: ALL[nm](**kw)}), flush=True)
+    ab.finalize()
