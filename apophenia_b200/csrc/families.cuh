@@ -61,7 +61,11 @@ struct FamProbit {
 #else
         o.s[0] = fm_log(arg);
 #endif
+#ifdef APB_USE_LIBM_DEVICE
         o.d = (yes ? pdf : -pdf) / arg;
+#else
+        o.d = fm_div(yes ? pdf : -pdf, arg);
+#endif
         return o;
     }
 };
@@ -86,7 +90,11 @@ struct FamLogit2 {
         const double lse = (xb < -700.0) ? 0.0 : xb + fm_log(1.0 + em);
 #endif
         o.s[0] = num - lse;
+#ifdef APB_USE_LIBM_DEVICE
         const double p = 1.0 / (1.0 + em);   // P(category 1); em=inf -> 0
+#else
+        const double p = fm_rcp(1.0 + fmin(em, 1e300));   // P(category 1); em = inf -> 0
+#endif
         o.d = (chosen ? 1.0 : 0.0) - p;
         return o;
     }

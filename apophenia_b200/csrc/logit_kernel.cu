@@ -77,7 +77,7 @@ logit_fused_kernel(const double* __restrict__ tiles, const unsigned long long n_
         const double lse = (mx < -700.0) ? 0.0 : mx + fm_log(sum + e0);
         ll.add(valid ? num - lse : 0.0);
         // probabilities for the score: overflow of e0 means p_c = 0 for every free category
-        const double inv = (mx < -700.0) ? 0.0 : 1.0 / (sum + e0);
+        const double inv = (mx < -700.0) ? 0.0 : fm_rcp(sum + e0);
         __syncwarp();
 #pragma unroll
         for (int j = 0; j < KB; j++) sx[lane * XS + j] = x[j];

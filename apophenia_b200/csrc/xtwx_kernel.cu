@@ -20,7 +20,7 @@ __device__ __forceinline__ double row_weight(double xb, double y, double w, cons
         return o.d * (o.d + xb);
     }
     if (MODE == XTWX_LOGIT2) {
-        const double p = 1.0 / (1.0 + fm_exp(-xb));
+        const double p = fm_rcp(1.0 + fmin(fm_exp(-xb), 1e300));
         return p * (1.0 - p);
     }
     return fm_exp(xb);

@@ -105,9 +105,7 @@ if __name__ == "__main__":
     names = sys.argv[1:] or list(ALL)
     for nm in names:
         kw = {}
-        if "=" in nm:
-            nm, arg = nm.split(":", 1) if ":" in nm else (nm, "")
-        if ":" in nm:
+        if ":" in nm:  # name:key=value,key=value
             nm, arg = nm.split(":", 1)
             kw = {a.split("=")[0]: int(a.split("=")[1]) for a in arg.split(",")}
         print(json.dumps({nm: ALL[nm](**kw)}), flush=True)
