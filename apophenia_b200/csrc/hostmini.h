@@ -70,6 +70,26 @@ typedef struct {
 } apop_mle_report;
 apop_mle_report apop_mle_last_report(void);
 
+/* ---- drivers.c ---- */
+int apop_b200_family_of(apop_model *m);      /* which device family is installed in m (-1: none) */
+void apop_b200_install_estimates(void);      /* closed-form estimate methods of poisson / normal / ols */
+apop_data *apop_data_covariance(const apop_data *in);
+apop_data *apop_model_numerical_covariance(apop_data *data, apop_model *m);   /* -H^-1 from one information pass */
+/* apop_bootstrap_cov (apop_bootstrap.m4.c:122): gsl_rng* replaced by a seed; iterations <= 0 means 1000 */
+apop_data *apop_bootstrap_cov(apop_data *data, apop_model *model, uint64_t seed, int iterations, apop_data **boot_store);
+/* apop_mcmc_settings (apop.m4.h, defaults apop_mcmc.m4.c:35-43) + initial proposal scale, seed, chain count */
+typedef struct {
+    int periods;
+    double burnin;
+    double target_accept_rate;
+    double initial_scale;
+    uint64_t seed;
+    int n_chains;
+} apop_mcmc_settings;
+apop_mcmc_settings apop_mcmc_settings_defaults(void);
+apop_data *apop_model_metropolis(apop_data *d, apop_model *m, apop_mcmc_settings s);
+apop_data *apop_b200_metropolis_chains(apop_data *d, apop_model *m, apop_mcmc_settings s);
+
 extern apop_model *apop_probit, *apop_logit, *apop_poisson, *apop_normal, *apop_ols, *apop_poisson_regression;
 
 #ifdef __cplusplus

@@ -240,12 +240,6 @@ static int minimize_simplex(mle_info *I, const apop_mle_settings *mp, double *x,
  * device pass (apop_b200_information), in place of the reference's finite-difference
  * Jacobian root finder (apop_mle.m4.c:885-916). */
 typedef int (*info_fn)(int, apop_data *, const double *, size_t, double *);
-static int family_of(apop_model *m) {
-    static const char *names[] = {"apop_b200_probit_ll", "apop_b200_logit_ll", "apop_b200_poisson_ll", "apop_b200_normal_ll",
-                                  "apop_b200_ols_ll", "apop_b200_poisson_reg_ll"};
-    for (int f = 0; f < 6; f++) { void *p = dlsym(RTLD_DEFAULT, names[f]); if (p && p == (void *)m->log_likelihood) return f; }
-    return -1;
-}
 static int chol_solve(double *A, double *b, size_t n) { /* A = L L', solves in place; 1 if not PD */
     for (size_t j = 0; j < n; j++) {
         long double s = A[j * n + j];
@@ -265,7 +259,7 @@ static int chol_solve(double *A, double *b, size_t n) { /* A = L L', solves in p
 static int minimize_newton(mle_info *I, const apop_mle_settings *mp, double *x, int *iters, double *gnorm_out) {
     const size_t n = I->n;
     info_fn information = (info_fn)dlsym(RTLD_DEFAULT, "apop_b200_information");
-    const int fam = family_of(I->model);
+    const int fam = apop_b200_family_of(I->model);
     if (!information || fam < 0) { fprintf(stderr, "Newton needs apop_b200_information and a registered device model\n"); return -1; }
     double *g = malloc(sizeof(double) * n), *p = malloc(sizeof(double) * n), *H = malloc(sizeof(double) * n * n);
     double f = fdf(x, I, g), gnorm = nrm(g, n);

@@ -30,6 +30,11 @@ class apop_mle_report(C.Structure):
                 ("ll", C.c_double), ("gradient_norm", C.c_double), ("seconds", C.c_double)]
 
 
+class apop_mcmc_settings(C.Structure):
+    _fields_ = [("periods", C.c_int), ("burnin", C.c_double), ("target_accept_rate", C.c_double),
+                ("initial_scale", C.c_double), ("seed", C.c_uint64), ("n_chains", C.c_int)]
+
+
 def lib():
     """dlopen the host mirror with RTLD_GLOBAL so apop_b200_register finds apop_vtable_add"""
     global _H
@@ -73,8 +78,51 @@ def lib():
         h.apop_b200_category_table.restype = _PD
         h.apop_b200_category_table.argtypes = [_PD]
         h.apop_b200_ols_shuffle.argtypes = [_PD]
+        h.apop_b200_family_of.argtypes = [_PM]
+        h.apop_data_covariance.restype = _PD
+        h.apop_data_covariance.argtypes = [_PD]
+        h.apop_model_numerical_covariance.restype = _PD
+        h.apop_model_numerical_covariance.argtypes = [_PD, _PM]
+        h.apop_bootstrap_cov.restype = _PD
+        h.apop_bootstrap_cov.argtypes = [_PD, _PM, C.c_uint64, C.c_int, C.POINTER(_PD)]
+        h.apop_mcmc_settings_defaults.restype = apop_mcmc_settings
+        h.apop_model_metropolis.restype = _PD
+        h.apop_model_metropolis.argtypes = [_PD, _PM, apop_mcmc_settings]
+        h.apop_b200_metropolis_chains.restype = _PD
+        h.apop_b200_metropolis_chains.argtypes = [_PD, _PM, apop_mcmc_settings]
+        h.apop_b200_install_estimates()
         _H = h
     return _H
+
+
+def matrix_of(data_ptr):
+    """copy of an apop_data's matrix as numpy"""
+    m = data_ptr.contents.matrix.contents
+    a = np.ctypeslib.as_array(m.data, shape=(m.size1, m.tda))
+    return np.array(a[:, :m.size2])
+
+
+def bootstrap_cov(data_ptr, est_ptr, iterations=1000, seed=8):
+    """apop_bootstrap_cov on a fitted, registered model; returns (cov, replicate estimates)"""
+    h = lib()
+    store = _PD()
+    cov = h.apop_bootstrap_cov(data_ptr, est_ptr, int(seed), int(iterations), C.byref(store))
+    if not cov:
+        raise abi.B200Error("apop_bootstrap_cov failed: " + abi.last_error())
+    return matrix_of(cov), matrix_of(store)
+
+
+def metropolis(data_ptr, model_ptr, periods=6000, burnin=0.05, target_accept_rate=0.35, initial_scale=1.0, seed=8,
+               n_chains=1):
+    """apop_model_metropolis (n_chains == 1: the unmodified one-LL-per-step caller) or the
+    lock-step batched chains; returns draws as (n_chains, kept, P)"""
+    h = lib()
+    s = apop_mcmc_settings(int(periods), float(burnin), float(target_accept_rate), float(initial_scale), int(seed), int(n_chains))
+    out = h.apop_model_metropolis(data_ptr, model_ptr, s) if n_chains == 1 else h.apop_b200_metropolis_chains(data_ptr, model_ptr, s)
+    if not out:
+        raise abi.B200Error("metropolis failed: " + abi.last_error())
+    a = matrix_of(out)
+    return a.reshape(n_chains, -1, a.shape[1])
 
 
 _MODEL_SYMS = {abi.PROBIT: "apop_probit", abi.LOGIT: "apop_logit", abi.POISSON: "apop_poisson",
