@@ -18,6 +18,7 @@
 // FP64 pipe is about level with HBM.
 #include "logit_kernel.cuh"
 #include "fastmath.cuh"
+#include <stdlib.h>
 
 namespace apb {
 
@@ -136,6 +137,230 @@ logit_fused_kernel(const double* __restrict__ tiles, const unsigned long long n_
     if (threadIdx.x == 0) *ticket = 0;
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Tensor-core variant (APOP_B200_LOGIT_DMMA=1; measured slower than the FP64-pipe kernel in
+// round 1: 1.89 ms vs 1.40 ms at 20M x 32, C = 8 -- the cross-lane soft-max costs more than the
+// DFMAs it saves; kept for the next round's hybrid): the two contractions of a tile run as FP64 DMMA
+// (mma.sync m8n8k4), which executes on the tensor pipe next to the FP64 pipe, leaving the
+// latter to the soft-max.  The (C-1 <= 7) free categories are the M = 8 rows of the MMA:
+//   stage 1  S^T[c][row] = B^T[c][j] . X^T[j][row]      (K = columns)
+//   soft-max across the 8 lanes that hold the 8 categories of a row (xor-shuffles 4, 8, 16);
+//            exp(-max), the log and nothing else are evaluated once per row, by the lane
+//            whose category index equals the row's slot, and exp(-max) is broadcast back
+//   stage 3  G^T[c][j] += R^T[c][row] . X[row][j]       (K = rows, slots = rows 2q+e)
+// Same fragment trick as batched_kernel.cu: the C fragment of stage 1 is already the A
+// fragment of stage 3.  X is read once from HBM (stage-1 fragments, 64-byte segments of the
+// tile columns) and once more from L1 (stage-3 fragments).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma_8x8x4(double& d0, double& d1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+__device__ __forceinline__ double shfl_xor_d(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+__device__ __forceinline__ double group_max(double v) {   // over the 8 lanes sharing q = lane%4
+    v = fmax(v, shfl_xor_d(v, 4)); v = fmax(v, shfl_xor_d(v, 8)); return fmax(v, shfl_xor_d(v, 16));
+}
+__device__ __forceinline__ double group_sum(double v) {
+    v += shfl_xor_d(v, 4); v += shfl_xor_d(v, 8); return v + shfl_xor_d(v, 16);
+}
+
+template <int KB>
+__global__ void __launch_bounds__(LOGIT_THREADS)
+logit_dmma_kernel(const double* __restrict__ tiles, const unsigned long long n_rows,
+                  const unsigned long long n_tiles, const int K, const int C1,
+                  const __grid_constant__ LogitParams prm, double* __restrict__ partials,
+                  unsigned int* __restrict__ ticket, double* __restrict__ out) {
+    constexpr int WARPS = LOGIT_THREADS / 32;
+    constexpr int KS = KB / 4, JB = KB / 8;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, q = lane & 3;
+    const unsigned long long gwarp = (unsigned long long)blockIdx.x * WARPS + warp;
+    const unsigned long long nwarps = (unsigned long long)gridDim.x * WARPS;
+    const int cols = K + 1;
+    const bool cat_ok = g < C1;   // this lane's category slot is a real category (g+1)
+    // per-warp double buffer: the next tile streams in with 16-byte cp.async while this one
+    // is being processed; columns are padded to CS doubles so that the stage-1 fragment reads
+    // (4 columns x 8 rows per request) are bank-conflict free
+    extern __shared__ __align__(16) double smem[];
+    double* ring = smem + warp * (2 * LOGIT_TILE_DOUBLES);
+    const int n_chunks = cols * 16;           // 16-byte chunks in a tile
+    auto prefetch = [&](unsigned long long tt, int buf) {
+        const double* src = tiles + tt * (unsigned long long)(cols * TILE_ROWS);
+        double* dst = ring + buf * LOGIT_TILE_DOUBLES;
+        for (int c = lane; c < n_chunks; c += 32) {
+            const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + (c >> 4) * LOGIT_CS + (c & 15) * 2);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src + c * 2));
+        }
+        asm volatile("cp.async.commit_group;");
+    };
+
+    double bfrag[KS];              // B^T[c = g][j = ks*4 + q]
+#pragma unroll
+    for (int ks = 0; ks < KS; ks++) {
+        const int j = ks * 4 + q;
+        bfrag[ks] = (cat_ok && j < K) ? prm.B[j * C1 + g] : 0.0;
+    }
+    double cat[LOGIT_MAX_C1];
+#pragma unroll
+    for (int c = 0; c < LOGIT_MAX_C1; c++) cat[c] = prm.cats[c];
+
+    double G[JB][2];
+#pragma unroll
+    for (int jb = 0; jb < JB; jb++) G[jb][0] = G[jb][1] = 0.0;
+    KSum ll;
+
+    int cur = 0;
+    if (gwarp < n_tiles) prefetch(gwarp, 0);
+    for (unsigned long long t = gwarp; t < n_tiles; t += nwarps) {
+        if (t + nwarps < n_tiles) {
+            prefetch(t + nwarps, cur ^ 1);
+            asm volatile("cp.async.wait_group 1;");
+        } else
+            asm volatile("cp.async.wait_group 0;");
+        __syncwarp();
+        const double* tile = ring + cur * LOGIT_TILE_DOUBLES;
+        // ---- stage 1: all fragment loads of the tile are issued before the first MMA
+        // (KS*4 x 256 B per warp in flight), like the lane = row kernels
+        double xf[KS][4];
+#pragma unroll
+        for (int ks = 0; ks < KS; ks++) {
+            const int j = ks * 4 + q;
+#pragma unroll
+            for (int nb = 0; nb < 4; nb++) xf[ks][nb] = (j < K) ? tile[j * LOGIT_CS + nb * 8 + g] : 0.0;
+        }
+        double S[4][2];
+#pragma unroll
+        for (int nb = 0; nb < 4; nb++) S[nb][0] = S[nb][1] = 0.0;
+#pragma unroll
+        for (int ks = 0; ks < KS; ks++)
+#pragma unroll
+            for (int nb = 0; nb < 4; nb++) dmma_8x8x4(S[nb][0], S[nb][1], bfrag[ks], xf[ks][nb]);
+        // ---- soft-max over the categories of each of this lane group's 8 rows
+        double mxs[4][2], den[4][2];
+        int hit[4][2];
+        double mine_mx = 0.0;     // max of the row whose slot (nb*2+e) equals g
+        bool mine_valid = false;
+#pragma unroll
+        for (int nb = 0; nb < 4; nb++) {
+            const double2 y2 = *reinterpret_cast<const double2*>(tile + K * LOGIT_CS + nb * 8 + 2 * q);
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const double y = e ? y2.y : y2.x;
+                // find_index (model/apop_probit.c:206-210): first category value equal to y, else C1
+                int idx = C1;
+#pragma unroll
+                for (int c = LOGIT_MAX_C1 - 1; c >= 0; c--) idx = (c < C1 && y == cat[c]) ? c : idx;
+                hit[nb][e] = (idx == g + 1) && cat_ok;
+                const double s = cat_ok ? S[nb][e] : -1e300;
+                const double mx = group_max(s);
+                const double ev = fm_exp(s - mx);
+                den[nb][e] = group_sum(ev);
+                mxs[nb][e] = mx;
+                S[nb][e] = ev;     // S now holds exp(xb_c - max)
+                ll.add((hit[nb][e] && t * TILE_ROWS + nb * 8 + 2 * q + e < n_rows) ? s : 0.0);   // the numerator x.beta_idx
+                if (nb * 2 + e == g) { mine_mx = mx; mine_valid = t * TILE_ROWS + nb * 8 + 2 * q + e < n_rows; }
+            }
+        }
+        // exp(-max) once per row (lane g owns slot g), broadcast to the row's 8 lanes
+        const double mine_e0 = fm_exp(-mine_mx);
+        double mine_den = 0.0;
+#pragma unroll
+        for (int nb = 0; nb < 4; nb++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const int slot = nb * 2 + e;
+                const double e0 = __shfl_sync(0xffffffffu, mine_e0, slot * 4 + q);
+                den[nb][e] += e0;
+                if (slot == g) mine_den = den[nb][e];
+            }
+        // when exp(-max) overflows the reference takes log-sum-exp = max - max
+        const double lse = (mine_mx < -700.0) ? 0.0 : mine_mx + fm_log(mine_den);
+        ll.add(mine_valid ? -lse : 0.0);
+        // residuals r = 1{idx = c} - p_c, in place: S becomes R^T
+#pragma unroll
+        for (int nb = 0; nb < 4; nb++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const double inv = (mxs[nb][e] < -700.0) ? 0.0 : fm_rcp(den[nb][e]);
+                const bool valid = t * TILE_ROWS + nb * 8 + 2 * q + e < n_rows;
+                const double r = (hit[nb][e] ? 1.0 : 0.0) - S[nb][e] * inv;
+                S[nb][e] = (valid && cat_ok) ? r : 0.0;
+            }
+        // ---- stage 3
+#pragma unroll
+        for (int jb = 0; jb < JB; jb++) {
+            const int j = jb * 8 + g;
+#pragma unroll
+            for (int nb = 0; nb < 4; nb++) {
+                double2 x2 = make_double2(0.0, 0.0);
+                if (j < K) x2 = *reinterpret_cast<const double2*>(tile + j * LOGIT_CS + nb * 8 + 2 * q);
+                dmma_8x8x4(G[jb][0], G[jb][1], S[nb][0], x2.x);
+                dmma_8x8x4(G[jb][0], G[jb][1], S[nb][1], x2.y);
+            }
+        }
+        __syncwarp();   // every lane is done with this buffer before the next prefetch overwrites it
+        cur ^= 1;
+    }
+
+    // ---- CTA reduction: lane (g, q) holds G^T[c = g][j = jb*8 + 2q + {0,1}]
+    const int NOUT = 1 + KB * C1;
+    __syncthreads();                   // the ring is reused as the WARPS x NOUT reduction scratch
+    const double llw = warp_sum(ll.value());
+    if (lane == 0) smem[warp * NOUT] = llw;
+    if (cat_ok) {
+#pragma unroll
+        for (int jb = 0; jb < JB; jb++) {
+            smem[warp * NOUT + 1 + (jb * 8 + 2 * q) * C1 + g] = G[jb][0];
+            smem[warp * NOUT + 1 + (jb * 8 + 2 * q + 1) * C1 + g] = G[jb][1];
+        }
+    }
+    __syncthreads();
+    for (int v = threadIdx.x; v < NOUT; v += LOGIT_THREADS) {
+        double s = 0.0;
+#pragma unroll
+        for (int wv = 0; wv < WARPS; wv++) s += smem[wv * NOUT + v];
+        partials[(size_t)blockIdx.x * NOUT + v] = s;
+    }
+    __shared__ unsigned int is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    for (int v = threadIdx.x; v < NOUT; v += LOGIT_THREADS) {
+        double s = 0.0, c = 0.0;
+        for (unsigned b = 0; b < gridDim.x; b++) {
+            double er;
+            two_sum(s, __ldcg(partials + (size_t)b * NOUT + v), s, er);
+            c += er;
+        }
+        out[v] = s + c;
+    }
+    if (threadIdx.x == 0) *ticket = 0;
+}
+
+static size_t dmma_smem() { return (size_t)(LOGIT_THREADS / 32) * 2 * LOGIT_TILE_DOUBLES * sizeof(double); }
+template <int KB>
+static cudaError_t dmma_launch_one(int c1, const LogitLaunch& L, const LogitParams& prm) {
+    const size_t sm = dmma_smem();
+    static bool done = false;
+    if (!done) { cudaFuncSetAttribute(logit_dmma_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); done = true; }
+    logit_dmma_kernel<KB><<<L.grid, LOGIT_THREADS, sm, L.stream>>>(L.tiles, L.n_rows, L.n_tiles, L.k, c1, prm,
+                                                                   L.partials, L.ticket, L.out);
+    return cudaGetLastError();
+}
+template <int KB>
+static int dmma_bps_one(int c1) {
+    const size_t sm = dmma_smem();
+    cudaFuncSetAttribute(logit_dmma_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    int nb = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, logit_dmma_kernel<KB>, LOGIT_THREADS, sm);
+    return nb;
+}
+
 template <int KB, int C1>
 static size_t logit_smem() { return (size_t)(LOGIT_THREADS / 32) * (32 * (KB + 1) + C1 * 32) * sizeof(double); }
 
@@ -172,7 +397,21 @@ static int bps_one() {
     }
 int logit_kb(int k) { return k <= 8 ? 8 : k <= 16 ? 16 : k <= 24 ? 24 : 32; }
 
+static bool use_smem_variant() {
+    static int v = -1;
+    // the FP64-pipe kernel is the default; APOP_B200_LOGIT_DMMA=1 selects the tensor-pipe variant
+    if (v < 0) { const char* e = getenv("APOP_B200_LOGIT_DMMA"); v = (e && e[0] == '1') ? 0 : 1; }
+    return v == 1;
+}
 cudaError_t logit_launch(int c1, const LogitLaunch& L, const LogitParams& prm) {
+    if (!use_smem_variant() && c1 >= 1 && c1 <= LOGIT_MAX_C1) {
+        switch (logit_kb(L.k)) {
+        case 8: return dmma_launch_one<8>(c1, L, prm);
+        case 16: return dmma_launch_one<16>(c1, L, prm);
+        case 24: return dmma_launch_one<24>(c1, L, prm);
+        case 32: return dmma_launch_one<32>(c1, L, prm);
+        }
+    }
 #define APB_OP(KB, C) launch_one<KB, C>(L, prm)
     switch (logit_kb(L.k)) {
     case 8: APB_LOGIT_C(8) break;
@@ -184,6 +423,14 @@ cudaError_t logit_launch(int c1, const LogitLaunch& L, const LogitParams& prm) {
     return cudaErrorInvalidValue;
 }
 int logit_blocks_per_sm(int k, int c1) {
+    if (!use_smem_variant() && c1 >= 1 && c1 <= LOGIT_MAX_C1) {
+        switch (logit_kb(k)) {
+        case 8: return dmma_bps_one<8>(c1);
+        case 16: return dmma_bps_one<16>(c1);
+        case 24: return dmma_bps_one<24>(c1);
+        case 32: return dmma_bps_one<32>(c1);
+        }
+    }
 #define APB_OP(KB, C) bps_one<KB, C>()
     switch (logit_kb(k)) {
     case 8: APB_LOGIT_C(8) break;
