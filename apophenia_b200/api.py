@@ -18,7 +18,7 @@ __all__ = ["init", "finalize", "pin", "unpin", "invalidate", "is_pinned", "log_l
            "pass_timer", "probit_model", "logit_model", "vector_model", "Data", "Model", "B200Error",
            "PROBIT", "LOGIT", "POISSON", "NORMAL", "OLS", "POISSON_REG", "comm_init_from_torch",
            "comm_finalize", "set_auto_pin", "last_error", "information", "ols_gram",
-           "ll_score_batched", "bootstrap_counts", "counts_download",
+           "col_sums", "probit_start", "ll_score_batched", "bootstrap_counts", "counts_download",
            "MAP_IDENTITY", "MAP_DEV", "MAP_DEV2", "MAP_POISSON", "MAP_LOG", "MAP_EXP"]
 
 _dp = C.POINTER(C.c_double)
@@ -146,6 +146,19 @@ def counts_download(d, m, n_rows):
     out = np.zeros((n_rows, m), dtype=np.uint8)
     abi.check(_lib().apop_b200_counts_download(_ptr(d), int(m), out.ctypes.data_as(C.POINTER(C.c_ubyte))),
               "apop_b200_counts_download")
+    return out
+
+
+def col_sums(d, mode, k):
+    out = np.zeros(k)
+    abi.check(_lib().apop_b200_col_sums(_ptr(d), int(mode), out.ctypes.data_as(_dp)), "apop_b200_col_sums")
+    return out
+
+
+def probit_start(d, k):
+    """probit_prep's start point exp(mean ln|x_ij|) computed on the device"""
+    out = np.zeros(k)
+    abi.check(_lib().apop_b200_probit_start(_ptr(d), out.ctypes.data_as(_dp)), "apop_b200_probit_start")
     return out
 
 

@@ -34,23 +34,23 @@ __device__ __forceinline__ void dmma_8x8x4(double& d0, double& d1, double a, dou
 // lane q = (r%8)/2 owns bytes q*8 .. q*8+7, ordered (nb = r/8, e = r%2)
 __host__ __device__ __forceinline__ int count_pos(int r) { return ((r & 7) >> 1) * 8 + (r >> 3) * 2 + (r & 1); }
 
-template <int KB, class Fam, bool WANT_SCORE, bool USE_COUNTS>
-__global__ void __launch_bounds__(BATCH_THREADS, 1)
+template <int KB, class Fam, bool WANT_SCORE, bool USE_COUNTS, int MB>
+__global__ void __launch_bounds__(BATCH_THREADS, (MB == 1) ? 2 : 1)
 batched_kernel(const double* __restrict__ tiles, const unsigned long long n_rows, const unsigned long long n_tiles,
                const int K, const int cols, const double* __restrict__ Bmat, const int P, const int m,
                const unsigned char* __restrict__ counts, const int m_pad, const double4 aux4,
                const int n_rowgroups, double* __restrict__ partials) {
     constexpr int WARPS = BATCH_THREADS / 32;
-    constexpr int MB = BATCH_RC / 8;   // replicate blocks of 8 per warp
+    constexpr int RC = MB * 8;         // replicates per warp (MB blocks of 8)
     constexpr int KS = KB / 4;         // stage-1 k-steps
     constexpr int JB = KB / 8;         // stage-3 column blocks
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, q = lane & 3;
-    const int n_repgroups = (m + WARPS * BATCH_RC - 1) / (WARPS * BATCH_RC);
+    const int n_repgroups = (m + WARPS * RC - 1) / (WARPS * RC);
     const int repgroup = blockIdx.x % n_repgroups;
     const int rowgroup = blockIdx.x / n_repgroups;
     if (rowgroup >= n_rowgroups) return;
-    const int rep0 = (repgroup * WARPS + warp) * BATCH_RC;   // first replicate of this warp
+    const int rep0 = (repgroup * WARPS + warp) * RC;   // first replicate of this warp
     const double aux[4] = {aux4.x, aux4.y, aux4.z, aux4.w};
 
     // loop-invariant A fragments of stage 1: B^T[rep0 + mb*8 + g][ks*4 + q]
@@ -212,8 +212,10 @@ template <int KB, class Fam>
 static cudaError_t launch_fam(const BatchedLaunch& L) {
     const double4 aux = make_double4(L.aux[0], L.aux[1], L.aux[2], L.aux[3]);
 #define APB_GO(S, C)                                                                                          \
-    batched_kernel<KB, Fam, S, C><<<L.grid, BATCH_THREADS, 0, L.stream>>>(L.tiles, L.n_rows, L.n_tiles, L.k, L.cols, \
-        L.B, L.P, L.m, L.counts, L.m_pad, aux, L.n_rowgroups, L.partials)
+    do { if (L.mb == 1) batched_kernel<KB, Fam, S, C, 1><<<L.grid, BATCH_THREADS, 0, L.stream>>>(L.tiles, L.n_rows, L.n_tiles, L.k, L.cols, \
+        L.B, L.P, L.m, L.counts, L.m_pad, aux, L.n_rowgroups, L.partials); \
+    else batched_kernel<KB, Fam, S, C, 2><<<L.grid, BATCH_THREADS, 0, L.stream>>>(L.tiles, L.n_rows, L.n_tiles, L.k, L.cols, \
+        L.B, L.P, L.m, L.counts, L.m_pad, aux, L.n_rowgroups, L.partials); } while (0)
     if (L.want_score) { if (L.counts) APB_GO(true, true); else APB_GO(true, false); }
     else { if (L.counts) APB_GO(false, true); else APB_GO(false, false); }
 #undef APB_GO

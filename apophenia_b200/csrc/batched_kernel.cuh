@@ -5,7 +5,7 @@
 
 namespace apb {
 constexpr int BATCH_THREADS = 256;  // 8 warps, one replicate group each, all on the same tile
-constexpr int BATCH_RC = 16;        // replicates per warp
+constexpr int BATCH_RC_MAX = 16;    // replicates per warp: 8 (two CTAs per SM) or 16 (one)
 struct BatchedLaunch {
     const double* tiles;
     unsigned long long n_rows, n_tiles;
@@ -19,6 +19,7 @@ struct BatchedLaunch {
     double* partials;             // [n_rowgroups][m][1 + KB]
     double* out;                  // [m][1 + KB]: LL, then the score of that replicate
     int grid;
+    int mb;                       // replicate blocks of 8 per warp: 1 or 2
     bool want_score;
     cudaStream_t stream;
 };

@@ -886,6 +886,48 @@ extern "C" double apop_b200_map_sum(apop_data* d, apop_b200_map_fn fn, double p0
     return res;
 }
 
+// ---- prep reductions on the device --------------------------------------
+extern "C" int apop_b200_col_sums(apop_data* d, int mode, double* out) {
+    LOCK;
+    if (!d || !out || mode < 0 || mode > 2) { set_error("apop_b200_col_sums: bad argument"); return 1; }
+    Resident* r = acquire(d);
+    if (!r) return 1;
+    Runtime& R = rt();
+    bool ok = false;
+    if (r->k < 1 || r->k > MAX_K_REG) set_error("apop_b200_col_sums: 1..%d columns", MAX_K_REG);
+    else {
+        const int grid = grid_for(4, r->n_tiles, CELLS_THREADS / 32);
+        if (ensure_partials((size_t)grid * MAX_K_REG)) {
+            time_begin();
+            ok = cuda_ok(colsums_launch(r->tiles, r->n_rows, r->n_tiles, r->k, r->cols, mode, R.d_partials, R.d_ticket,
+                                        R.d_out, grid, R.stream), "column sums launch");
+            time_end_record();
+            R.launches++;
+            ok = ok && reduce_and_fetch(MAX_K_REG);
+            if (ok) { time_collect(); memcpy(out, R.h_out, r->k * sizeof(double)); }
+        }
+    }
+    release(r);
+    return ok ? 0 : 1;
+}
+// probit_prep's start point (model/apop_probit.c:65-80): beta0_j = exp(mean_i ln|x_ij|), zeros skipped
+extern "C" int apop_b200_probit_start(apop_data* d, double* beta0) {
+    LOCK;
+    if (!d || !beta0) { set_error("apop_b200_probit_start: NULL argument"); return 1; }
+    Resident* r = acquire(d);
+    if (!r) return 1;
+    double n, mc, vc;
+    const int k = r->k;
+    const bool okc = global_counts(r, n, mc, vc);
+    const bool keep = !r->transient;
+    release(r);
+    if (!okc) return 1;
+    if (apop_b200_col_sums(d, 0, beta0)) return 1;
+    (void)keep;
+    for (int j = 0; j < k; j++) beta0[j] = (double)expl((long double)beta0[j] / n);
+    return 0;
+}
+
 // ---- generic fused value + gradient ------------------------------------------
 extern "C" double apop_b200_ll_score(apop_b200_family family, apop_data* d, const double* beta, size_t P, double* score) {
     LOCK;
@@ -1024,9 +1066,12 @@ extern "C" int apop_b200_ll_score_batched(apop_b200_family family, apop_data* d,
         if (use_counts && (!r->counts || r->counts_m < m)) { set_error("batched path: no resident resample counts for %zu replicates (call apop_b200_bootstrap_counts)", m); break; }
         if (use_counts && fam == GLM_POISSON_REG) { set_error("batched path: resample counts are not supported for the Poisson regression constant"); break; }
         const int KB = batched_kb(K), NOUT = 1 + KB;
-        const int reps_per_cta = (BATCH_THREADS / 32) * BATCH_RC;
+        static int mb_env = -1;
+        if (mb_env < 0) { const char* e = getenv("APOP_B200_BATCH_MB"); mb_env = (e && e[0] == '2') ? 2 : 1; }
+        const int mb = mb_env, ctas_per_sm = (mb == 1) ? 2 : 1;
+        const int reps_per_cta = (BATCH_THREADS / 32) * mb * 8;
         const int n_repgroups = (int)((m + reps_per_cta - 1) / reps_per_cta);
-        long long n_rowgroups = R.num_sms / n_repgroups;
+        long long n_rowgroups = (long long)R.num_sms * ctas_per_sm / n_repgroups;
         if (n_rowgroups < 1) n_rowgroups = 1;
         if ((unsigned long long)n_rowgroups > r->n_tiles) n_rowgroups = r->n_tiles ? (long long)r->n_tiles : 1;
         BatchedLaunch L;
@@ -1037,7 +1082,7 @@ extern "C" int apop_b200_ll_score_batched(apop_b200_family family, apop_data* d,
         const apop_data* pg = category_page(d);
         if (fam == GLM_LOGIT2 && pg && pg->vector && pg->vector->size >= 2) { L.aux[0] = pg->vector->data[0]; L.aux[1] = pg->vector->data[pg->vector->stride]; }
         L.n_rowgroups = (int)n_rowgroups; L.grid = (int)(n_rowgroups * n_repgroups);
-        L.want_score = score != nullptr; L.stream = R.stream;
+        L.want_score = score != nullptr; L.stream = R.stream; L.mb = mb;
         if (!ensure_partials((size_t)n_rowgroups * m * NOUT)) break;
         L.partials = R.d_partials;
         if (!cuda_ok(cudaMalloc(&dB, P * m * sizeof(double)), "cudaMalloc(B)")) break;

@@ -8,6 +8,7 @@
 // with its validity test (model/apop_poisson.c:14-28,66-73).
 // Bound: HBM (8 bytes per cell, read once).
 #include "cells.cuh"
+#include "fastmath.cuh"
 
 namespace apb {
 
@@ -119,6 +120,79 @@ cudaError_t cells_launch(int mode, const double* tiles, size_t n_rows, size_t n_
     default: return cudaErrorInvalidValue;
     }
 #undef APB_CELLS
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------
+// Per-column sums over the rows: the O(N k) prep reductions either side of the path
+// (SURVEY 8(f) rank 2).  mode 0: sum ln|x| over non-zero cells -- probit_prep's start point
+// exp(mean ln|x_ij|) (model/apop_probit.c:65-80); mode 1: sum x; mode 2: sum x^2.
+// ---------------------------------------------------------------------------------------
+template <int KB>
+__global__ void __launch_bounds__(CELLS_THREADS)
+colsums_kernel(const double* __restrict__ tiles, unsigned long long n_rows, unsigned long long n_tiles, int K,
+               int cols, int mode, double* __restrict__ partials, unsigned int* __restrict__ ticket,
+               double* __restrict__ out) {
+    constexpr int WARPS = CELLS_THREADS / 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned long long gwarp = (unsigned long long)blockIdx.x * WARPS + warp;
+    const unsigned long long nwarps = (unsigned long long)gridDim.x * WARPS;
+    double acc[KB];
+#pragma unroll
+    for (int j = 0; j < KB; j++) acc[j] = 0.0;
+    for (unsigned long long t = gwarp; t < n_tiles; t += nwarps) {
+        const double* base = tiles + t * (unsigned long long)cols * TILE_ROWS + lane;
+        const bool valid = t * TILE_ROWS + lane < n_rows;
+        double x[KB];
+#pragma unroll
+        for (int j = 0; j < KB; j++) x[j] = (j < K) ? ld_stream(base + j * TILE_ROWS) : 0.0;
+#pragma unroll
+        for (int j = 0; j < KB; j++) {
+            double f;
+            if (mode == 0) f = (x[j] != 0.0) ? fm_log(fabs(x[j])) : 0.0;
+            else if (mode == 1) f = x[j];
+            else f = x[j] * x[j];
+            acc[j] += valid ? f : 0.0;
+        }
+    }
+    __shared__ double red[WARPS][KB];
+#pragma unroll
+    for (int j = 0; j < KB; j++) {
+        const double v = warp_sum(acc[j]);
+        if (lane == 0) red[warp][j] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < KB) {
+        double s = 0.0;
+#pragma unroll
+        for (int wv = 0; wv < WARPS; wv++) s += red[wv][threadIdx.x];
+        partials[(size_t)blockIdx.x * KB + threadIdx.x] = s;
+    }
+    __shared__ unsigned int is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if (threadIdx.x < KB) {
+        double s = 0.0, c = 0.0;
+        for (unsigned b = 0; b < gridDim.x; b++) {
+            double e;
+            two_sum(s, __ldcg(partials + (size_t)b * KB + threadIdx.x), s, e);
+            c += e;
+        }
+        out[threadIdx.x] = s + c;
+    }
+    if (threadIdx.x == 0) *ticket = 0;
+}
+
+cudaError_t colsums_launch(const double* tiles, size_t n_rows, size_t n_tiles, int k, int cols, int mode,
+                           double* partials, unsigned int* ticket, double* out, int grid, cudaStream_t st) {
+    if (k <= 8) colsums_kernel<8><<<grid, CELLS_THREADS, 0, st>>>(tiles, n_rows, n_tiles, k, cols, mode, partials, ticket, out);
+    else if (k <= 16) colsums_kernel<16><<<grid, CELLS_THREADS, 0, st>>>(tiles, n_rows, n_tiles, k, cols, mode, partials, ticket, out);
+    else if (k <= 32) colsums_kernel<32><<<grid, CELLS_THREADS, 0, st>>>(tiles, n_rows, n_tiles, k, cols, mode, partials, ticket, out);
+    else return cudaErrorInvalidValue;
     return cudaGetLastError();
 }
 

@@ -88,7 +88,12 @@ static int line_search(mle_info *I, size_t n, double *x, double *f, double *g, c
             if (a - lo.a < 1e-16 * fmax(1.0, lo.a)) break;
             continue;
         }
-        const int armijo_fail = cur.f > f0 + c1 * cur.a * d0 || (lo.a > 0 && cur.f >= lo.f);
+        /* near the optimum the decrease of f drops below its rounding noise (|f| ~ 1e8 at 1e8 rows):
+         * there the sufficient-decrease test is replaced by Hager & Zhang's approximate Wolfe
+         * condition on the directional derivative, (2 delta - 1) d0 >= d(a) >= sigma d0 */
+        const double noise = 1e-14 * fabs(f0);
+        if (fabs(cur.f - f0) <= noise && cur.d >= c2 * d0 && cur.d <= (2 * 0.1 - 1) * d0) { rc = 0; break; }
+        const int armijo_fail = cur.f > f0 + c1 * cur.a * d0 + noise || (lo.a > 0 && cur.f >= lo.f + noise);
         if (armijo_fail) { hi = cur; have_hi = 1; }
         else if (fabs(cur.d) <= -c2 * d0) { rc = 0; break; }
         else if (have_hi) { if (cur.d * (hi.a - lo.a) >= 0) hi = lo; lo = cur; }

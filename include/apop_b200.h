@@ -191,6 +191,13 @@ typedef enum {
 /* part: 'a' all (vector and matrix), 'v' vector only, 'm' matrix only */
 double apop_b200_map_sum(apop_data *d, apop_b200_map_fn fn, double p0, char part);
 
+/* Prep reductions on the resident data (the O(N k) steps either side of the path):
+ * per-column sums, mode 0 = ln|x| over non-zero cells, 1 = x, 2 = x^2; out has k entries.
+ * apop_b200_probit_start is probit_prep's start point exp(mean ln|x_ij|)
+ * (model/apop_probit.c:65-80). */
+int apop_b200_col_sums(apop_data *d, int mode, double *out);
+int apop_b200_probit_start(apop_data *d, double *beta0);
+
 /* OLS normal equations X'X (k*k, row-major) and X'y (k) in one pass
  * (apop_estimate_OLS, model/apop_ols.c:333-334). */
 int apop_b200_ols_gram(apop_data *d, double *xtx, double *xty);

@@ -312,3 +312,15 @@ def test_nist_pontius_through_device_gram(b200):
     for got, want, tol in zip(beta, g["certified_beta"], g["tolerances"]):
         assert abs(got - want) < tol
     ab.unpin(d)
+
+
+def test_prep_reductions_on_device(b200, oracle):
+    """probit_prep's start point and the column sums, reduced on the resident data"""
+    ab = b200
+    X, y, beta = gen_probit_logit_sample(30011, 12, seed=9)
+    X[5, 3] = 0.0; X[77, 11] = 0.0                    # zeros contribute 0 to the mean log
+    d = ab.pin(ab.Data(matrix=X, vector=y))
+    assert np.allclose(ab.probit_start(d, 12), oracle.probit_start(X), rtol=1e-13)
+    assert np.allclose(ab.col_sums(d, 1, 12), X.sum(0), rtol=1e-13, atol=1e-9)
+    assert np.allclose(ab.col_sums(d, 2, 12), (X * X).sum(0), rtol=1e-13)
+    ab.unpin(d)
