@@ -280,7 +280,9 @@ apop_data *apop_bootstrap_cov(apop_data *data, apop_model *model, uint64_t seed,
             double *x = X + r * P, *g = G + r * P, *p = Pd + r * P, *H = Hs + r * P * P, *xt = XT + r * P, *gt = GT + r * P;
             const double ft = -FT[r];
             double pg = 0; for (size_t i = 0; i < P; i++) pg += p[i] * g[i];
-            if (isfinite(ft) && ft <= F[r] + 1e-4 * alpha[r] * pg) {
+            /* the achievable decrease is bounded below by the rounding noise of the sums */
+            const double noise = 1e-14 * fabs(F[r]);
+            if (isfinite(ft) && ft <= F[r] + 1e-4 * alpha[r] * pg + noise) {
                 double sy = 0, yy = 0, s[64], y[64], Hy[64];   /* P <= 32 on the batched path */
                 for (size_t i = 0; i < P; i++) { s[i] = xt[i] - x[i]; y[i] = -gt[i] - g[i]; sy += s[i] * y[i]; yy += y[i] * y[i]; }
                 if (sy > 1e-12 * sqrt(yy)) {
@@ -295,7 +297,8 @@ apop_data *apop_bootstrap_cov(apop_data *data, apop_model *model, uint64_t seed,
                 state[r] = 0;
             } else {
                 alpha[r] *= 0.5;
-                if (alpha[r] < 1e-12) { state[r] = 2; n_done++; } /* no further progress */
+                /* no further measurable progress along this direction: the replicate is done */
+                if (alpha[r] < 1e-12 || alpha[r] * fabs(pg) < noise) { state[r] = 2; n_done++; }
             }
         }
     }

@@ -98,7 +98,61 @@ def cfg_newton(rows=100_000_000, k=32):
             "GBps": rows * (k + 1) * 8 / kms / 1e6, "dfma_TFLOPs": 2.0 * rows * k * (k + 1) / (kms * 1e-3) / 1e12}
 
 
-ALL = {"logit8": cfg_logit8, "bootstrap": cfg_bootstrap, "chains": cfg_chains, "poisson": cfg_poisson, "newton": cfg_newton}
+def _fit_on_synth(fam, s, k, start, method="Newton"):
+    from apophenia_b200 import abi, host
+    h, lib = host.lib(), abi.load_library()
+    m = h.apop_model_copy(host.model_object(fam))
+    abi.check(lib.apop_b200_register(m, fam), "register")
+    m.contents.parameters = h.apop_data_alloc(k, 1, 0)
+    m.contents.data = s.ptr
+    keep = []
+    host.mle_settings(m, method=method, tolerance=1e-10, relative_tolerance=True, max_iterations=200, starting_pt=start, keep=keep)
+    h.apop_maximum_likelihood(s.ptr, m)
+    return m, host.parameters_of(m), keep
+
+
+def cfg_bootstrap_cov(rows=5_000_000, k=20, m=1000):
+    """BASELINE config 4 end to end: apop_bootstrap_cov of a probit fit (counts + lock-step replicate fits)"""
+    from apophenia_b200 import host
+    rng = np.random.default_rng(8)
+    beta = rng.uniform(-1, 1, k)
+    s = ab.synth(ab.PROBIT, rows, k, beta)
+    est, mle, keep = _fit_on_synth(ab.PROBIT, s, k, ab.probit_start(s, k))
+    l0 = ab.launch_count()
+    t0 = time.perf_counter()
+    cov, boots = host.bootstrap_cov(s.ptr, est, iterations=m, seed=8)
+    dt = time.perf_counter() - t0
+    passes = (ab.launch_count() - l0 - 2) // 2
+    H = ab.information(ab.PROBIT, s, mle)
+    want = np.linalg.inv(H)
+    s.free()
+    return {"config": f"apop_bootstrap_cov of probit, {m} replicates on {rows}x{k}", "seconds": dt, "batched_passes": int(passes),
+            "max_rel_dev_of_var_from_inverse_information": float(np.max(np.abs(np.diag(cov) / np.diag(want) - 1))),
+            "mean_abs_bias_of_replicates": float(np.max(np.abs(boots.mean(0) - mle)))}
+
+
+def cfg_metropolis(rows=50_000_000, k=24, m=256, periods=200):
+    """BASELINE config 5: adaptive Metropolis on binary logit, m chains in lock-step"""
+    from apophenia_b200 import host
+    rng = np.random.default_rng(8)
+    beta = rng.uniform(-1, 1, k)
+    s = ab.synth(ab.LOGIT, rows, k, beta)
+    est, mle, keep = _fit_on_synth(ab.LOGIT, s, k, np.zeros(k))
+    sd = np.sqrt(np.diag(np.linalg.inv(ab.information(ab.LOGIT, s, mle))))
+    t0 = time.perf_counter()
+    draws = host.metropolis(s.ptr, est, periods=periods, burnin=0.5, initial_scale=float(sd.mean()) / np.sqrt(k), seed=8, n_chains=m)
+    dt = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    one = host.metropolis(s.ptr, est, periods=periods, burnin=0.5, initial_scale=float(sd.mean()) / np.sqrt(k), seed=8, n_chains=1)
+    dt1 = time.perf_counter() - t0
+    s.free()
+    acc = float(np.mean(np.any(np.diff(draws, axis=1) != 0, axis=2)))
+    return {"config": f"metropolis on logit, {m} chains x {periods} periods over {rows}x{k}", "seconds": dt,
+            "ms_per_step_all_chains": 1e3 * dt / periods, "chain_steps_per_s": m * periods / dt,
+            "single_chain_seconds": dt1, "single_chain_steps_per_s": periods / dt1, "acceptance_rate": acc}
+
+
+ALL = {"bootstrap_cov": cfg_bootstrap_cov, "metropolis": cfg_metropolis, "logit8": cfg_logit8, "bootstrap": cfg_bootstrap, "chains": cfg_chains, "poisson": cfg_poisson, "newton": cfg_newton}
 
 if __name__ == "__main__":
     ab.init(0)
