@@ -116,6 +116,7 @@ SIGNATURES = {
     "apop_b200_poisson_reg_score": (None, [_PD, _PV, _PM]),
     "apop_b200_map_sum": (C.c_double, [_PD, C.c_int, C.c_double, C.c_char]),
     "apop_b200_ols_gram": (C.c_int, [_PD, _dp, _dp]),
+    "apop_b200_dot": (C.c_int, [_PD, _dp, C.c_size_t, C.c_size_t, _dp]),
     "apop_b200_col_sums": (C.c_int, [_PD, C.c_int, _dp]),
     "apop_b200_probit_start": (C.c_int, [_PD, _dp]),
     "apop_b200_ll_score": (C.c_double, [C.c_int, _PD, _dp, C.c_size_t, _dp]),

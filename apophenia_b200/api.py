@@ -18,7 +18,7 @@ __all__ = ["init", "finalize", "pin", "unpin", "invalidate", "is_pinned", "log_l
            "pass_timer", "probit_model", "logit_model", "vector_model", "Data", "Model", "B200Error",
            "PROBIT", "LOGIT", "POISSON", "NORMAL", "OLS", "POISSON_REG", "comm_init_from_torch",
            "comm_finalize", "set_auto_pin", "last_error", "information", "ols_gram",
-           "col_sums", "probit_start", "ll_score_batched", "bootstrap_counts", "counts_download",
+           "dot", "col_sums", "probit_start", "ll_score_batched", "bootstrap_counts", "counts_download",
            "MAP_IDENTITY", "MAP_DEV", "MAP_DEV2", "MAP_POISSON", "MAP_LOG", "MAP_EXP"]
 
 _dp = C.POINTER(C.c_double)
@@ -146,6 +146,17 @@ def counts_download(d, m, n_rows):
     out = np.zeros((n_rows, m), dtype=np.uint8)
     abi.check(_lib().apop_b200_counts_download(_ptr(d), int(m), out.ctypes.data_as(C.POINTER(C.c_ubyte))),
               "apop_b200_counts_download")
+    return out
+
+
+def dot(d, B, n_rows):
+    """apop_dot(d, parameters): X.B as an (n_rows, c) array"""
+    B = np.ascontiguousarray(B, dtype=np.float64)
+    if B.ndim == 1:
+        B = B.reshape(-1, 1)
+    out = np.zeros((n_rows, B.shape[1]))
+    abi.check(_lib().apop_b200_dot(_ptr(d), B.ctypes.data_as(_dp), B.shape[0], B.shape[1], out.ctypes.data_as(_dp)),
+              "apop_b200_dot")
     return out
 
 

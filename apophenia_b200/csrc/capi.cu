@@ -886,6 +886,42 @@ extern "C" double apop_b200_map_sum(apop_data* d, apop_b200_map_fn fn, double p0
     return res;
 }
 
+// ---- apop_dot(d, parameters): the N x c index X.B, copied back in chunks ----------------------
+extern "C" int apop_b200_dot(apop_data* d, const double* B, size_t k, size_t c, double* out) {
+    LOCK;
+    if (!d || !B || !out || !c) { set_error("apop_b200_dot: NULL argument"); return 1; }
+    Resident* r = acquire(d);
+    if (!r) return 1;
+    Runtime& R = rt();
+    bool ok = false;
+    double *dB = nullptr, *dOut = nullptr;
+    do {
+        if ((size_t)r->k != k || r->k < 1 || r->k > MAX_K_REG) {
+            // the reference's dimension error: error char 'd' (apop_linear_algebra.m4.c:347-349)
+            set_error("apop_b200_dot: the data has %d columns, the parameters %zu rows", r->k, k);
+            d->error = 'd';
+            break;
+        }
+        size_t chunk = ((size_t)16 << 20) / c;   // <= 128 MB of output per chunk
+        if (chunk > r->n_rows) chunk = r->n_rows;
+        if (!chunk) { ok = true; break; }
+        if (!cuda_ok(cudaMalloc(&dB, k * c * sizeof(double)), "cudaMalloc") || !cuda_ok(cudaMalloc(&dOut, chunk * c * sizeof(double)), "cudaMalloc")) break;
+        if (!cuda_ok(cudaMemcpyAsync(dB, B, k * c * sizeof(double), cudaMemcpyHostToDevice, R.stream), "H2D B")) break;
+        ok = true;
+        for (size_t r0 = 0; ok && r0 < r->n_rows; r0 += chunk) {
+            const size_t rows = (r->n_rows - r0 < chunk) ? r->n_rows - r0 : chunk;
+            ok = cuda_ok(xbeta_launch(r->tiles, r0, rows, r->k, r->cols, (int)c, dB, dOut, R.stream), "xbeta launch") &&
+                 cuda_ok(cudaMemcpyAsync(out + r0 * c, dOut, rows * c * sizeof(double), cudaMemcpyDeviceToHost, R.stream), "D2H") &&
+                 cuda_ok(cudaStreamSynchronize(R.stream), "sync");
+            R.launches++;
+        }
+    } while (0);
+    if (dB) cudaFree(dB);
+    if (dOut) cudaFree(dOut);
+    release(r);
+    return ok ? 0 : 1;
+}
+
 // ---- prep reductions on the device --------------------------------------
 extern "C" int apop_b200_col_sums(apop_data* d, int mode, double* out) {
     LOCK;

@@ -198,4 +198,39 @@ cudaError_t synth_fill(int family, size_t n_rows, int k, int cols, int ncat, con
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------
+// apop_dot(d, parameters) (apop_linear_algebra.m4.c:424-448): the materialised N x c
+// product X.B that the reference forms before every map (and that ols_predict /
+// multilogit_expected return, model/apop_ols.c:359-366, model/apop_probit.c:166-199).  The
+// fused kernels never need it; it exists for callers that want the fitted index itself.
+// ---------------------------------------------------------------------------------------
+template <int KB>
+__global__ void __launch_bounds__(128)
+xbeta_kernel(const double* __restrict__ tiles, unsigned long long row0, unsigned long long rows, int K, int cols, int C1,
+             const double* __restrict__ B, double* __restrict__ out) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows) return;
+    const unsigned long long r = row0 + i;
+    const double* base = tiles + (r / TILE_ROWS) * (unsigned long long)cols * TILE_ROWS + (r % TILE_ROWS);
+    double x[KB];
+#pragma unroll
+    for (int j = 0; j < KB; j++) x[j] = (j < K) ? __ldcs(base + j * TILE_ROWS) : 0.0;
+    for (int c = 0; c < C1; c++) {
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < KB; j++) s = fma(x[j], (j < K) ? __ldg(B + j * C1 + c) : 0.0, s);
+        out[i * C1 + c] = s;
+    }
+}
+cudaError_t xbeta_launch(const double* tiles, size_t row0, size_t rows, int k, int cols, int c1, const double* B,
+                         double* out, cudaStream_t st) {
+    if (!rows) return cudaSuccess;
+    const unsigned grid = (unsigned)((rows + 127) / 128);
+    if (k <= 8) xbeta_kernel<8><<<grid, 128, 0, st>>>(tiles, row0, rows, k, cols, c1, B, out);
+    else if (k <= 16) xbeta_kernel<16><<<grid, 128, 0, st>>>(tiles, row0, rows, k, cols, c1, B, out);
+    else if (k <= 32) xbeta_kernel<32><<<grid, 128, 0, st>>>(tiles, row0, rows, k, cols, c1, B, out);
+    else return cudaErrorInvalidValue;
+    return cudaGetLastError();
+}
+
 }  // namespace apb

@@ -19,4 +19,6 @@ cudaError_t synth_fill(int family, size_t n_rows, int k, int cols, int ncat, con
                        unsigned long long seed, unsigned long long row_offset, double* tiles,
                        cudaStream_t st);
 
+cudaError_t xbeta_launch(const double* tiles, size_t row0, size_t rows, int k, int cols, int c1, const double* B,
+                         double* out, cudaStream_t st);
 }  // namespace apb

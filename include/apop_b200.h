@@ -191,6 +191,12 @@ typedef enum {
 /* part: 'a' all (vector and matrix), 'v' vector only, 'm' matrix only */
 double apop_b200_map_sum(apop_data *d, apop_b200_map_fn fn, double p0, char part);
 
+/* apop_dot(d, parameters) (apop_linear_algebra.m4.c:424-448): the N x c index X.B, row-major
+ * into a caller buffer; B is k x c row-major (parameters->matrix).  On a dimension mismatch
+ * d->error = 'd' like the reference.  This is also ols_predict / the index of
+ * multilogit_expected (model/apop_ols.c:359-366, model/apop_probit.c:166-199). */
+int apop_b200_dot(apop_data *d, const double *B, size_t k, size_t c, double *out);
+
 /* Prep reductions on the resident data (the O(N k) steps either side of the path):
  * per-column sums, mode 0 = ln|x| over non-zero cells, 1 = x, 2 = x^2; out has k entries.
  * apop_b200_probit_start is probit_prep's start point exp(mean ln|x_ij|)

@@ -324,3 +324,23 @@ def test_prep_reductions_on_device(b200, oracle):
     assert np.allclose(ab.col_sums(d, 1, 12), X.sum(0), rtol=1e-13, atol=1e-9)
     assert np.allclose(ab.col_sums(d, 2, 12), (X * X).sum(0), rtol=1e-13)
     ab.unpin(d)
+
+
+def test_dot_matches_reference_dgemm(b200):
+    """apop_dot (tests/test_apop.c:527-550 checks exact equality of small products; here the
+    index X.B against numpy, and the 'd' error char on a dimension mismatch)"""
+    ab = b200
+    rng = np.random.default_rng(3)
+    X = rng.uniform(-1, 1, (10007, 9)); y = np.zeros(10007)
+    d = ab.pin(ab.Data(matrix=X, vector=y))
+    for c in (1, 3):
+        B = rng.uniform(-1, 1, (9, c))
+        got = ab.dot(d, B, 10007)
+        assert np.max(np.abs(got - X @ B)) < 1e-14
+    Xi = np.arange(12.0).reshape(4, 3)
+    di = ab.pin(ab.Data(matrix=Xi, vector=np.zeros(4)))
+    assert np.array_equal(ab.dot(di, np.array([1.0, 2.0, 3.0]), 4).ravel(), Xi @ [1.0, 2.0, 3.0])  # exact on small integers
+    with pytest.raises(ab.B200Error):
+        ab.dot(d, np.ones((5, 1)), 10007)
+    assert d.struct.error == b"d"
+    ab.unpin(d); ab.unpin(di)
