@@ -94,6 +94,9 @@ SIGNATURES = {
     "apop_b200_comm_init": (C.c_int, [C.c_int, C.c_int, C.c_void_p]),
     "apop_b200_comm_finalize": (C.c_int, []),
     "apop_b200_comm_size": (C.c_int, []),
+    "apop_b200_comm_p2p_handle": (C.c_int, [C.c_int, C.c_void_p]),
+    "apop_b200_comm_p2p_init": (C.c_int, [C.c_int, C.c_int, C.c_void_p]),
+    "apop_b200_comm_p2p_active": (C.c_int, []),
     "apop_b200_pin": (C.c_int, [_PD]),
     "apop_b200_unpin": (C.c_int, [_PD]),
     "apop_b200_invalidate": (C.c_int, [_PD]),

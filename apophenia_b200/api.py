@@ -264,6 +264,20 @@ def comm_init_from_torch():
     raw = bytes(t.cpu().tolist())
     buf2 = (C.c_char * 128).from_buffer_copy(raw)
     abi.check(lib.apop_b200_comm_init(world, rank, C.cast(buf2, C.c_void_p)), "apop_b200_comm_init")
+    # fused allreduce over NVLink peer memory (default; APOP_B200_ALLREDUCE=nccl keeps NCCL only)
+    import os
+    if os.environ.get("APOP_B200_ALLREDUCE", "p2p") != "nccl" and world <= 8:
+        hbuf = (C.c_char * 64)()
+        abi.check(lib.apop_b200_comm_p2p_handle(world, C.cast(hbuf, C.c_void_p)), "apop_b200_comm_p2p_handle")
+        mine = torch.tensor(list(bytes(hbuf)), dtype=torch.uint8)
+        if dist.get_backend() == "nccl":
+            mine = mine.cuda()
+        allh = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allh, mine)
+        raw = b"".join(bytes(t.cpu().tolist()) for t in allh)
+        hall = (C.c_char * (64 * world)).from_buffer_copy(raw)
+        abi.check(lib.apop_b200_comm_p2p_init(world, rank, C.cast(hall, C.c_void_p)), "apop_b200_comm_p2p_init")
+        dist.barrier()
 
 
 def comm_finalize():

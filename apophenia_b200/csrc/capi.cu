@@ -99,7 +99,12 @@ extern "C" int apop_b200_init(int device) {
     if (!cuda_ok(cudaMalloc(&R.d_ticket, 64), "cudaMalloc")) return 1;
     cudaMemset(R.d_ticket, 0, 64);
     if (!cuda_ok(cudaMalloc(&R.d_out, OUT_CAP * sizeof(double)), "cudaMalloc")) return 1;
-    if (!cuda_ok(cudaHostAlloc(&R.h_out, OUT_CAP * sizeof(double), cudaHostAllocDefault), "cudaHostAlloc")) return 1;
+    if (!cuda_ok(cudaHostAlloc(&R.h_out, OUT_CAP * sizeof(double), cudaHostAllocMapped), "cudaHostAlloc")) return 1;
+    if (!cuda_ok(cudaHostGetDevicePointer(&R.h_out_dev, R.h_out, 0), "cudaHostGetDevicePointer")) return 1;
+    if (!cuda_ok(cudaHostAlloc(&R.h_err, 64, cudaHostAllocMapped), "cudaHostAlloc")) return 1;
+    *R.h_err = 0;
+    if (!cuda_ok(cudaHostGetDevicePointer(&R.h_err_dev, R.h_err, 0), "cudaHostGetDevicePointer")) return 1;
+    if (!cuda_ok(cudaMalloc(&R.d_vals, 64 * sizeof(double)), "cudaMalloc")) return 1;
     R.ready = true;
     R.err.clear();
     return 0;
@@ -126,6 +131,8 @@ extern "C" void apop_b200_finalize(void) {
     cudaFree(R.d_ticket);
     cudaFree(R.d_out);
     cudaFreeHost(R.h_out);
+    cudaFreeHost(R.h_err);
+    cudaFree(R.d_vals);
     cudaEventDestroy(R.ev0);
     cudaEventDestroy(R.ev1);
     cudaStreamDestroy(R.stream);
@@ -196,15 +203,89 @@ extern "C" int apop_b200_comm_finalize(void) {
         R.nccl.CommDestroy(R.comm);
         R.comm = nullptr;
     }
+    if (R.p2p_active) {
+        for (int p = 0; p < R.nranks; p++)
+            if (p != R.rank && R.p2p_inbox[p]) cudaIpcCloseMemHandle(R.p2p_inbox[p]);
+        R.p2p_active = false;
+    }
+    if (R.p2p_local) { cudaFree(R.p2p_local); R.p2p_local = nullptr; }
     R.nranks = 1;
     R.rank = 0;
     return 0;
 }
 extern "C" int apop_b200_comm_size(void) { return rt().nranks; }
 
-// sum `n` doubles at d_out across ranks (no-op on one rank), bring them to h_out
-static bool reduce_and_fetch(size_t n) {
+// ---- fused allreduce over NVLink peer memory ------------------------------------------------
+// Each rank allocates one buffer [2][nranks][slot] doubles + [2][nranks] flags, exports it with
+// cudaIpcGetMemHandle (64 bytes, carried to the peers by the host program like the NCCL id), and
+// maps every peer's buffer.  From then on the reduction kernels exchange their result vectors
+// themselves (common.cuh: grid_finalize); NCCL stays for the large batched outputs.
+static const int P2P_SLOT = 1088;   // >= the widest fused result (32 x 33 information matrix)
+static size_t p2p_bytes(int nranks) { return (size_t)2 * nranks * P2P_SLOT * sizeof(double) + (size_t)2 * nranks * sizeof(unsigned long long); }
+extern "C" int apop_b200_comm_p2p_handle(int nranks, void* handle64) {
+    LOCK;
+    if (!require_ready()) return 1;
     Runtime& R = rt();
+    if (nranks < 2 || nranks > P2P_MAX_RANKS) { set_error("fused allreduce: 2..%d ranks", P2P_MAX_RANKS); return 1; }
+    cudaSetDevice(R.device);
+    if (R.p2p_local) { cudaFree(R.p2p_local); R.p2p_local = nullptr; }
+    if (!cuda_ok(cudaMalloc(&R.p2p_local, p2p_bytes(nranks)), "cudaMalloc(p2p inbox)")) return 1;
+    cudaMemset(R.p2p_local, 0, p2p_bytes(nranks));
+    cudaDeviceSynchronize();
+    cudaIpcMemHandle_t h;
+    if (!cuda_ok(cudaIpcGetMemHandle(&h, R.p2p_local), "cudaIpcGetMemHandle")) return 1;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    memcpy(handle64, &h, 64);
+    return 0;
+}
+extern "C" int apop_b200_comm_p2p_init(int nranks, int rank, const void* handles) {
+    LOCK;
+    Runtime& R = rt();
+    if (!R.p2p_local || nranks != R.nranks || rank != R.rank) { set_error("fused allreduce: call apop_b200_comm_init and apop_b200_comm_p2p_handle first"); return 1; }
+    cudaSetDevice(R.device);
+    for (int p = 0; p < nranks; p++) {
+        void* base = R.p2p_local;
+        if (p != rank) {
+            cudaIpcMemHandle_t h;
+            memcpy(&h, (const char*)handles + 64 * p, 64);
+            if (!cuda_ok(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle")) return 1;
+        }
+        R.p2p_inbox[p] = (double*)base;
+        R.p2p_flags[p] = (unsigned long long*)((char*)base + (size_t)2 * nranks * P2P_SLOT * sizeof(double));
+    }
+    R.p2p_slot = P2P_SLOT;
+    R.p2p_seq = 0;
+    R.p2p_active = true;
+    return 0;
+}
+extern "C" int apop_b200_comm_p2p_active(void) { return rt().p2p_active ? 1 : 0;}
+
+// The context the last CTA of a reduction kernel gets: where to publish, and -- with the fused
+// allreduce active -- the peers' inboxes.  Without it on several ranks the kernel only writes
+// d_out and NCCL sums afterwards.
+static FinalizeCtx make_fin(int nout) {
+    Runtime& R = rt();
+    FinalizeCtx f;
+    memset(&f, 0, sizeof f);
+    f.nranks = 1;
+    f.spin_limit = 40000000ull;   // ~10 s of 64 ns sleeps + loads, then the error flag
+    f.err = R.h_err_dev;
+    if (R.nranks > 1 && R.p2p_active && nout <= R.p2p_slot) {
+        f.nranks = R.nranks; f.rank = R.rank; f.seq = ++R.p2p_seq; f.slot = R.p2p_slot;
+        for (int p = 0; p < R.nranks; p++) { f.inbox[p] = R.p2p_inbox[p]; f.flags[p] = R.p2p_flags[p]; }
+        f.host_out = R.h_out_dev;
+    } else if (R.nranks <= 1)
+        f.host_out = R.h_out_dev;
+    return f;
+}
+// complete a reduction launched with `fin`: `n` doubles, summed over all ranks, end up in h_out
+static bool reduce_and_fetch(size_t n, const FinalizeCtx& fin) {
+    Runtime& R = rt();
+    if (fin.host_out) {   // the kernel published (and, with peers, exchanged) the result itself
+        if (!cuda_ok(cudaStreamSynchronize(R.stream), "stream sync")) return false;
+        if (*R.h_err) { *R.h_err = 0; return set_error("fused allreduce: a peer rank never arrived (sequence %llu)", fin.seq); }
+        return true;
+    }
     if (R.comm && R.nranks > 1)
         if (!nccl_ok(R.nccl.AllReduce(R.d_out, R.d_out, n, /*ncclDouble*/ 8, /*ncclSum*/ 0, R.comm, R.stream),
                      "ncclAllReduce"))
@@ -212,15 +293,18 @@ static bool reduce_and_fetch(size_t n) {
     if (!cuda_ok(cudaMemcpyAsync(R.h_out, R.d_out, n * sizeof(double), cudaMemcpyDeviceToHost, R.stream), "D2H")) return false;
     return cuda_ok(cudaStreamSynchronize(R.stream), "stream sync");
 }
-// sum one host double across ranks
-static bool allreduce_scalar(double* v) {
+// sum host doubles across ranks (n <= 64); result back in v
+static bool allreduce_host(double* v, int n) {
     Runtime& R = rt();
-    if (!(R.comm && R.nranks > 1)) return true;
-    if (!cuda_ok(cudaMemcpyAsync(R.d_out, v, sizeof(double), cudaMemcpyHostToDevice, R.stream), "H2D")) return false;
-    if (!reduce_and_fetch(1)) return false;
-    *v = R.h_out[0];
+    if (R.nranks <= 1) return true;
+    if (!cuda_ok(cudaMemcpyAsync(R.d_vals, v, n * sizeof(double), cudaMemcpyHostToDevice, R.stream), "H2D")) return false;
+    const FinalizeCtx fin = make_fin(n);
+    if (!cuda_ok(exchange_launch(R.d_vals, n, R.d_ticket, R.d_out, R.stream, fin), "exchange launch")) return false;
+    if (!reduce_and_fetch(n, fin)) return false;
+    memcpy(v, R.h_out, n * sizeof(double));
     return true;
 }
+static bool allreduce_scalar(double* v) { return allreduce_host(v, 1); }
 
 // --------------------------------------------------------------------------
 //  residency
@@ -475,6 +559,7 @@ static bool eval_glm(Resident* r, GlmFam fam, const double* beta, size_t P, cons
     L.grid = grid_for(bps, r->n_tiles, GLM_THREADS / 32);
     if (!ensure_partials((size_t)L.grid * NOUT)) return false;
     L.partials = R.d_partials; L.ticket = R.d_ticket; L.out = R.d_out; L.stream = R.stream;
+    L.fin = make_fin(NOUT);
     GlmParams prm;
     memset(&prm, 0, sizeof prm);
     memcpy(prm.beta, beta, P * sizeof(double));
@@ -483,7 +568,7 @@ static bool eval_glm(Resident* r, GlmFam fam, const double* beta, size_t P, cons
     if (!cuda_ok(glm_launch(fam, K, has_w, L, prm), "glm kernel launch")) return false;
     time_end_record();
     R.launches++;
-    if (!reduce_and_fetch(NOUT)) return false;
+    if (!reduce_and_fetch(NOUT, L.fin)) return false;
     time_collect();
     out.assign(R.h_out, R.h_out + NOUT);
     r->memo_valid = true; r->memo_fam = (int)fam; r->memo_beta = key; r->memo_out = out;
@@ -494,12 +579,13 @@ static bool eval_cells(Resident* r, int mode, double p0, double* out5, bool matr
     Runtime& R = rt();
     const int grid = grid_for(8, r->n_tiles, CELLS_THREADS / 32);
     if (!ensure_partials((size_t)grid * CELLS_NOUT)) return false;
+    const FinalizeCtx fin = make_fin(CELLS_NOUT);
     time_begin();
     if (!cuda_ok(cells_launch(mode, r->tiles, r->n_rows, r->n_tiles, matrix ? r->k : 0, r->has_y ? r->k : -1, r->cols, p0, R.d_partials,
-                              R.d_ticket, R.d_out, grid, R.stream), "cells kernel launch")) return false;
+                              R.d_ticket, R.d_out, grid, R.stream, fin), "cells kernel launch")) return false;
     time_end_record();
     R.launches++;
-    if (!reduce_and_fetch(CELLS_NOUT)) return false;
+    if (!reduce_and_fetch(CELLS_NOUT, fin)) return false;
     time_collect();
     memcpy(out5, R.h_out, CELLS_NOUT * sizeof(double));
     return true;
@@ -624,6 +710,7 @@ static bool eval_logit(Resident* r, const std::vector<double>& B, size_t C1, con
     L.grid = grid_for(bps, r->n_tiles, LOGIT_THREADS / 32);
     if (!ensure_partials((size_t)L.grid * NOUT)) return false;
     L.partials = R.d_partials; L.ticket = R.d_ticket; L.out = R.d_out; L.stream = R.stream;
+    L.fin = make_fin(NOUT);
     LogitParams prm;
     memset(&prm, 0, sizeof prm);
     memcpy(prm.B, B.data(), B.size() * sizeof(double));
@@ -632,7 +719,7 @@ static bool eval_logit(Resident* r, const std::vector<double>& B, size_t C1, con
     if (!cuda_ok(logit_launch((int)C1, L, prm), "logit kernel launch")) return false;
     time_end_record();
     R.launches++;
-    if (!reduce_and_fetch(NOUT)) return false;
+    if (!reduce_and_fetch(NOUT, L.fin)) return false;
     time_collect();
     out.assign(R.h_out, R.h_out + 1 + (size_t)K * C1);
     r->memo_valid = true; r->memo_fam = 200 + (int)C1; r->memo_beta = key; r->memo_out = out;
@@ -934,12 +1021,13 @@ extern "C" int apop_b200_col_sums(apop_data* d, int mode, double* out) {
     else {
         const int grid = grid_for(4, r->n_tiles, CELLS_THREADS / 32);
         if (ensure_partials((size_t)grid * MAX_K_REG)) {
+            const FinalizeCtx fin = make_fin(MAX_K_REG);
             time_begin();
             ok = cuda_ok(colsums_launch(r->tiles, r->n_rows, r->n_tiles, r->k, r->cols, mode, R.d_partials, R.d_ticket,
-                                        R.d_out, grid, R.stream), "column sums launch");
+                                        R.d_out, grid, R.stream, fin), "column sums launch");
             time_end_record();
             R.launches++;
-            ok = ok && reduce_and_fetch(MAX_K_REG);
+            ok = ok && reduce_and_fetch(MAX_K_REG, fin);
             if (ok) { time_collect(); memcpy(out, R.h_out, r->k * sizeof(double)); }
         }
     }
@@ -1016,6 +1104,7 @@ static bool eval_xtwx(Resident* r, int mode, const double* beta, const double* a
     L.grid = grid_for(bps, r->n_tiles, XTWX_THREADS / 32);
     if (!ensure_partials((size_t)L.grid * NOUT)) return false;
     L.partials = R.d_partials; L.ticket = R.d_ticket; L.out = R.d_out; L.stream = R.stream;
+    L.fin = make_fin(NOUT);
     XtwxParams prm;
     memset(&prm, 0, sizeof prm);
     if (beta) memcpy(prm.beta, beta, K * sizeof(double));
@@ -1024,7 +1113,7 @@ static bool eval_xtwx(Resident* r, int mode, const double* beta, const double* a
     if (!cuda_ok(xtwx_launch(mode, L, prm), "X'WX kernel launch")) return false;
     time_end_record();
     R.launches++;
-    if (!reduce_and_fetch(NOUT)) return false;
+    if (!reduce_and_fetch(NOUT, L.fin)) return false;
     time_collect();
     out.assign((size_t)K * (K + 1), 0.0);
     for (int j = 0; j < K; j++) {
@@ -1190,10 +1279,9 @@ extern "C" int apop_b200_bootstrap_counts(apop_data* d, size_t m, uint64_t seed)
         // exclusive prefix of the shard sizes = this rank's first global row
         std::vector<double> sizes(R.nranks, 0.0);
         sizes[R.rank] = (double)r->n_rows;
-        if (!cuda_ok(cudaMemcpyAsync(R.d_out, sizes.data(), R.nranks * sizeof(double), cudaMemcpyHostToDevice, R.stream), "H2D")) return 1;
-        if (!reduce_and_fetch(R.nranks)) return 1;
+        if (!allreduce_host(sizes.data(), R.nranks)) return 1;
         n_global = 0;
-        for (int q = 0; q < R.nranks; q++) { if (q < R.rank) offset += R.h_out[q]; n_global += R.h_out[q]; }
+        for (int q = 0; q < R.nranks; q++) { if (q < R.rank) offset += sizes[q]; n_global += sizes[q]; }
     }
     if (!cuda_ok(bootstrap_counts_launch(r->counts, r->n_rows, (size_t)offset, (size_t)n_global, (int)m, (int)m_pad, seed, R.stream), "bootstrap counts") ||
         !cuda_ok(cudaStreamSynchronize(R.stream), "counts sync")) return 1;

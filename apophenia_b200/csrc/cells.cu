@@ -37,7 +37,7 @@ template <int MODE>
 __global__ void __launch_bounds__(CELLS_THREADS)
 cells_kernel(const double* __restrict__ tiles, unsigned long long n_rows, unsigned long long n_tiles,
              int k, int ycol, int cols, double p0, double* __restrict__ partials,
-             unsigned int* __restrict__ ticket, double* __restrict__ out) {
+             unsigned int* __restrict__ ticket, double* __restrict__ out, const __grid_constant__ FinalizeCtx fin) {
     constexpr int WARPS = CELLS_THREADS / 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned long long gwarp = (unsigned long long)blockIdx.x * WARPS + warp;
@@ -84,32 +84,16 @@ cells_kernel(const double* __restrict__ tiles, unsigned long long n_rows, unsign
         for (int wv = 0; wv < WARPS; wv++) s += red[wv][threadIdx.x];
         partials[(size_t)blockIdx.x * CELLS_NOUT + threadIdx.x] = s;
     }
-    __shared__ unsigned int is_last;
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence();
-    if (threadIdx.x < CELLS_NOUT) {
-        double s = 0.0, c = 0.0;
-        for (unsigned b = 0; b < gridDim.x; b++) {
-            double e;
-            two_sum(s, __ldcg(partials + (size_t)b * CELLS_NOUT + threadIdx.x), s, e);
-            c += e;
-        }
-        out[threadIdx.x] = s + c;
-    }
-    if (threadIdx.x == 0) *ticket = 0;
+    grid_finalize(partials, CELLS_NOUT, ticket, out, fin, &red[0][0]);
 }
 
 cudaError_t cells_launch(int mode, const double* tiles, size_t n_rows, size_t n_tiles, int k,
                          int ycol, int cols, double p0, double* partials, unsigned int* ticket,
-                         double* out, int grid, cudaStream_t st) {
+                         double* out, int grid, cudaStream_t st, const FinalizeCtx& fin) {
 #define APB_CELLS(M)                                                                          \
     case M:                                                                                   \
         cells_kernel<M><<<grid, CELLS_THREADS, 0, st>>>(tiles, n_rows, n_tiles, k, ycol,         \
-                                                        cols, p0, partials, ticket, out);     \
+                                                        cols, p0, partials, ticket, out, fin); \
         break;
     switch (mode) {
         APB_CELLS(CELLS_IDENTITY)
@@ -132,7 +116,7 @@ template <int KB>
 __global__ void __launch_bounds__(CELLS_THREADS)
 colsums_kernel(const double* __restrict__ tiles, unsigned long long n_rows, unsigned long long n_tiles, int K,
                int cols, int mode, double* __restrict__ partials, unsigned int* __restrict__ ticket,
-               double* __restrict__ out) {
+               double* __restrict__ out, const __grid_constant__ FinalizeCtx fin) {
     constexpr int WARPS = CELLS_THREADS / 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned long long gwarp = (unsigned long long)blockIdx.x * WARPS + warp;
@@ -168,31 +152,27 @@ colsums_kernel(const double* __restrict__ tiles, unsigned long long n_rows, unsi
         for (int wv = 0; wv < WARPS; wv++) s += red[wv][threadIdx.x];
         partials[(size_t)blockIdx.x * KB + threadIdx.x] = s;
     }
-    __shared__ unsigned int is_last;
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence();
-    if (threadIdx.x < KB) {
-        double s = 0.0, c = 0.0;
-        for (unsigned b = 0; b < gridDim.x; b++) {
-            double e;
-            two_sum(s, __ldcg(partials + (size_t)b * KB + threadIdx.x), s, e);
-            c += e;
-        }
-        out[threadIdx.x] = s + c;
-    }
-    if (threadIdx.x == 0) *ticket = 0;
+    grid_finalize(partials, KB, ticket, out, fin, &red[0][0]);
 }
 
 cudaError_t colsums_launch(const double* tiles, size_t n_rows, size_t n_tiles, int k, int cols, int mode,
-                           double* partials, unsigned int* ticket, double* out, int grid, cudaStream_t st) {
-    if (k <= 8) colsums_kernel<8><<<grid, CELLS_THREADS, 0, st>>>(tiles, n_rows, n_tiles, k, cols, mode, partials, ticket, out);
-    else if (k <= 16) colsums_kernel<16><<<grid, CELLS_THREADS, 0, st>>>(tiles, n_rows, n_tiles, k, cols, mode, partials, ticket, out);
-    else if (k <= 32) colsums_kernel<32><<<grid, CELLS_THREADS, 0, st>>>(tiles, n_rows, n_tiles, k, cols, mode, partials, ticket, out);
+                           double* partials, unsigned int* ticket, double* out, int grid, cudaStream_t st, const FinalizeCtx& fin) {
+    if (k <= 8) colsums_kernel<8><<<grid, CELLS_THREADS, 0, st>>>(tiles, n_rows, n_tiles, k, cols, mode, partials, ticket, out, fin);
+    else if (k <= 16) colsums_kernel<16><<<grid, CELLS_THREADS, 0, st>>>(tiles, n_rows, n_tiles, k, cols, mode, partials, ticket, out, fin);
+    else if (k <= 32) colsums_kernel<32><<<grid, CELLS_THREADS, 0, st>>>(tiles, n_rows, n_tiles, k, cols, mode, partials, ticket, out, fin);
     else return cudaErrorInvalidValue;
+    return cudaGetLastError();
+}
+
+// a device vector summed across ranks with the same tail (for host-side scalars)
+__global__ void __launch_bounds__(128)
+exchange_kernel(const double* __restrict__ vals, int n, unsigned int* __restrict__ ticket, double* __restrict__ out,
+                const __grid_constant__ FinalizeCtx fin) {
+    extern __shared__ double sc[];
+    grid_finalize(vals, n, ticket, out, fin, sc);
+}
+cudaError_t exchange_launch(const double* vals, int n, unsigned int* ticket, double* out, cudaStream_t st, const FinalizeCtx& fin) {
+    exchange_kernel<<<1, 128, n * sizeof(double), st>>>(vals, n, ticket, out, fin);
     return cudaGetLastError();
 }
 

@@ -9,8 +9,10 @@ constexpr int CELLS_THREADS = 256;
 constexpr int CELLS_NOUT = 5;  // matrix s0, s1; vector s0, s1; count of -inf cells
 cudaError_t cells_launch(int mode, const double* tiles, size_t n_rows, size_t n_tiles, int k,
                          int ycol, int cols, double p0, double* partials, unsigned int* ticket,
-                         double* out, int grid, cudaStream_t st);
+                         double* out, int grid, cudaStream_t st, const FinalizeCtx& fin);
 // per-column sums (mode 0: ln|x| over non-zero cells, 1: x, 2: x^2); out has 32 slots
 cudaError_t colsums_launch(const double* tiles, size_t n_rows, size_t n_tiles, int k, int cols, int mode,
-                           double* partials, unsigned int* ticket, double* out, int grid, cudaStream_t st);
+                           double* partials, unsigned int* ticket, double* out, int grid, cudaStream_t st, const FinalizeCtx& fin);
+// a device vector of n doubles summed across ranks by the fused tail alone
+cudaError_t exchange_launch(const double* vals, int n, unsigned int* ticket, double* out, cudaStream_t st, const FinalizeCtx& fin);
 }  // namespace apb

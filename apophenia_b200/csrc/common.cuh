@@ -48,4 +48,100 @@ __device__ __forceinline__ double warp_sum(double v) {
 // streaming 8-byte load: read once, do not keep in L1
 __device__ __forceinline__ double ld_stream(const double* p) { return __ldcs(p); }
 
+// ---------------------------------------------------------------------------------------
+// Grid reduction tail, fused with the cross-GPU sum.
+//
+// Every reduction kernel of the library ends the same way: per-CTA partials in global
+// memory, a ticket counter, and the last CTA to finish sums the partials in block order
+// (two-sum compensated) -- bitwise reproducible for a given grid.  With several ranks (one
+// process per GPU) the same CTA then performs the allreduce itself over NVLink: it stores its
+// vector into a slot of EVERY rank's inbox (peer memory mapped through CUDA IPC), publishes a
+// sequence number with a system-scope release, waits for the other ranks' sequence numbers in
+// its own inbox, and adds the slots in rank order -- so all ranks obtain bitwise identical
+// sums without a separate NCCL kernel, and the result lands directly in mapped pinned host
+// memory.  Inboxes are double buffered on the parity of the sequence number: a rank can be at
+// most one pass ahead of its slowest peer.
+// ---------------------------------------------------------------------------------------
+constexpr int P2P_MAX_RANKS = 8;
+struct FinalizeCtx {
+    int nranks, rank;                       // nranks <= 1: no exchange
+    unsigned long long seq;                 // > 0, incremented by the host every launch
+    int slot;                               // doubles per rank slot in an inbox
+    double* inbox[P2P_MAX_RANKS];           // inbox of rank p as mapped on this GPU: [2][nranks][slot]
+    unsigned long long* flags[P2P_MAX_RANKS];  // flags of rank p: [2][nranks]
+    double* host_out;                       // mapped pinned host buffer (may be null)
+    unsigned long long spin_limit;
+    int* err;                               // set to 1 if a peer never arrived
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ double ld_relaxed_sys(const double* p) {
+    double v;
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Call with all threads of every CTA after the CTA's partials[blockIdx.x * nout + v] are
+// written.  `scratch` is shared memory with at least nout doubles (used by the last CTA only).
+__device__ __forceinline__ void grid_finalize(const double* __restrict__ partials, int nout,
+                                              unsigned int* __restrict__ ticket, double* __restrict__ out,
+                                              const FinalizeCtx& ctx, double* scratch) {
+    __shared__ unsigned int is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    for (int v = threadIdx.x; v < nout; v += blockDim.x) {
+        double s = 0.0, c = 0.0;
+        for (unsigned b = 0; b < gridDim.x; b++) {
+            double e;
+            two_sum(s, __ldcg(partials + (size_t)b * nout + v), s, e);
+            c += e;
+        }
+        scratch[v] = s + c;
+    }
+    __syncthreads();
+    if (ctx.nranks > 1) {
+        const int par = (int)(ctx.seq & 1ull);
+        const size_t my_slot = ((size_t)par * ctx.nranks + ctx.rank) * ctx.slot;
+        for (int p = 0; p < ctx.nranks; p++)
+            for (int v = threadIdx.x; v < nout; v += blockDim.x) ctx.inbox[p][my_slot + v] = scratch[v];
+        __threadfence_system();
+        __syncthreads();
+        if ((int)threadIdx.x < ctx.nranks)   // thread p tells rank p that this rank's slot is complete
+            st_release_sys(ctx.flags[threadIdx.x] + par * ctx.nranks + ctx.rank, ctx.seq);
+        if ((int)threadIdx.x < ctx.nranks) {  // and waits for rank threadIdx.x in its own inbox
+            const unsigned long long* f = ctx.flags[ctx.rank] + par * ctx.nranks + threadIdx.x;
+            unsigned long long spins = 0;
+            while (ld_acquire_sys(f) < ctx.seq) {
+                if (++spins > ctx.spin_limit) { *ctx.err = 1; break; }
+                __nanosleep(64);
+            }
+        }
+        __syncthreads();
+        const double* mine = ctx.inbox[ctx.rank] + (size_t)par * ctx.nranks * ctx.slot;
+        for (int v = threadIdx.x; v < nout; v += blockDim.x) {
+            double s = 0.0;
+            for (int r = 0; r < ctx.nranks; r++) s += ld_relaxed_sys(mine + (size_t)r * ctx.slot + v);  // rank order: same bits everywhere
+            scratch[v] = s;
+        }
+        __syncthreads();
+    }
+    for (int v = threadIdx.x; v < nout; v += blockDim.x) {
+        out[v] = scratch[v];
+        if (ctx.host_out) ctx.host_out[v] = scratch[v];
+    }
+    if (ctx.host_out) __threadfence_system();
+    if (threadIdx.x == 0) *ticket = 0;
+}
+
 }  // namespace apb

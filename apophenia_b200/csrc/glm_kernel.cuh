@@ -32,6 +32,7 @@ struct GlmLaunch {
     double* out;             // [MAX_ACC + K]
     int grid;
     cudaStream_t stream;
+    FinalizeCtx fin;
 };
 
 template <int K, class Fam, bool HAS_W>
@@ -39,7 +40,7 @@ __global__ void __launch_bounds__(GLM_THREADS)
 glm_fused_kernel(const double* __restrict__ tiles, const unsigned long long n_rows,
                  const unsigned long long n_tiles, const __grid_constant__ GlmParams prm,
                  double* __restrict__ partials, unsigned int* __restrict__ ticket,
-                 double* __restrict__ out) {
+                 double* __restrict__ out, const __grid_constant__ FinalizeCtx fin) {
     constexpr int COLS = K + 1 + (HAS_W ? 1 : 0);
     constexpr int NOUT = MAX_ACC + K;
     constexpr int WARPS = GLM_THREADS / 32;
@@ -94,31 +95,14 @@ glm_fused_kernel(const double* __restrict__ tiles, const unsigned long long n_ro
         partials[(size_t)blockIdx.x * NOUT + threadIdx.x] = s;
     }
 
-    // ---- grid reduction by the last CTA ---------------------------------
-    __shared__ unsigned int is_last;
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence();
-    if (threadIdx.x < NOUT) {
-        double s = 0.0, c = 0.0;
-        const double* p = partials + threadIdx.x;
-        for (unsigned b = 0; b < gridDim.x; b++) {
-            double e;
-            two_sum(s, __ldcg(p + (size_t)b * NOUT), s, e);
-            c += e;
-        }
-        out[threadIdx.x] = s + c;
-    }
-    if (threadIdx.x == 0) *ticket = 0;
+    // ---- grid reduction (+ cross-GPU sum over NVLink) by the last CTA --------
+    grid_finalize(partials, NOUT, ticket, out, fin, &red[0][0]);
 }
 
 template <int K, class Fam, bool HAS_W>
 cudaError_t glm_launch_one(const GlmLaunch& L, const GlmParams& prm) {
     glm_fused_kernel<K, Fam, HAS_W><<<L.grid, GLM_THREADS, 0, L.stream>>>(
-        L.tiles, L.n_rows, L.n_tiles, prm, L.partials, L.ticket, L.out);
+        L.tiles, L.n_rows, L.n_tiles, prm, L.partials, L.ticket, L.out, L.fin);
     return cudaGetLastError();
 }
 

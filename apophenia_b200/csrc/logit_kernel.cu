@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(LOGIT_THREADS)
 logit_fused_kernel(const double* __restrict__ tiles, const unsigned long long n_rows,
                    const unsigned long long n_tiles, const int K, const __grid_constant__ LogitParams prm,
                    double* __restrict__ partials, unsigned int* __restrict__ ticket,
-                   double* __restrict__ out) {
+                   double* __restrict__ out, const __grid_constant__ FinalizeCtx fin) {
     constexpr int WARPS = LOGIT_THREADS / 32;
     constexpr int XS = KB + 1;  // row stride of the parked x rows (odd: conflict-free)
     constexpr int NOUT = 1 + KB * C1;
@@ -118,23 +118,7 @@ logit_fused_kernel(const double* __restrict__ tiles, const unsigned long long n_
         for (int wv = 0; wv < WARPS; wv++) s += red[wv * NOUT + v];
         partials[(size_t)blockIdx.x * NOUT + v] = s;
     }
-    __shared__ unsigned int is_last;
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence();
-    for (int v = threadIdx.x; v < NOUT; v += LOGIT_THREADS) {
-        double s = 0.0, c = 0.0;
-        for (unsigned b = 0; b < gridDim.x; b++) {
-            double er;
-            two_sum(s, __ldcg(partials + (size_t)b * NOUT + v), s, er);
-            c += er;
-        }
-        out[v] = s + c;
-    }
-    if (threadIdx.x == 0) *ticket = 0;
+    grid_finalize(partials, NOUT, ticket, out, fin, red);
 }
 
 
@@ -171,7 +155,8 @@ __global__ void __launch_bounds__(LOGIT_THREADS)
 logit_dmma_kernel(const double* __restrict__ tiles, const unsigned long long n_rows,
                   const unsigned long long n_tiles, const int K, const int C1,
                   const __grid_constant__ LogitParams prm, double* __restrict__ partials,
-                  unsigned int* __restrict__ ticket, double* __restrict__ out) {
+                  unsigned int* __restrict__ ticket, double* __restrict__ out,
+                  const __grid_constant__ FinalizeCtx fin) {
     constexpr int WARPS = LOGIT_THREADS / 32;
     constexpr int KS = KB / 4, JB = KB / 8;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -323,23 +308,7 @@ logit_dmma_kernel(const double* __restrict__ tiles, const unsigned long long n_r
         for (int wv = 0; wv < WARPS; wv++) s += smem[wv * NOUT + v];
         partials[(size_t)blockIdx.x * NOUT + v] = s;
     }
-    __shared__ unsigned int is_last;
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence();
-    for (int v = threadIdx.x; v < NOUT; v += LOGIT_THREADS) {
-        double s = 0.0, c = 0.0;
-        for (unsigned b = 0; b < gridDim.x; b++) {
-            double er;
-            two_sum(s, __ldcg(partials + (size_t)b * NOUT + v), s, er);
-            c += er;
-        }
-        out[v] = s + c;
-    }
-    if (threadIdx.x == 0) *ticket = 0;
+    grid_finalize(partials, NOUT, ticket, out, fin, smem);
 }
 
 static size_t dmma_smem() { return (size_t)(LOGIT_THREADS / 32) * 2 * LOGIT_TILE_DOUBLES * sizeof(double); }
@@ -349,7 +318,7 @@ static cudaError_t dmma_launch_one(int c1, const LogitLaunch& L, const LogitPara
     static bool done = false;
     if (!done) { cudaFuncSetAttribute(logit_dmma_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); done = true; }
     logit_dmma_kernel<KB><<<L.grid, LOGIT_THREADS, sm, L.stream>>>(L.tiles, L.n_rows, L.n_tiles, L.k, c1, prm,
-                                                                   L.partials, L.ticket, L.out);
+                                                                   L.partials, L.ticket, L.out, L.fin);
     return cudaGetLastError();
 }
 template <int KB>
@@ -373,7 +342,7 @@ static cudaError_t launch_one(const LogitLaunch& L, const LogitParams& prm) {
         attr_done = true;
     }
     logit_fused_kernel<KB, C1><<<L.grid, LOGIT_THREADS, sm, L.stream>>>(L.tiles, L.n_rows, L.n_tiles, L.k, prm,
-                                                                        L.partials, L.ticket, L.out);
+                                                                        L.partials, L.ticket, L.out, L.fin);
     return cudaGetLastError();
 }
 template <int KB, int C1>

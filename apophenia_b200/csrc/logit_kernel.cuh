@@ -21,6 +21,7 @@ struct LogitLaunch {
     double* out;           // [1 + KB*(C-1)]: LL, then G[j][c] at 1 + j*(C-1) + c
     int grid;
     cudaStream_t stream;
+    FinalizeCtx fin;
 };
 int logit_kb(int k);
 cudaError_t logit_launch(int c1, const LogitLaunch& L, const LogitParams& prm);

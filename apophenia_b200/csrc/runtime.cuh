@@ -57,7 +57,11 @@ struct Runtime {
     size_t partials_cap = 0;  // doubles
     unsigned int* d_ticket = nullptr;
     double* d_out = nullptr;  // OUT_CAP doubles
-    double* h_out = nullptr;  // pinned
+    double* h_out = nullptr;  // pinned + mapped: the last CTA writes results straight into it
+    double* h_out_dev = nullptr;  // device address of h_out
+    int* h_err = nullptr;     // mapped flag: a peer never arrived in the fused allreduce
+    int* h_err_dev = nullptr;
+    double* d_vals = nullptr; // staging for host scalars to be summed across ranks
     bool auto_pin = false;
     std::unordered_map<const apop_data*, Resident*> reg;
     // stats
@@ -67,6 +71,13 @@ struct Runtime {
     NcclApi nccl;
     void* comm = nullptr;
     int nranks = 1, rank = 0;
+    // fused allreduce over NVLink peer memory (CUDA IPC), see common.cuh grid_finalize
+    bool p2p_active = false;
+    int p2p_slot = 0;
+    unsigned long long p2p_seq = 0;
+    double* p2p_local = nullptr;                 // this rank's inbox + flags allocation
+    double* p2p_inbox[P2P_MAX_RANKS] = {nullptr};
+    unsigned long long* p2p_flags[P2P_MAX_RANKS] = {nullptr};
     std::string err;
 };
 constexpr size_t OUT_CAP = 4096;

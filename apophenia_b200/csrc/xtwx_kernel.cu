@@ -30,7 +30,8 @@ template <int KB, int MODE>
 __global__ void __launch_bounds__(XTWX_THREADS)
 xtwx_kernel(const double* __restrict__ tiles, const unsigned long long n_rows, const unsigned long long n_tiles,
             const int K, const int cols, const int has_w, const __grid_constant__ XtwxParams prm,
-            double* __restrict__ partials, unsigned int* __restrict__ ticket, double* __restrict__ out) {
+            double* __restrict__ partials, unsigned int* __restrict__ ticket, double* __restrict__ out,
+            const __grid_constant__ FinalizeCtx fin) {
     constexpr int WARPS = XTWX_THREADS / 32;
     constexpr int XS = KB + 1;       // parked x rows: odd stride, conflict-free both ways
     constexpr int NC = KB + 1;       // columns of [X | y]
@@ -93,23 +94,7 @@ xtwx_kernel(const double* __restrict__ tiles, const unsigned long long n_rows, c
         for (int wv = 0; wv < WARPS; wv++) s += red[wv * NOUT + v];
         partials[(size_t)blockIdx.x * NOUT + v] = s;
     }
-    __shared__ unsigned int is_last;
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence();
-    for (int v = threadIdx.x; v < NOUT; v += XTWX_THREADS) {
-        double s = 0.0, c = 0.0;
-        for (unsigned b = 0; b < gridDim.x; b++) {
-            double er;
-            two_sum(s, __ldcg(partials + (size_t)b * NOUT + v), s, er);
-            c += er;
-        }
-        out[v] = s + c;
-    }
-    if (threadIdx.x == 0) *ticket = 0;
+    grid_finalize(partials, NOUT, ticket, out, fin, red);
 }
 
 template <int KB>
@@ -121,7 +106,7 @@ static cudaError_t launch_one(const XtwxLaunch& L, const XtwxParams& prm) {
     static bool done = false;
     if (!done) { cudaFuncSetAttribute(xtwx_kernel<KB, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); done = true; }
     xtwx_kernel<KB, MODE><<<L.grid, XTWX_THREADS, sm, L.stream>>>(L.tiles, L.n_rows, L.n_tiles, L.k, L.cols, L.has_w, prm,
-                                                                 L.partials, L.ticket, L.out);
+                                                                 L.partials, L.ticket, L.out, L.fin);
     return cudaGetLastError();
 }
 template <int KB, int MODE>

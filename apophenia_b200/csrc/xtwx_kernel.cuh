@@ -25,6 +25,7 @@ struct XtwxLaunch {
     double* out;           // [KB*(KB+1)]: H[j][c] at j*(KB+1)+c, c = KB is the y column
     int grid;
     cudaStream_t stream;
+    FinalizeCtx fin;
 };
 int xtwx_kb(int k);
 cudaError_t xtwx_launch(int mode, const XtwxLaunch& L, const XtwxParams& prm);

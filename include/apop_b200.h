@@ -131,6 +131,14 @@ int apop_b200_comm_unique_id(void *id128);
 int apop_b200_comm_init(int nranks, int rank, const void *id128);
 int apop_b200_comm_finalize(void);
 int apop_b200_comm_size(void);
+/* Fused allreduce over NVLink peer memory: after apop_b200_comm_init every rank exports a
+ * 64-byte CUDA IPC handle of its inbox (apop_b200_comm_p2p_handle), the host program gathers
+ * the nranks handles (rank order) and hands them to apop_b200_comm_p2p_init.  The reduction
+ * kernels then sum [LL | score] across GPUs in their own last CTA (peer stores + system-scope
+ * flags) instead of a separate ncclAllReduce; NCCL remains for the large batched outputs. */
+int apop_b200_comm_p2p_handle(int nranks, void *handle64);
+int apop_b200_comm_p2p_init(int nranks, int rank, const void *handles);
+int apop_b200_comm_p2p_active(void);
 
 /* ------------------------------------------------------------------ *
  *  Residency: X, y (and weights) live in HBM between optimizer iterations

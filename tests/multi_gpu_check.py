@@ -1,0 +1,89 @@
+#!/usr/bin/env python
+"""Multi-GPU parity check, run under torchrun on a box with >= 2 B200s (not collected by
+pytest):  torchrun --nproc-per-node 2 tests/multi_gpu_check.py
+Rows are sharded contiguously; every rank must return the oracle's full-data LL/score, and
+bitwise the same numbers as every other rank, with the fused NVLink allreduce (default) and
+with APOP_B200_ALLREDUCE=nccl."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import apophenia_b200 as ab  # noqa: E402
+from apophenia_b200 import abi  # noqa: E402
+from apophenia_b200.shard import shard_range  # noqa: E402
+from conftest import gen_probit_logit_sample  # noqa: E402
+from oracle import oracle as o  # noqa: E402
+
+
+def same_everywhere(arr, world):
+    t = torch.tensor(np.asarray(arr, dtype=np.float64).ravel()).cuda()
+    gathered = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(gathered, t)
+    return all(torch.equal(gathered[0], g) for g in gathered)
+
+
+def main():
+    local = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    ab.init(local)
+    ab.comm_init_from_torch()
+    mode = "p2p-fused" if abi.load_library().apop_b200_comm_p2p_active() else "nccl"
+    n, k = 200003, 12
+    X, y, beta = gen_probit_logit_sample(n, k, seed=8)
+    lo, hi = shard_range(n, world, rank)
+    d = ab.pin(ab.Data(matrix=X[lo:hi], vector=y[lo:hi]))
+    checks = []
+    for b in (beta, np.zeros(k), 0.5 * beta):
+        ll, g = ab.ll_score(ab.PROBIT, d, b)
+        want = float(o.probit_ll(X, y, b, o.EXACT))
+        ge, scale = o.probit_score(X, y, b, o.EXACT)
+        checks.append(abs(ll - want) <= 1e-12 * abs(want))
+        checks.append(bool(np.all(np.abs(g - ge.astype(float)) <= 1e-12 * scale.astype(float))))
+        checks.append(same_everywhere(np.concatenate([[ll], g]), world))
+    H = ab.information(ab.PROBIT, d, beta)
+    Hw = o.information(0, X, y, beta).astype(float)
+    checks.append(bool(np.max(np.abs(H - Hw)) <= 1e-11 * np.abs(Hw).max()))
+    checks.append(same_everywhere(H, world))
+    # OLS needs the global row count for the variance; Poisson regression the global lgamma constant
+    yo = X @ beta + np.sin(np.arange(n))
+    do = ab.pin(ab.Data(matrix=X[lo:hi], vector=yo[lo:hi]))
+    m = ab.vector_model(beta * 1.1, do)
+    checks.append(abs(ab.log_likelihood(ab.OLS, do, m) - float(o.ols_ll(X, yo, beta * 1.1, None, o.EXACT))) <= 1e-11 * n)
+    yp = np.floor(np.abs(yo)) % 7
+    dp = ab.pin(ab.Data(matrix=X[lo:hi], vector=yp[lo:hi]))
+    bp = beta / 4
+    checks.append(abs(ab.log_likelihood(ab.POISSON_REG, dp, ab.vector_model(bp, dp)) - float(o.poisson_reg_ll(X, yp, bp, o.EXACT)))
+                  <= 1e-12 * abs(float(o.poisson_reg_ll(X, yp, bp, o.EXACT))))
+    # multinomial logit and the batched path (NCCL for the large output)
+    Xl, yl, B = gen_probit_logit_sample(n, 8, seed=3, method="logit", ncat=5)
+    dl = ab.pin(ab.Data(matrix=Xl[lo:hi], vector=yl[lo:hi]))
+    ml = ab.logit_model(B, dl)
+    checks.append(abs(ab.log_likelihood(ab.LOGIT, dl, ml) - float(o.logit_ll(Xl, yl, B, mode=o.EXACT))) <= 1e-12 * abs(float(o.logit_ll(Xl, yl, B, mode=o.EXACT))))
+    Bs = beta[None, :] + 0.01 * np.arange(5)[:, None]
+    llb, gb = ab.ll_score_batched(ab.PROBIT, d, Bs)
+    checks.append(all(abs(llb[r] - float(o.probit_ll(X, y, Bs[r], o.EXACT))) <= 1e-12 * abs(llb[r]) for r in range(5)))
+    ab.bootstrap_counts(d, 4, seed=5)
+    c = ab.counts_download(d, 4, hi - lo)
+    tot = torch.tensor(c.sum(0).astype(np.float64)).cuda()
+    dist.all_reduce(tot)
+    checks.append(bool(torch.all(tot == n)))     # the resample is of the GLOBAL data set
+    ok = all(checks)
+    flag = torch.tensor([1.0 if ok else 0.0]).cuda()
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print(f"multi_gpu_check world={world} allreduce={mode}: {'OK' if flag.item() == 1 else 'FAILED'} {checks}")
+    ab.comm_finalize()
+    dist.destroy_process_group()
+    sys.exit(0 if flag.item() == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()
