@@ -123,15 +123,15 @@ logit_fused_kernel(const double* __restrict__ tiles, const unsigned long long n_
 
 
 // ---------------------------------------------------------------------------------------
-// Tensor-core variant (APOP_B200_LOGIT_DMMA=1; measured slower than the FP64-pipe kernel in
-// round 1: 1.89 ms vs 1.40 ms at 20M x 32, C = 8 -- the cross-lane soft-max costs more than the
-// DFMAs it saves; kept for the next round's hybrid): the two contractions of a tile run as FP64 DMMA
+// Tensor-core variant (APOP_B200_LOGIT_DMMA=1; round-1 measurement at 20M x 32, C = 8: 1.38-1.40 ms,
+// level with the FP64-pipe kernel's 1.40 ms -- DMMA pipe ~40 % busy, bounded by the latency of its
+// short dependent MMA chains at 8-16 warps per SM): the two contractions of a tile run as FP64 DMMA
 // (mma.sync m8n8k4), which executes on the tensor pipe next to the FP64 pipe, leaving the
 // latter to the soft-max.  The (C-1 <= 7) free categories are the M = 8 rows of the MMA:
 //   stage 1  S^T[c][row] = B^T[c][j] . X^T[j][row]      (K = columns)
-//   soft-max across the 8 lanes that hold the 8 categories of a row (xor-shuffles 4, 8, 16);
-//            exp(-max), the log and nothing else are evaluated once per row, by the lane
-//            whose category index equals the row's slot, and exp(-max) is broadcast back
+//   soft-max with lane = row: the 8 x 32 block of x.beta goes through a per-warp shared-memory
+//            slab, so each row's exps, log and reciprocal are evaluated exactly once (FP64
+//            pipe), and the residuals return through the slab as stage-3 fragments
 //   stage 3  G^T[c][j] += R^T[c][row] . X[row][j]       (K = rows, slots = rows 2q+e)
 // Same fragment trick as batched_kernel.cu: the C fragment of stage 1 is already the A
 // fragment of stage 3.  X is read once from HBM (stage-1 fragments, 64-byte segments of the
@@ -150,8 +150,8 @@ __device__ __forceinline__ double group_sum(double v) {
     v += shfl_xor_d(v, 4); v += shfl_xor_d(v, 8); return v + shfl_xor_d(v, 16);
 }
 
-template <int KB>
-__global__ void __launch_bounds__(LOGIT_THREADS)
+template <int KB, int NBUF>
+__global__ void __launch_bounds__(LOGIT_THREADS, NBUF == 1 ? 4 : 2)
 logit_dmma_kernel(const double* __restrict__ tiles, const unsigned long long n_rows,
                   const unsigned long long n_tiles, const int K, const int C1,
                   const __grid_constant__ LogitParams prm, double* __restrict__ partials,
@@ -169,14 +169,18 @@ logit_dmma_kernel(const double* __restrict__ tiles, const unsigned long long n_r
     // is being processed; columns are padded to CS doubles so that the stage-1 fragment reads
     // (4 columns x 8 rows per request) are bank-conflict free
     extern __shared__ __align__(16) double smem[];
-    double* ring = smem + warp * (2 * LOGIT_TILE_DOUBLES);
-    const int n_chunks = cols * 16;           // 16-byte chunks in a tile
+    double* ring = smem + warp * (NBUF * LOGIT_TILE_DOUBLES + 8 * LOGIT_XS);
+    double* xs = ring + NBUF * LOGIT_TILE_DOUBLES;   // 8 x LOGIT_XS exchange slab
+    // chunk c = lane + 32 i of a tile lies in column (lane >> 4) + 2 i at 16-byte slot lane & 15
+    const int pf_dst = (lane >> 4) * LOGIT_CS + (lane & 15) * 2, pf_src = lane * 2;
     auto prefetch = [&](unsigned long long tt, int buf) {
-        const double* src = tiles + tt * (unsigned long long)(cols * TILE_ROWS);
-        double* dst = ring + buf * LOGIT_TILE_DOUBLES;
-        for (int c = lane; c < n_chunks; c += 32) {
-            const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + (c >> 4) * LOGIT_CS + (c & 15) * 2);
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src + c * 2));
+        const double* src = tiles + tt * (unsigned long long)(cols * TILE_ROWS) + pf_src;
+        const unsigned sa = (unsigned)__cvta_generic_to_shared(ring + buf * LOGIT_TILE_DOUBLES + pf_dst);
+#pragma unroll
+        for (int i = 0; i < (KB + 2) / 2; i++) {
+            const int col = (lane >> 4) + 2 * i;
+            if (col < cols)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa + i * 2 * LOGIT_CS * 8), "l"(src + i * 64));
         }
         asm volatile("cp.async.commit_group;");
     };
@@ -191,15 +195,18 @@ logit_dmma_kernel(const double* __restrict__ tiles, const unsigned long long n_r
 #pragma unroll
     for (int c = 0; c < LOGIT_MAX_C1; c++) cat[c] = prm.cats[c];
 
-    double G[JB][2];
+    double G[JB][2], G2[JB][2];   // even / odd contraction slots accumulate separately
 #pragma unroll
-    for (int jb = 0; jb < JB; jb++) G[jb][0] = G[jb][1] = 0.0;
+    for (int jb = 0; jb < JB; jb++) G[jb][0] = G[jb][1] = G2[jb][0] = G2[jb][1] = 0.0;
     KSum ll;
 
     int cur = 0;
-    if (gwarp < n_tiles) prefetch(gwarp, 0);
+    if (NBUF == 2 && gwarp < n_tiles) prefetch(gwarp, 0);
     for (unsigned long long t = gwarp; t < n_tiles; t += nwarps) {
-        if (t + nwarps < n_tiles) {
+        if (NBUF == 1) {   // single buffer, twice the warps: latency is hidden across warps
+            prefetch(t, 0);
+            asm volatile("cp.async.wait_group 0;");
+        } else if (t + nwarps < n_tiles) {
             prefetch(t + nwarps, cur ^ 1);
             asm volatile("cp.async.wait_group 1;");
         } else
@@ -215,64 +222,67 @@ logit_dmma_kernel(const double* __restrict__ tiles, const unsigned long long n_r
 #pragma unroll
             for (int nb = 0; nb < 4; nb++) xf[ks][nb] = (j < K) ? tile[j * LOGIT_CS + nb * 8 + g] : 0.0;
         }
-        double S[4][2];
+        double S[4][2], S2[4][2];   // two accumulator sets: 8 independent MMA chains of depth KS/2
 #pragma unroll
-        for (int nb = 0; nb < 4; nb++) S[nb][0] = S[nb][1] = 0.0;
+        for (int nb = 0; nb < 4; nb++) S[nb][0] = S[nb][1] = S2[nb][0] = S2[nb][1] = 0.0;
 #pragma unroll
-        for (int ks = 0; ks < KS; ks++)
+        for (int ks = 0; ks < KS; ks += 2)
 #pragma unroll
-            for (int nb = 0; nb < 4; nb++) dmma_8x8x4(S[nb][0], S[nb][1], bfrag[ks], xf[ks][nb]);
-        // ---- soft-max over the categories of each of this lane group's 8 rows
-        double mxs[4][2], den[4][2];
-        int hit[4][2];
-        double mine_mx = 0.0;     // max of the row whose slot (nb*2+e) equals g
-        bool mine_valid = false;
+            for (int nb = 0; nb < 4; nb++) {
+                dmma_8x8x4(S[nb][0], S[nb][1], bfrag[ks], xf[ks][nb]);
+                dmma_8x8x4(S2[nb][0], S2[nb][1], bfrag[ks + 1], xf[ks + 1][nb]);
+            }
+#pragma unroll
+        for (int nb = 0; nb < 4; nb++) { S[nb][0] += S2[nb][0]; S[nb][1] += S2[nb][1]; }
+        // ---- soft-max with lane = row: the C fragments go through the warp's exchange slab
+        // (category-major, stride LOGIT_XS), every row's exp / log / reciprocal is evaluated
+        // exactly once, and the residuals come back as the A fragments of stage 3
+        __syncwarp();
 #pragma unroll
         for (int nb = 0; nb < 4; nb++) {
-            const double2 y2 = *reinterpret_cast<const double2*>(tile + K * LOGIT_CS + nb * 8 + 2 * q);
-#pragma unroll
-            for (int e = 0; e < 2; e++) {
-                const double y = e ? y2.y : y2.x;
-                // find_index (model/apop_probit.c:206-210): first category value equal to y, else C1
-                int idx = C1;
-#pragma unroll
-                for (int c = LOGIT_MAX_C1 - 1; c >= 0; c--) idx = (c < C1 && y == cat[c]) ? c : idx;
-                hit[nb][e] = (idx == g + 1) && cat_ok;
-                const double s = cat_ok ? S[nb][e] : -1e300;
-                const double mx = group_max(s);
-                const double ev = fm_exp(s - mx);
-                den[nb][e] = group_sum(ev);
-                mxs[nb][e] = mx;
-                S[nb][e] = ev;     // S now holds exp(xb_c - max)
-                ll.add((hit[nb][e] && t * TILE_ROWS + nb * 8 + 2 * q + e < n_rows) ? s : 0.0);   // the numerator x.beta_idx
-                if (nb * 2 + e == g) { mine_mx = mx; mine_valid = t * TILE_ROWS + nb * 8 + 2 * q + e < n_rows; }
-            }
+            xs[g * LOGIT_XS + nb * 8 + 2 * q] = S[nb][0];
+            xs[g * LOGIT_XS + nb * 8 + 2 * q + 1] = S[nb][1];
         }
-        // exp(-max) once per row (lane g owns slot g), broadcast to the row's 8 lanes
-        const double mine_e0 = fm_exp(-mine_mx);
-        double mine_den = 0.0;
+        __syncwarp();
+        {
+            const double y = tile[K * LOGIT_CS + lane];
+            double xbv[LOGIT_MAX_C1];
 #pragma unroll
-        for (int nb = 0; nb < 4; nb++)
+            for (int c = 0; c < LOGIT_MAX_C1; c++) xbv[c] = (c < C1) ? xs[c * LOGIT_XS + lane] : -1e300;
+            // find_index (model/apop_probit.c:206-210): first category value equal to y, else C1
+            int idx = C1;
 #pragma unroll
-            for (int e = 0; e < 2; e++) {
-                const int slot = nb * 2 + e;
-                const double e0 = __shfl_sync(0xffffffffu, mine_e0, slot * 4 + q);
-                den[nb][e] += e0;
-                if (slot == g) mine_den = den[nb][e];
+            for (int c = LOGIT_MAX_C1 - 1; c >= 0; c--) idx = (c < C1 && y == cat[c]) ? c : idx;
+            double mx = xbv[0];
+#pragma unroll
+            for (int c = 1; c < LOGIT_MAX_C1; c++) mx = fmax(mx, xbv[c]);
+            double ev[LOGIT_MAX_C1], sum = 0.0, num = 0.0;
+#pragma unroll
+            for (int c = 0; c < LOGIT_MAX_C1; c++) {
+                ev[c] = fm_exp(xbv[c] - mx);       // padded categories: exp(-1e300) ~ 1e-308, vanishes in the sum
+                sum += ev[c];
+                num = (idx == c + 1) ? xbv[c] : num;
             }
-        // when exp(-max) overflows the reference takes log-sum-exp = max - max
-        const double lse = (mine_mx < -700.0) ? 0.0 : mine_mx + fm_log(mine_den);
-        ll.add(mine_valid ? -lse : 0.0);
-        // residuals r = 1{idx = c} - p_c, in place: S becomes R^T
+            const double e0 = fm_exp(-mx);         // the numeraire's exp(0 - max)
+            const bool valid = t * TILE_ROWS + lane < n_rows;
+            // when exp(-max) overflows the reference takes log-sum-exp = max - max
+            const double lse = (mx < -700.0) ? 0.0 : mx + fm_log(sum + e0);
+            ll.add(valid ? num - lse : 0.0);
+            const double inv = (mx < -700.0) ? 0.0 : fm_rcp(sum + e0);
+            __syncwarp();
 #pragma unroll
-        for (int nb = 0; nb < 4; nb++)
-#pragma unroll
-            for (int e = 0; e < 2; e++) {
-                const double inv = (mxs[nb][e] < -700.0) ? 0.0 : fm_rcp(den[nb][e]);
-                const bool valid = t * TILE_ROWS + nb * 8 + 2 * q + e < n_rows;
-                const double r = (hit[nb][e] ? 1.0 : 0.0) - S[nb][e] * inv;
-                S[nb][e] = (valid && cat_ok) ? r : 0.0;
+            for (int c = 0; c < LOGIT_MAX_C1; c++) {
+                const double r = ((idx == c + 1) ? 1.0 : 0.0) - ev[c] * inv;
+                xs[c * LOGIT_XS + lane] = (valid && c < C1) ? r : 0.0;
             }
+            xs[LOGIT_MAX_C1 * LOGIT_XS + lane] = 0.0;   // the padding category (M = 8)
+        }
+        __syncwarp();
+#pragma unroll
+        for (int nb = 0; nb < 4; nb++) {
+            const double2 r2 = *reinterpret_cast<const double2*>(xs + g * LOGIT_XS + nb * 8 + 2 * q);
+            S[nb][0] = r2.x; S[nb][1] = r2.y;           // S now holds R^T
+        }
         // ---- stage 3
 #pragma unroll
         for (int jb = 0; jb < JB; jb++) {
@@ -282,14 +292,16 @@ logit_dmma_kernel(const double* __restrict__ tiles, const unsigned long long n_r
                 double2 x2 = make_double2(0.0, 0.0);
                 if (j < K) x2 = *reinterpret_cast<const double2*>(tile + j * LOGIT_CS + nb * 8 + 2 * q);
                 dmma_8x8x4(G[jb][0], G[jb][1], S[nb][0], x2.x);
-                dmma_8x8x4(G[jb][0], G[jb][1], S[nb][1], x2.y);
+                dmma_8x8x4(G2[jb][0], G2[jb][1], S[nb][1], x2.y);
             }
         }
         __syncwarp();   // every lane is done with this buffer before the next prefetch overwrites it
-        cur ^= 1;
+        if (NBUF == 2) cur ^= 1;
     }
 
     // ---- CTA reduction: lane (g, q) holds G^T[c = g][j = jb*8 + 2q + {0,1}]
+#pragma unroll
+    for (int jb = 0; jb < JB; jb++) { G[jb][0] += G2[jb][0]; G[jb][1] += G2[jb][1]; }
     const int NOUT = 1 + KB * C1;
     __syncthreads();                   // the ring is reused as the WARPS x NOUT reduction scratch
     const double llw = warp_sum(ll.value());
@@ -311,22 +323,37 @@ logit_dmma_kernel(const double* __restrict__ tiles, const unsigned long long n_r
     grid_finalize(partials, NOUT, ticket, out, fin, smem);
 }
 
-static size_t dmma_smem() { return (size_t)(LOGIT_THREADS / 32) * 2 * LOGIT_TILE_DOUBLES * sizeof(double); }
+static int dmma_nbuf() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("APOP_B200_LOGIT_NBUF"); v = (e && e[0] == '2') ? 2 : 1; }
+    return v;
+}
+static size_t dmma_smem() { return (size_t)(LOGIT_THREADS / 32) * (dmma_nbuf() * LOGIT_TILE_DOUBLES + 8 * LOGIT_XS) * sizeof(double); }
 template <int KB>
 static cudaError_t dmma_launch_one(int c1, const LogitLaunch& L, const LogitParams& prm) {
     const size_t sm = dmma_smem();
-    static bool done = false;
-    if (!done) { cudaFuncSetAttribute(logit_dmma_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); done = true; }
-    logit_dmma_kernel<KB><<<L.grid, LOGIT_THREADS, sm, L.stream>>>(L.tiles, L.n_rows, L.n_tiles, L.k, c1, prm,
-                                                                   L.partials, L.ticket, L.out, L.fin);
+    if (dmma_nbuf() == 1) {
+        static bool done = false;
+        if (!done) { cudaFuncSetAttribute(logit_dmma_kernel<KB, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); done = true; }
+        logit_dmma_kernel<KB, 1><<<L.grid, LOGIT_THREADS, sm, L.stream>>>(L.tiles, L.n_rows, L.n_tiles, L.k, c1, prm, L.partials, L.ticket, L.out, L.fin);
+    } else {
+        static bool done = false;
+        if (!done) { cudaFuncSetAttribute(logit_dmma_kernel<KB, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); done = true; }
+        logit_dmma_kernel<KB, 2><<<L.grid, LOGIT_THREADS, sm, L.stream>>>(L.tiles, L.n_rows, L.n_tiles, L.k, c1, prm, L.partials, L.ticket, L.out, L.fin);
+    }
     return cudaGetLastError();
 }
 template <int KB>
 static int dmma_bps_one(int c1) {
     const size_t sm = dmma_smem();
-    cudaFuncSetAttribute(logit_dmma_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     int nb = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, logit_dmma_kernel<KB>, LOGIT_THREADS, sm);
+    if (dmma_nbuf() == 1) {
+        cudaFuncSetAttribute(logit_dmma_kernel<KB, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, logit_dmma_kernel<KB, 1>, LOGIT_THREADS, sm);
+    } else {
+        cudaFuncSetAttribute(logit_dmma_kernel<KB, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, logit_dmma_kernel<KB, 2>, LOGIT_THREADS, sm);
+    }
     return nb;
 }
 
