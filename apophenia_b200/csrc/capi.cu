@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <dlfcn.h>
+#include <thread>
 
 using namespace apb;
 
@@ -132,6 +133,8 @@ extern "C" void apop_b200_finalize(void) {
     cudaFree(R.d_out);
     cudaFreeHost(R.h_out);
     cudaFreeHost(R.h_err);
+    for (int b2 = 0; b2 < 2; b2++) { if (R.pin_host[b2]) cudaFreeHost(R.pin_host[b2]); if (R.pin_dev[b2]) cudaFree(R.pin_dev[b2]); R.pin_host[b2] = nullptr; R.pin_dev[b2] = nullptr; }
+    R.pin_cap = 0;
     cudaFree(R.d_vals);
     cudaEventDestroy(R.ev0);
     cudaEventDestroy(R.ev1);
@@ -340,36 +343,77 @@ static bool upload(Resident* r, const apop_data* d) {
     r->memo_valid = false; r->have_lgamma_y = false; r->have_poisson = false; r->dirty = false;
     if (!need) return true;
 
-    // staged upload: chunks of rows in the reference layout, then the tile transpose
-    size_t chunk = ((size_t)32 << 20) / (size_t)(cols ? cols : 1);  // ~256 MB of doubles
+    // Staged, pipelined upload.  Chunks of rows are gathered from the caller's (pageable,
+    // possibly strided) buffers into one of two pinned staging buffers by a few host threads,
+    // sent with one asynchronous copy each, and re-tiled on the device; the gather of chunk
+    // i+1 overlaps the copy and the transpose of chunk i.
+    size_t chunk = ((size_t)8 << 20) / (size_t)(cols ? cols : 1);   // ~64 MB of doubles per chunk
     chunk = chunk / TILE_ROWS * TILE_ROWS;
     if (chunk < TILE_ROWS) chunk = TILE_ROWS;
     if (chunk > n_tiles * TILE_ROWS) chunk = n_tiles * TILE_ROWS;
-    double *Xs = nullptr, *ys = nullptr, *ws = nullptr;
-    bool ok = true;
-    if (k) ok = ok && cuda_ok(cudaMalloc(&Xs, chunk * k * sizeof(double)), "cudaMalloc(staging)");
-    if (hy) ok = ok && cuda_ok(cudaMalloc(&ys, chunk * sizeof(double)), "cudaMalloc(staging)");
-    if (hw) ok = ok && cuda_ok(cudaMalloc(&ws, chunk * sizeof(double)), "cudaMalloc(staging)");
-    for (size_t r0 = 0; ok && r0 < n; r0 += chunk) {
-        const size_t rows = (n - r0 < chunk) ? n - r0 : chunk;
-        if (k)
-            ok = ok && cuda_ok(cudaMemcpy2DAsync(Xs, k * sizeof(double), d->matrix->data + r0 * d->matrix->tda,
-                                                 d->matrix->tda * sizeof(double), k * sizeof(double), rows,
-                                                 cudaMemcpyHostToDevice, R.stream), "H2D X");
-        if (hy)
-            ok = ok && cuda_ok(cudaMemcpy2DAsync(ys, sizeof(double), d->vector->data + r0 * d->vector->stride,
-                                                 d->vector->stride * sizeof(double), sizeof(double), rows,
-                                                 cudaMemcpyHostToDevice, R.stream), "H2D y");
-        if (hw)
-            ok = ok && cuda_ok(cudaMemcpy2DAsync(ws, sizeof(double), d->weights->data + r0 * d->weights->stride,
-                                                 d->weights->stride * sizeof(double), sizeof(double), rows,
-                                                 cudaMemcpyHostToDevice, R.stream), "H2D w");
-        ok = ok && cuda_ok(tile_pack(Xs, ys, ws, rows, k, cols, r->tiles + (r0 / TILE_ROWS) * (size_t)cols * TILE_ROWS, R.stream), "tile_pack");
-        ok = ok && cuda_ok(cudaStreamSynchronize(R.stream), "pin sync");
+    const size_t chunk_doubles = chunk * (size_t)cols;
+    if (R.pin_cap < chunk_doubles) {
+        for (int b2 = 0; b2 < 2; b2++) {
+            if (R.pin_host[b2]) cudaFreeHost(R.pin_host[b2]);
+            if (R.pin_dev[b2]) cudaFree(R.pin_dev[b2]);
+            R.pin_host[b2] = nullptr; R.pin_dev[b2] = nullptr;
+        }
+        R.pin_cap = 0;
+        bool okb = true;
+        for (int b2 = 0; b2 < 2 && okb; b2++)
+            okb = cuda_ok(cudaHostAlloc(&R.pin_host[b2], chunk_doubles * sizeof(double), cudaHostAllocDefault), "cudaHostAlloc(staging)") &&
+                  cuda_ok(cudaMalloc(&R.pin_dev[b2], chunk_doubles * sizeof(double)), "cudaMalloc(staging)");
+        if (!okb) return false;
+        if (!R.pin_ev[0]) { cudaEventCreateWithFlags(&R.pin_ev[0], cudaEventDisableTiming); cudaEventCreateWithFlags(&R.pin_ev[1], cudaEventDisableTiming); }
+        R.pin_cap = chunk_doubles;
     }
-    if (Xs) cudaFree(Xs);
-    if (ys) cudaFree(ys);
-    if (ws) cudaFree(ws);
+    static int n_threads = 0;
+    if (!n_threads) {
+        const char* e = getenv("APOP_B200_PIN_THREADS");
+        n_threads = e ? atoi(e) : 8;
+        const int hw = (int)std::thread::hardware_concurrency();
+        if (hw > 0 && n_threads > hw) n_threads = hw;
+        if (n_threads < 1) n_threads = 1;
+    }
+    bool ok = true;
+    int ci = 0;
+    for (size_t r0 = 0; ok && r0 < n; r0 += chunk, ci++) {
+        const size_t rows = (n - r0 < chunk) ? n - r0 : chunk;
+        const int buf = ci & 1;
+        if (ci >= 2) ok = cuda_ok(cudaEventSynchronize(R.pin_ev[buf]), "pin staging wait");   // chunk ci-2 has left this buffer
+        double* hX = R.pin_host[buf];
+        double* hy_ = hX + rows * (size_t)k;
+        double* hw_ = hy_ + (hy ? rows : 0);
+        auto gather = [&](size_t a0, size_t a1) {   // rows [a0, a1) of this chunk
+            if (k) {
+                if (d->matrix->tda == (size_t)k) memcpy(hX + a0 * k, d->matrix->data + (r0 + a0) * k, (a1 - a0) * k * sizeof(double));
+                else for (size_t i = a0; i < a1; i++) memcpy(hX + i * k, d->matrix->data + (r0 + i) * d->matrix->tda, k * sizeof(double));
+            }
+            if (hy) {
+                if (d->vector->stride == 1) memcpy(hy_ + a0, d->vector->data + r0 + a0, (a1 - a0) * sizeof(double));
+                else for (size_t i = a0; i < a1; i++) hy_[i] = d->vector->data[(r0 + i) * d->vector->stride];
+            }
+            if (hw) {
+                if (d->weights->stride == 1) memcpy(hw_ + a0, d->weights->data + r0 + a0, (a1 - a0) * sizeof(double));
+                else for (size_t i = a0; i < a1; i++) hw_[i] = d->weights->data[(r0 + i) * d->weights->stride];
+            }
+        };
+        const int nt = (rows * (size_t)cols < ((size_t)1 << 17)) ? 1 : n_threads;   // small chunks: not worth a thread
+        if (nt == 1) gather(0, rows);
+        else {
+            std::vector<std::thread> pool;
+            for (int t = 0; t < nt; t++) pool.emplace_back(gather, rows * t / nt, rows * (t + 1) / nt);
+            for (auto& th : pool) th.join();
+        }
+        double* dX = R.pin_dev[buf];
+        double* dy = dX + rows * (size_t)k;
+        double* dw = dy + (hy ? rows : 0);
+        ok = ok && cuda_ok(cudaMemcpyAsync(dX, hX, rows * (size_t)cols * sizeof(double), cudaMemcpyHostToDevice, R.stream), "H2D chunk");
+        ok = ok && cuda_ok(tile_pack(k ? dX : nullptr, hy ? dy : nullptr, hw ? dw : nullptr, rows, k, cols,
+                                     r->tiles + (r0 / TILE_ROWS) * (size_t)cols * TILE_ROWS, R.stream), "tile_pack");
+        ok = ok && cuda_ok(cudaEventRecord(R.pin_ev[buf], R.stream), "event");
+    }
+    ok = ok && cuda_ok(cudaStreamSynchronize(R.stream), "pin sync");
     return ok;
 }
 

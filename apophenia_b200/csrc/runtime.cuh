@@ -63,6 +63,11 @@ struct Runtime {
     int* h_err_dev = nullptr;
     double* d_vals = nullptr; // staging for host scalars to be summed across ranks
     bool auto_pin = false;
+    // pinned / device staging pair for the pipelined upload in apop_b200_pin
+    double* pin_host[2] = {nullptr, nullptr};
+    double* pin_dev[2] = {nullptr, nullptr};
+    cudaEvent_t pin_ev[2] = {nullptr, nullptr};
+    size_t pin_cap = 0;   // doubles per staging buffer
     std::unordered_map<const apop_data*, Resident*> reg;
     // stats
     unsigned long long launches = 0, n_passes = 0;
