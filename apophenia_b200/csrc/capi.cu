@@ -370,7 +370,7 @@ static bool upload(Resident* r, const apop_data* d) {
     static int n_threads = 0;
     if (!n_threads) {
         const char* e = getenv("APOP_B200_PIN_THREADS");
-        n_threads = e ? atoi(e) : 8;
+        n_threads = e ? atoi(e) : 16;
         const int hw = (int)std::thread::hardware_concurrency();
         if (hw > 0 && n_threads > hw) n_threads = hw;
         if (n_threads < 1) n_threads = 1;

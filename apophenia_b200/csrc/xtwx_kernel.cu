@@ -9,6 +9,7 @@
 // k (k+1) DFMA, so for k = 32 it is FP64-pipe bound (~1056 DFMA per lane per 32 rows).
 #include "xtwx_kernel.cuh"
 #include "families.cuh"
+#include <stdlib.h>
 
 namespace apb {
 
@@ -97,6 +98,162 @@ xtwx_kernel(const double* __restrict__ tiles, const unsigned long long n_rows, c
     grid_finalize(partials, NOUT, ticket, out, fin, red);
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Tensor-pipe variant (default): H = (W X)' [X | y] as FP64 DMMA (mma.sync m8n8k4) with the
+// rows of the tile as the contraction dimension.  Each warp stages its tile in shared memory
+// with cp.async (padded columns), computes the row weights with lane = row (x.beta against the
+// constant bank, then the family's weight), and keeps the X fragments of the tile in registers:
+// fragment (jb, ks) = X[rows ks*4 + q][columns jb*8 + g] serves both as the A operand (scaled by
+// the row weight) of column block jb and as the B operand of column block jb.  Only the upper
+// block triangle is accumulated (H is symmetric); X'y is one extra block column in GRAM mode.
+// Per 32-row tile: 8 k-steps x (JB (JB+1)/2 [+ JB]) DMMA instead of k (k+1) DFMA per lane.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma_8x8x4(double& d0, double& d1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(d0), "+d"(d1)
+        : "d"(a), "d"(b));
+}
+constexpr int XTWX_CS = 36;   // padded column stride of a staged tile (doubles)
+
+template <int KB, int MODE>
+__global__ void __launch_bounds__(XTWX_THREADS, 3)
+xtwx_dmma_kernel(const double* __restrict__ tiles, const unsigned long long n_rows, const unsigned long long n_tiles,
+                 const int K, const int cols, const int has_w, const __grid_constant__ XtwxParams prm,
+                 double* __restrict__ partials, unsigned int* __restrict__ ticket, double* __restrict__ out,
+                 const __grid_constant__ FinalizeCtx fin) {
+    constexpr int WARPS = XTWX_THREADS / 32;
+    constexpr int JB = KB / 8;
+    constexpr int NTRI = JB * (JB + 1) / 2;
+    constexpr bool WITH_Y = (MODE == XTWX_GRAM);
+    constexpr int NC = KB + 1;
+    constexpr int NOUT = KB * NC;
+    constexpr int TILE_D = (MAX_K_REG + 2) * XTWX_CS;   // X columns, y, w
+    extern __shared__ __align__(16) double smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, q = lane & 3;
+    double* tile = smem + warp * (TILE_D + 32);
+    double* wbuf = tile + TILE_D;
+    const unsigned long long gwarp = (unsigned long long)blockIdx.x * WARPS + warp;
+    const unsigned long long nwarps = (unsigned long long)gridDim.x * WARPS;
+    const int pf_dst = (lane >> 4) * XTWX_CS + (lane & 15) * 2, pf_src = lane * 2;
+
+    double acc[NTRI][2], accy[JB][2];
+#pragma unroll
+    for (int b = 0; b < NTRI; b++) acc[b][0] = acc[b][1] = 0.0;
+#pragma unroll
+    for (int b = 0; b < JB; b++) accy[b][0] = accy[b][1] = 0.0;
+
+    for (unsigned long long t = gwarp; t < n_tiles; t += nwarps) {
+        {   // stage the tile: chunk c = lane + 32 i lies in column (lane >> 4) + 2 i, 16-byte slot lane & 15
+            const double* src = tiles + t * (unsigned long long)(cols * TILE_ROWS) + pf_src;
+            const unsigned sa = (unsigned)__cvta_generic_to_shared(tile + pf_dst);
+#pragma unroll
+            for (int i = 0; i < (KB + 3) / 2; i++) {
+                const int col = (lane >> 4) + 2 * i;
+                if (col < cols)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa + i * 2 * XTWX_CS * 8), "l"(src + i * 64));
+            }
+            asm volatile("cp.async.commit_group;");
+            asm volatile("cp.async.wait_group 0;");
+        }
+        __syncwarp();
+        // ---- row weights, lane = row
+        {
+            double xb = 0.0;
+            if (MODE != XTWX_GRAM) {
+#pragma unroll
+                for (int j = 0; j < KB; j++) xb = fma((j < K) ? tile[j * XTWX_CS + lane] : 0.0, prm.beta[j], xb);
+            }
+            const double y = tile[K * XTWX_CS + lane];
+            const double w = has_w ? tile[(K + 1) * XTWX_CS + lane] : 1.0;
+            const bool valid = t * TILE_ROWS + lane < n_rows;
+            wbuf[lane] = valid ? row_weight<MODE>(xb, y, w, prm.aux) : 0.0;
+        }
+        __syncwarp();
+        // ---- fragments: X[rows ks*4+q][columns jb*8+g], and the weights of the same rows
+        double wv[8];
+#pragma unroll
+        for (int ks = 0; ks < 8; ks++) wv[ks] = wbuf[ks * 4 + q];
+#pragma unroll
+        for (int ks = 0; ks < 8; ks++) {
+            double xf[JB];
+#pragma unroll
+            for (int jb = 0; jb < JB; jb++) xf[jb] = (jb * 8 + g < K) ? tile[(jb * 8 + g) * XTWX_CS + ks * 4 + q] : 0.0;
+            int b = 0;
+#pragma unroll
+            for (int ab = 0; ab < JB; ab++) {
+                const double a = xf[ab] * wv[ks];
+#pragma unroll
+                for (int cb = ab; cb < JB; cb++, b++) dmma_8x8x4(acc[b][0], acc[b][1], a, xf[cb]);
+                if (WITH_Y) {   // the y column sits in slot n = 0 of an otherwise empty block
+                    const double yb = (g == 0) ? tile[K * XTWX_CS + ks * 4 + q] : 0.0;
+                    dmma_8x8x4(accy[ab][0], accy[ab][1], a, yb);
+                }
+            }
+        }
+        __syncwarp();   // the tile buffer is about to be overwritten
+    }
+
+    // ---- CTA reduction: expand the block triangle into the full H[j][c] layout
+    __syncthreads();
+    double* red = smem;   // NOUT doubles, accumulated warp by warp in fixed order
+    for (int v = threadIdx.x; v < NOUT; v += XTWX_THREADS) red[v] = 0.0;
+    __syncthreads();
+    for (int wv_ = 0; wv_ < WARPS; wv_++) {
+        if (warp == wv_) {
+            int b = 0;
+#pragma unroll
+            for (int ab = 0; ab < JB; ab++) {
+#pragma unroll
+                for (int cb = ab; cb < JB; cb++, b++) {
+#pragma unroll
+                    for (int e = 0; e < 2; e++) {
+                        const int a = ab * 8 + g, c = cb * 8 + 2 * q + e;
+                        // diagonal blocks hold both triangles already; off-diagonal ones are mirrored
+                        red[a * NC + c] += acc[b][e];
+                        if (cb != ab) red[c * NC + a] += acc[b][e];
+                    }
+                }
+                if (WITH_Y && q == 0) red[(ab * 8 + g) * NC + KB] += accy[ab][0];
+            }
+        }
+        __syncthreads();
+    }
+    for (int v = threadIdx.x; v < NOUT; v += XTWX_THREADS) partials[(size_t)blockIdx.x * NOUT + v] = red[v];
+    __syncthreads();
+    grid_finalize(partials, NOUT, ticket, out, fin, red);
+}
+
+template <int KB>
+static size_t xtwx_dmma_smem() {
+    const size_t ring = (size_t)(XTWX_THREADS / 32) * ((MAX_K_REG + 2) * XTWX_CS + 32) * sizeof(double);
+    const size_t red = (size_t)KB * (KB + 1) * sizeof(double);
+    return ring > red ? ring : red;
+}
+template <int KB, int MODE>
+static cudaError_t dmma_launch_one(const XtwxLaunch& L, const XtwxParams& prm) {
+    const size_t sm = xtwx_dmma_smem<KB>();
+    static bool done = false;
+    if (!done) { cudaFuncSetAttribute(xtwx_dmma_kernel<KB, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); done = true; }
+    xtwx_dmma_kernel<KB, MODE><<<L.grid, XTWX_THREADS, sm, L.stream>>>(L.tiles, L.n_rows, L.n_tiles, L.k, L.cols, L.has_w, prm,
+                                                                      L.partials, L.ticket, L.out, L.fin);
+    return cudaGetLastError();
+}
+template <int KB, int MODE>
+static int dmma_bps_one() {
+    const size_t sm = xtwx_dmma_smem<KB>();
+    cudaFuncSetAttribute(xtwx_dmma_kernel<KB, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    int nb = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, xtwx_dmma_kernel<KB, MODE>, XTWX_THREADS, sm);
+    return nb;
+}
+static bool xtwx_use_fp64_variant() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("APOP_B200_XTWX_FP64"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v == 1;
+}
+
 template <int KB>
 static size_t xtwx_smem() { return (size_t)(XTWX_THREADS / 32) * (32 * (KB + 1) + (KB + 1) * 32) * sizeof(double); }
 
@@ -128,6 +285,17 @@ int xtwx_kb(int k) { return k <= 8 ? 8 : k <= 16 ? 16 : k <= 24 ? 24 : 32; }
     default: break;                                \
     }
 cudaError_t xtwx_launch(int mode, const XtwxLaunch& L, const XtwxParams& prm) {
+    if (!xtwx_use_fp64_variant()) {
+#define APB_OP(KB, M) dmma_launch_one<KB, M>(L, prm)
+        switch (xtwx_kb(L.k)) {
+        case 8: APB_MODES(8) break;
+        case 16: APB_MODES(16) break;
+        case 24: APB_MODES(24) break;
+        case 32: APB_MODES(32) break;
+        }
+#undef APB_OP
+        return cudaErrorInvalidValue;
+    }
 #define APB_OP(KB, M) launch_one<KB, M>(L, prm)
     switch (xtwx_kb(L.k)) {
     case 8: APB_MODES(8) break;
@@ -139,6 +307,17 @@ cudaError_t xtwx_launch(int mode, const XtwxLaunch& L, const XtwxParams& prm) {
     return cudaErrorInvalidValue;
 }
 int xtwx_blocks_per_sm(int mode, int k) {
+    if (!xtwx_use_fp64_variant()) {
+#define APB_OP(KB, M) dmma_bps_one<KB, M>()
+        switch (xtwx_kb(k)) {
+        case 8: APB_MODES(8) break;
+        case 16: APB_MODES(16) break;
+        case 24: APB_MODES(24) break;
+        case 32: APB_MODES(32) break;
+        }
+#undef APB_OP
+        return 0;
+    }
 #define APB_OP(KB, M) bps_one<KB, M>()
     switch (xtwx_kb(k)) {
     case 8: APB_MODES(8) break;

@@ -344,3 +344,52 @@ def test_dot_matches_reference_dgemm(b200):
         ab.dot(d, np.ones((5, 1)), 10007)
     assert d.struct.error == b"d"
     ab.unpin(d); ab.unpin(di)
+
+
+@pytest.mark.parametrize("fam", ["probit", "logit", "poisson_reg", "ols"])
+def test_every_column_count_1_to_32(b200, oracle, fam):
+    """each K = 1..32 is its own kernel instantiation: all of them against the oracle"""
+    ab = b200
+    rng = np.random.default_rng(17)
+    n = 2500
+    for k in range(1, 33):
+        X = rng.uniform(-1, 1, (n, k)); X[:, 0] = 1
+        beta = rng.uniform(-1, 1, k) / np.sqrt(k)
+        xb = X @ beta
+        if fam == "probit":
+            y = (rng.standard_normal(n) > -xb).astype(float)
+            F, ll_o, sc_o = ab.PROBIT, oracle.probit_ll(X, y, beta), oracle.probit_score(X, y, beta)
+            m = lambda d: ab.probit_model(beta, d)
+        elif fam == "logit":
+            y = (rng.uniform(size=n) < 1 / (1 + np.exp(-xb))).astype(float)
+            F, ll_o, sc_o = ab.LOGIT, oracle.logit_ll(X, y, beta), oracle.logit_score(X, y, beta)
+            m = lambda d: ab.logit_model(beta, d)
+        elif fam == "poisson_reg":
+            y = rng.poisson(np.exp(xb)).astype(float)
+            F, ll_o, sc_o = ab.POISSON_REG, oracle.poisson_reg_ll(X, y, beta), oracle.poisson_reg_score(X, y, beta)
+            m = lambda d: ab.vector_model(beta, d)
+        else:
+            y = xb + rng.standard_normal(n)
+            F, ll_o, sc_o = ab.OLS, oracle.ols_ll(X, y, beta * 1.05), oracle.ols_score(X, y, beta * 1.05)
+            m = lambda d: ab.vector_model(beta * 1.05, d)
+        d = ab.pin(ab.Data(matrix=X, vector=y))
+        mod = m(d)
+        _check_ll(ab.log_likelihood(F, d, mod), ll_o)
+        _check_score(ab.score(F, d, mod), sc_o[0], sc_o[1])
+        ab.unpin(d)
+
+
+def test_empty_and_too_wide_inputs(b200):
+    """ragged edges: zero rows give a zero sum (apop_map_sum of nothing), k > 32 is refused loudly"""
+    ab = b200
+    d0 = ab.pin(ab.Data(matrix=np.zeros((0, 3)), vector=np.zeros(0)))
+    assert ab.log_likelihood(ab.PROBIT, d0, ab.probit_model([0.1, 0.2, 0.3], d0)) == 0.0
+    assert np.all(ab.score(ab.PROBIT, d0, ab.probit_model([0.1, 0.2, 0.3], d0)) == 0.0)
+    assert ab.map_sum(d0, ab.MAP_IDENTITY) == 0.0
+    ab.unpin(d0)
+    X = np.ones((64, 40)); y = np.zeros(64)
+    dw = ab.pin(ab.Data(matrix=X, vector=y))
+    mw = ab.probit_model(np.zeros(40), dw)
+    assert np.isnan(ab.log_likelihood(ab.PROBIT, dw, mw)) and mw.error == b"d"
+    assert "1..32" in ab.last_error()
+    ab.unpin(dw)
