@@ -136,6 +136,7 @@ extern "C" void apop_b200_finalize(void) {
     for (int b2 = 0; b2 < 2; b2++) { if (R.pin_host[b2]) cudaFreeHost(R.pin_host[b2]); if (R.pin_dev[b2]) cudaFree(R.pin_dev[b2]); R.pin_host[b2] = nullptr; R.pin_dev[b2] = nullptr; }
     R.pin_cap = 0;
     cudaFree(R.d_vals);
+    if (R.d_beta) { cudaFree(R.d_beta); R.d_beta = nullptr; }
     cudaEventDestroy(R.ev0);
     cudaEventDestroy(R.ev1);
     cudaStreamDestroy(R.stream);
@@ -580,7 +581,7 @@ static bool eval_glm(Resident* r, GlmFam fam, const double* beta, size_t P, cons
     Runtime& R = rt();
     const int K = r->k;
     if ((size_t)K != P) return set_error("parameter count %zu does not match the %d data columns", P, K);
-    if (K < 1 || K > MAX_K_REG) return set_error("k = %d columns: the fused kernels cover 1..%d", K, MAX_K_REG);
+    if (K < 1 || K > GLM_WIDE_MAX_K) return set_error("k = %d columns: the fused kernels cover 1..%d", K, GLM_WIDE_MAX_K);
     if (!r->has_y) return set_error("the data set has no outcome vector (run the model's prep first)");
     std::vector<double> key(beta, beta + P);
     for (int a = 0; a < 4; a++) key.push_back(aux ? aux[a] : 0.0);
@@ -593,9 +594,11 @@ static bool eval_glm(Resident* r, GlmFam fam, const double* beta, size_t P, cons
     // a weights column the family ignores still sits in the tile: the kernels
     // index columns by COLS, so only OLS may carry weights
     if (r->has_w && fam != GLM_OLS) return set_error("weights are only used by the OLS family; drop them before pinning");
+    const bool wide = K > MAX_K_REG;
     static int bps_cache[GLM_FAM_COUNT][MAX_K_REG + 1][2];
-    int& bps = bps_cache[fam][K][has_w ? 1 : 0];
-    if (!bps) bps = glm_blocks_per_sm(fam, K, has_w);
+    int bps_wide = 0;
+    int& bps = wide ? bps_wide : bps_cache[fam][K][has_w ? 1 : 0];
+    if (!bps) bps = wide ? glm_wide_blocks_per_sm(fam, K) : glm_blocks_per_sm(fam, K, has_w);
     if (bps <= 0) return set_error("kernel for family %d, k=%d is not available on this device", (int)fam, K);
     const int NOUT = MAX_ACC + K;
     GlmLaunch L;
@@ -606,10 +609,15 @@ static bool eval_glm(Resident* r, GlmFam fam, const double* beta, size_t P, cons
     L.fin = make_fin(NOUT);
     GlmParams prm;
     memset(&prm, 0, sizeof prm);
-    memcpy(prm.beta, beta, P * sizeof(double));
+    if (!wide) memcpy(prm.beta, beta, P * sizeof(double));
     if (aux) memcpy(prm.aux, aux, 4 * sizeof(double));
+    if (wide) {   // beta does not fit the kernel parameter: stage it in device memory
+        if (!R.d_beta && !cuda_ok(cudaMalloc(&R.d_beta, GLM_WIDE_MAX_K * sizeof(double)), "cudaMalloc(beta)")) return false;
+        if (!cuda_ok(cudaMemcpyAsync(R.d_beta, beta, P * sizeof(double), cudaMemcpyHostToDevice, R.stream), "H2D beta")) return false;
+    }
     time_begin();
-    if (!cuda_ok(glm_launch(fam, K, has_w, L, prm), "glm kernel launch")) return false;
+    if (!cuda_ok(wide ? glm_wide_launch(fam, K, r->cols, has_w, L, R.d_beta, prm.aux) : glm_launch(fam, K, has_w, L, prm),
+                 "glm kernel launch")) return false;
     time_end_record();
     R.launches++;
     if (!reduce_and_fetch(NOUT, L.fin)) return false;
@@ -1237,7 +1245,7 @@ extern "C" int apop_b200_ll_score_batched(apop_b200_family family, apop_data* d,
         const int KB = batched_kb(K), NOUT = 1 + KB;
         static int mb_env = -1;
         if (mb_env < 0) { const char* e = getenv("APOP_B200_BATCH_MB"); mb_env = (e && e[0] == '2') ? 2 : 1; }
-        const int mb = mb_env, ctas_per_sm = (mb == 1) ? 2 : 1;
+        const int mb = mb_env, ctas_per_sm = (mb == 1) ? 2 : 1;   // matches the kernels' launch bounds
         const int reps_per_cta = (BATCH_THREADS / 32) * mb * 8;
         const int n_repgroups = (int)((m + reps_per_cta - 1) / reps_per_cta);
         long long n_rowgroups = (long long)R.num_sms * ctas_per_sm / n_repgroups;

@@ -131,6 +131,11 @@ struct GlmTable<Fam, HAS_W, 0> {
     static int blocks_per_sm(int) { return 0; }
 };
 
+// wide data (32 < k <= GLM_WIDE_MAX_K): glm_wide.cu; beta is a device pointer there
+constexpr int GLM_WIDE_MAX_K = 1024;
+cudaError_t glm_wide_launch(GlmFam fam, int k, int cols, bool has_w, const GlmLaunch& L, const double* beta, const double* aux);
+int glm_wide_blocks_per_sm(GlmFam fam, int k);
+
 // defined in glm_<family>.cu
 cudaError_t glm_launch(GlmFam fam, int k, bool has_w, const GlmLaunch& L, const GlmParams& prm);
 int glm_blocks_per_sm(GlmFam fam, int k, bool has_w);

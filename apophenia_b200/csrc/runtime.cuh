@@ -62,6 +62,7 @@ struct Runtime {
     int* h_err = nullptr;     // mapped flag: a peer never arrived in the fused allreduce
     int* h_err_dev = nullptr;
     double* d_vals = nullptr; // staging for host scalars to be summed across ranks
+    double* d_beta = nullptr; // parameters of the wide (k > 32) kernels
     bool auto_pin = false;
     // pinned / device staging pair for the pipelined upload in apop_b200_pin
     double* pin_host[2] = {nullptr, nullptr};

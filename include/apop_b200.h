@@ -171,6 +171,10 @@ int apop_b200_download(const apop_data *d, double *X_rowmajor, double *y, double
 
 /* ------------------------------------------------------------------ *
  *  The path: log likelihood and score, reference signatures
+ *  Column counts: probit / binary logit / Poisson regression / OLS take 1..1024 columns
+ *  (1..32 on the register-resident kernels, wider data on a two-sweep kernel);
+ *  multinomial logit, the information matrix and the batched path take 1..32 and up to
+ *  8 outcome categories.  Anything else is refused with NaN and model->error = 'd'.
  * ------------------------------------------------------------------ */
 long double apop_b200_probit_ll(apop_data *d, apop_model *m);       /* replaces multiprobit_log_likelihood, model/apop_probit.c:104 */
 void apop_b200_probit_score(apop_data *d, gsl_vector *g, apop_model *m); /* replaces probit_dlog_likelihood, :130 */

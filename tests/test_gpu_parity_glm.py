@@ -387,9 +387,42 @@ def test_empty_and_too_wide_inputs(b200):
     assert np.all(ab.score(ab.PROBIT, d0, ab.probit_model([0.1, 0.2, 0.3], d0)) == 0.0)
     assert ab.map_sum(d0, ab.MAP_IDENTITY) == 0.0
     ab.unpin(d0)
-    X = np.ones((64, 40)); y = np.zeros(64)
+    X = np.ones((64, 1100)); y = np.zeros(64)
     dw = ab.pin(ab.Data(matrix=X, vector=y))
-    mw = ab.probit_model(np.zeros(40), dw)
+    mw = ab.probit_model(np.zeros(1100), dw)
     assert np.isnan(ab.log_likelihood(ab.PROBIT, dw, mw)) and mw.error == b"d"
-    assert "1..32" in ab.last_error()
+    assert "1..1024" in ab.last_error()
     ab.unpin(dw)
+
+
+@pytest.mark.parametrize("fam,n,k", [("probit", 20011, 40), ("probit", 5000, 33), ("logit", 9000, 64), ("poisson_reg", 6000, 100),
+                                     ("ols", 7000, 48), ("probit", 3000, 257)])
+def test_wide_data_beyond_32_columns(b200, oracle, fam, n, k):
+    """k > 32: the two-sweep kernel (glm_wide.cu); same parity bar"""
+    ab = b200
+    rng = np.random.default_rng(n + k)
+    X = rng.uniform(-1, 1, (n, k)); X[:, 0] = 1
+    beta = rng.uniform(-1, 1, k) / np.sqrt(k)
+    xb = X @ beta
+    w = None
+    if fam == "probit":
+        y = (rng.standard_normal(n) > -xb).astype(float)
+        F, want, sc, mk = ab.PROBIT, oracle.probit_ll(X, y, beta), oracle.probit_score(X, y, beta), ab.probit_model
+    elif fam == "logit":
+        y = (rng.uniform(size=n) < 1 / (1 + np.exp(-xb))).astype(float)
+        F, want, sc, mk = ab.LOGIT, oracle.logit_ll(X, y, beta), oracle.logit_score(X, y, beta), ab.logit_model
+    elif fam == "poisson_reg":
+        y = rng.poisson(np.exp(xb)).astype(float)
+        F, want, sc, mk = ab.POISSON_REG, oracle.poisson_reg_ll(X, y, beta), oracle.poisson_reg_score(X, y, beta), ab.vector_model
+    else:
+        y = xb + rng.standard_normal(n)
+        w = rng.uniform(0.5, 2, n)
+        F, want, sc, mk = ab.OLS, oracle.ols_ll(X, y, beta, w), oracle.ols_score(X, y, beta, w), ab.vector_model
+    d = ab.pin(ab.Data(matrix=X, vector=y, weights=w))
+    m = mk(beta, d)
+    launches = ab.launch_count()
+    _check_ll(ab.log_likelihood(F, d, m), want)
+    _check_score(ab.score(F, d, m), sc[0], sc[1])
+    # one fused pass for LL and score (+ the one-off lgamma constant of the Poisson regression)
+    assert ab.launch_count() == launches + (2 if fam == "poisson_reg" else 1)
+    ab.unpin(d)
