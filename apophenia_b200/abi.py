@@ -15,9 +15,9 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libapop_b200.so")
 HOSTMINI_PATH = os.path.join(_PKG, "libapop_hostmini.so")
 
-PROBIT, LOGIT, POISSON, NORMAL, OLS, POISSON_REG = range(6)
+PROBIT, LOGIT, POISSON, NORMAL, OLS, POISSON_REG, EXPONENTIAL, GAMMA, LOGNORMAL = range(9)
 FAMILY_NAMES = {PROBIT: "probit", LOGIT: "logit", POISSON: "poisson", NORMAL: "normal", OLS: "ols",
-                POISSON_REG: "poisson_reg"}
+                POISSON_REG: "poisson_reg", EXPONENTIAL: "exponential", GAMMA: "gamma", LOGNORMAL: "lognormal"}
 MAP_IDENTITY, MAP_DEV, MAP_DEV2, MAP_POISSON, MAP_LOG, MAP_EXP = range(6)
 
 
@@ -115,6 +115,12 @@ SIGNATURES = {
     "apop_b200_normal_score": (None, [_PD, _PV, _PM]),
     "apop_b200_ols_ll": (C.c_longdouble, [_PD, _PM]),
     "apop_b200_ols_score": (None, [_PD, _PV, _PM]),
+    "apop_b200_exponential_ll": (C.c_longdouble, [_PD, _PM]),
+    "apop_b200_exponential_score": (None, [_PD, _PV, _PM]),
+    "apop_b200_gamma_ll": (C.c_longdouble, [_PD, _PM]),
+    "apop_b200_gamma_score": (None, [_PD, _PV, _PM]),
+    "apop_b200_lognormal_ll": (C.c_longdouble, [_PD, _PM]),
+    "apop_b200_lognormal_score": (None, [_PD, _PV, _PM]),
     "apop_b200_poisson_reg_ll": (C.c_longdouble, [_PD, _PM]),
     "apop_b200_poisson_reg_score": (None, [_PD, _PV, _PM]),
     "apop_b200_map_sum": (C.c_double, [_PD, C.c_int, C.c_double, C.c_char]),

@@ -341,7 +341,7 @@ static bool upload(Resident* r, const apop_data* d) {
     if (!r->tiles && need)
         if (!cuda_ok(cudaMalloc(&r->tiles, need * sizeof(double)), "cudaMalloc(resident tiles)")) return false;
     r->n_rows = n; r->k = k; r->has_y = hy; r->has_w = hw; r->cols = cols; r->n_tiles = n_tiles;
-    r->memo_valid = false; r->have_lgamma_y = false; r->have_poisson = false; r->dirty = false;
+    r->memo_valid = false; r->have_lgamma_y = false; r->have_poisson = false; r->have_gamma = false; r->dirty = false;
     if (!need) return true;
 
     // Staged, pipelined upload.  Chunks of rows are gathered from the caller's (pageable,
@@ -994,6 +994,99 @@ extern "C" void apop_b200_normal_score(apop_data* d, gsl_vector* g, apop_model* 
     release(r);
 }
 
+// ---- exponential, gamma, lognormal ----------------------------------------
+// sum x, sum_{x != 0} ln x and the number of zero cells do not depend on the parameters:
+// one pass per residency, like the Poisson sums
+static bool gamma_consts(Resident* r, double* o) {
+    if (!r->have_gamma) {
+        if (!eval_cells(r, CELLS_GAMMA, 0.0, r->gam)) return false;
+        r->have_gamma = true;
+    }
+    memcpy(o, r->gam, sizeof r->gam);
+    return true;
+}
+static long double digamma_l(long double x) {   // gsl_sf_psi: recurrence to x >= 12, then the asymptotic series
+    long double r = 0;
+    while (x < 12) { r -= 1 / x; x += 1; }
+    const long double f = 1 / (x * x);
+    return r + logl(x) - 0.5L / x - f * (1.0L / 12 - f * (1.0L / 120 - f * (1.0L / 252 - f * (1.0L / 240 - f * (1.0L / 132 - f * (691.0L / 32760 - f / 12))))));
+}
+struct IidEval { bool ok = false; double o[CELLS_NOUT]; double cells = 0; std::vector<double> p; };
+static IidEval iid_entry(apop_data* d, apop_model* m, size_t nparams, int mode, double p0_index) {
+    IidEval e;
+    if (!m || !m->parameters || !d || !pack_parameters(m->parameters, e.p) || e.p.size() < nparams) { set_error("NULL model, parameters or data"); return e; }
+    Resident* r = acquire(d);
+    if (!r) return e;
+    double n, mc, vc;
+    bool ok = global_counts(r, n, mc, vc);
+    if (ok && mode == CELLS_GAMMA) ok = gamma_consts(r, e.o);
+    else if (ok) {   // lognormal: memo on mu, like the Normal
+        const double mu = e.p[(size_t)p0_index];
+        const double key[5] = {mu, 1, 0, 0, 0};
+        if (r->memo_valid && r->memo_fam == 101 && r->memo_beta.size() == 5 && !memcmp(r->memo_beta.data(), key, sizeof key))
+            memcpy(e.o, r->memo_out.data(), sizeof e.o);
+        else if ((ok = eval_cells(r, mode, mu, e.o))) {
+            r->memo_valid = true; r->memo_fam = 101;
+            r->memo_beta.assign(key, key + 5);
+            r->memo_out.assign(e.o, e.o + CELLS_NOUT);
+        }
+    }
+    e.cells = mc + vc;
+    e.ok = ok;
+    release(r);
+    return e;
+}
+extern "C" long double apop_b200_exponential_ll(apop_data* d, apop_model* m) {
+    LOCK;
+    IidEval e = iid_entry(d, m, 1, CELLS_GAMMA, 0);
+    if (!e.ok) return NAN;
+    const long double mu = e.p[0];
+    return -((long double)e.o[0] + e.o[2]) / mu - (long double)e.cells * logl(mu);
+}
+extern "C" void apop_b200_exponential_score(apop_data* d, gsl_vector* g, apop_model* m) {
+    LOCK;
+    if (!g) return;
+    IidEval e = iid_entry(d, m, 1, CELLS_GAMMA, 0);
+    if (!e.ok) { fill_nan(g); return; }
+    const long double mu = e.p[0];
+    g->data[0] = (double)(((long double)e.o[0] + e.o[2]) / (mu * mu) - (long double)e.cells / mu);
+}
+extern "C" long double apop_b200_gamma_ll(apop_data* d, apop_model* m) {
+    LOCK;
+    IidEval e = iid_entry(d, m, 2, CELLS_GAMMA, 0);
+    if (!e.ok) return NAN;
+    const long double a = e.p[0], b = e.p[1];
+    const long double nz = (long double)e.cells - e.o[4];   // cells with x != 0
+    return (a - 1) * ((long double)e.o[1] + e.o[3]) - ((long double)e.o[0] + e.o[2]) / b - nz * (lgammal(a) + a * logl(b));
+}
+extern "C" void apop_b200_gamma_score(apop_data* d, gsl_vector* g, apop_model* m) {
+    LOCK;
+    if (!g) return;
+    IidEval e = iid_entry(d, m, 2, CELLS_GAMMA, 0);
+    if (!e.ok || g->size < 2) { fill_nan(g); return; }
+    const long double a = e.p[0], b = e.p[1];
+    // a_callback has no x != 0 guard: a zero cell sends dLL/da to -inf (log 0)
+    g->data[0] = (e.o[4] > 0) ? -INFINITY
+                              : (double)(((long double)e.o[1] + e.o[3]) - (long double)e.cells * (digamma_l(a) + logl(b)));
+    g->data[g->stride] = (double)(((long double)e.o[0] + e.o[2]) / (b * b) - (long double)e.cells * a / b);
+}
+extern "C" long double apop_b200_lognormal_ll(apop_data* d, apop_model* m) {
+    LOCK;
+    IidEval e = iid_entry(d, m, 2, CELLS_LOGNORMAL, 0);
+    if (!e.ok) return NAN;
+    const long double sd = e.p[1], lnpi = 1.14472988584940017414342735135305871L, ln2 = 0.693147180559945309417232121458176568L;
+    return -((long double)e.o[1] + e.o[3]) / (2 * sd * sd) - ((long double)e.o[0] + e.o[2]) - (long double)e.cells * ((lnpi + ln2) / 2 + logl(sd));
+}
+extern "C" void apop_b200_lognormal_score(apop_data* d, gsl_vector* g, apop_model* m) {
+    LOCK;
+    if (!g) return;
+    IidEval e = iid_entry(d, m, 2, CELLS_LOGNORMAL, 0);
+    if (!e.ok || g->size < 2) { fill_nan(g); return; }
+    const long double mu = e.p[0], sd = e.p[1];
+    g->data[0] = (double)((((long double)e.o[0] + e.o[2]) - mu * (long double)e.cells) / (sd * sd));
+    g->data[g->stride] = (double)(((long double)e.o[1] + e.o[3]) / (sd * sd * sd) - (long double)e.cells / sd);
+}
+
 extern "C" double apop_b200_map_sum(apop_data* d, apop_b200_map_fn fn, double p0, char part) {
     LOCK;
     if (!d) { set_error("NULL data"); return 0; }  // apop_map_sum returns 0 on NULL input
@@ -1133,6 +1226,9 @@ extern "C" double apop_b200_ll_score(apop_b200_family family, apop_data* d, cons
     case APOP_B200_NORMAL: ll = apop_b200_normal_ll(d, &m); if (score) apop_b200_normal_score(d, &g, &m); break;
     case APOP_B200_OLS: ll = apop_b200_ols_ll(d, &m); if (score) apop_b200_ols_score(d, &g, &m); break;
     case APOP_B200_POISSON_REG: ll = apop_b200_poisson_reg_ll(d, &m); if (score) apop_b200_poisson_reg_score(d, &g, &m); break;
+    case APOP_B200_EXPONENTIAL: ll = apop_b200_exponential_ll(d, &m); if (score) apop_b200_exponential_score(d, &g, &m); break;
+    case APOP_B200_GAMMA: ll = apop_b200_gamma_ll(d, &m); if (score) apop_b200_gamma_score(d, &g, &m); break;
+    case APOP_B200_LOGNORMAL: ll = apop_b200_lognormal_ll(d, &m); if (score) apop_b200_lognormal_score(d, &g, &m); break;
     default: set_error("unknown family %d", (int)family);
     }
     return (double)ll;
@@ -1355,6 +1451,9 @@ static Entry entry_of(apop_b200_family f) {
     case APOP_B200_NORMAL: return {apop_b200_normal_ll, apop_b200_normal_score};
     case APOP_B200_OLS: return {apop_b200_ols_ll, apop_b200_ols_score};
     case APOP_B200_POISSON_REG: return {apop_b200_poisson_reg_ll, apop_b200_poisson_reg_score};
+    case APOP_B200_EXPONENTIAL: return {apop_b200_exponential_ll, apop_b200_exponential_score};
+    case APOP_B200_GAMMA: return {apop_b200_gamma_ll, apop_b200_gamma_score};
+    case APOP_B200_LOGNORMAL: return {apop_b200_lognormal_ll, apop_b200_lognormal_score};
     default: return {nullptr, nullptr};
     }
 }

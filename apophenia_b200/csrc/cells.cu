@@ -26,6 +26,14 @@ __device__ __forceinline__ void cell_eval(double x, double p0, double& f0, doubl
         f1 = (x == 0.0 || invalid) ? 0.0 : lgamma(x + 1.0);
     } else if (MODE == CELLS_IDENTITY) {
         f0 = x; f1 = 0.0;
+    } else if (MODE == CELLS_GAMMA) {
+        bad += (x == 0.0) ? 1 : 0;                 // here: the number of zero cells
+        f0 = x;
+        f1 = (x != 0.0) ? fm_log(x) : 0.0;
+    } else if (MODE == CELLS_LOGNORMAL) {
+        const double l = log(x);                   // ln 0 = -inf propagates, as in the reference
+        f0 = l;
+        f1 = (l - p0) * (l - p0);
     } else if (MODE == CELLS_LOG) {
         f0 = log(x); f1 = 0.0;
     } else {  // CELLS_EXP
@@ -101,6 +109,8 @@ cudaError_t cells_launch(int mode, const double* tiles, size_t n_rows, size_t n_
         APB_CELLS(CELLS_POISSON)
         APB_CELLS(CELLS_LOG)
         APB_CELLS(CELLS_EXP)
+        APB_CELLS(CELLS_GAMMA)
+        APB_CELLS(CELLS_LOGNORMAL)
     default: return cudaErrorInvalidValue;
     }
 #undef APB_CELLS

@@ -4,7 +4,9 @@
 #include <stddef.h>
 
 namespace apb {
-enum CellsMode { CELLS_IDENTITY = 0, CELLS_NORMAL = 1, CELLS_POISSON = 2, CELLS_LOG = 3, CELLS_EXP = 4 };
+enum CellsMode { CELLS_IDENTITY = 0, CELLS_NORMAL = 1, CELLS_POISSON = 2, CELLS_LOG = 3, CELLS_EXP = 4,
+                 CELLS_GAMMA = 5,       // f0 = x, f1 = ln x over non-zero cells; slot 4 counts the ZERO cells
+                 CELLS_LOGNORMAL = 6 }; // f0 = ln x, f1 = (ln x - p0)^2
 constexpr int CELLS_THREADS = 256;
 constexpr int CELLS_NOUT = 5;  // matrix s0, s1; vector s0, s1; count of -inf cells
 cudaError_t cells_launch(int mode, const double* tiles, size_t n_rows, size_t n_tiles, int k,

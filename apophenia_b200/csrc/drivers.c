@@ -41,9 +41,10 @@ static void *dev(const char *name) {
 }
 int apop_b200_family_of(apop_model *m) {
     static const char *names[] = {"apop_b200_probit_ll", "apop_b200_logit_ll", "apop_b200_poisson_ll", "apop_b200_normal_ll",
-                                  "apop_b200_ols_ll", "apop_b200_poisson_reg_ll"};
+                                  "apop_b200_ols_ll", "apop_b200_poisson_reg_ll", "apop_b200_exponential_ll",
+                                  "apop_b200_gamma_ll", "apop_b200_lognormal_ll"};
     if (!m || !m->log_likelihood) return -1;
-    for (int f = 0; f < 6; f++) { void *p = dlsym(RTLD_DEFAULT, names[f]); if (p && p == (void *)m->log_likelihood) return f; }
+    for (int f = 0; f < 9; f++) { void *p = dlsym(RTLD_DEFAULT, names[f]); if (p && p == (void *)m->log_likelihood) return f; }
     return -1;
 }
 

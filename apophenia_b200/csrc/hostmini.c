@@ -399,6 +399,10 @@ static apop_model poisson_obj = {.name = "Poisson distribution", .vsize = 1, .ds
 static apop_model normal_obj = {.name = "Normal distribution", .vsize = 2, .dsize = 1};
 static apop_model ols_obj = {.name = "Ordinary Least Squares", .vsize = -1, .dsize = -1, .prep = ols_prep};
 static apop_model poisson_reg_obj = {.name = "Poisson regression", .vsize = -1, .dsize = -1, .prep = ols_prep};
+static apop_model exponential_obj = {.name = "Exponential distribution", .vsize = 1, .dsize = 1};
+static apop_model gamma_obj = {.name = "Gamma distribution", .vsize = 2, .dsize = 1};
+static apop_model lognormal_obj = {.name = "Lognormal distribution", .vsize = 2, .dsize = 1};
+apop_model *apop_exponential = &exponential_obj, *apop_gamma = &gamma_obj, *apop_lognormal = &lognormal_obj;
 apop_model *apop_probit = &probit_obj, *apop_logit = &logit_obj, *apop_poisson = &poisson_obj,
            *apop_normal = &normal_obj, *apop_ols = &ols_obj, *apop_poisson_regression = &poisson_reg_obj;
 

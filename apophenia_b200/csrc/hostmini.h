@@ -90,6 +90,7 @@ apop_mcmc_settings apop_mcmc_settings_defaults(void);
 apop_data *apop_model_metropolis(apop_data *d, apop_model *m, apop_mcmc_settings s);
 apop_data *apop_b200_metropolis_chains(apop_data *d, apop_model *m, apop_mcmc_settings s);
 
+extern apop_model *apop_exponential, *apop_gamma, *apop_lognormal;
 extern apop_model *apop_probit, *apop_logit, *apop_poisson, *apop_normal, *apop_ols, *apop_poisson_regression;
 
 #ifdef __cplusplus

@@ -28,6 +28,8 @@ struct Resident {
     double lgamma_y = 0.0;   // sum_i lgamma(y_i + 1)
     bool have_poisson = false;
     double pois[CELLS_NOUT];
+    bool have_gamma = false;   // sum x, sum ln x over non-zero cells, zero-cell count (exponential / gamma)
+    double gam[CELLS_NOUT];
     // last evaluation (f then df at the same beta costs one pass)
     bool memo_valid = false;
     int memo_fam = -1;

@@ -102,7 +102,10 @@ typedef enum {
     APOP_B200_NORMAL = 3,       /* iid Normal(mu,sigma)     model/apop_normal.c:38-50,108-118 */
     APOP_B200_OLS = 4,          /* Gaussian-error OLS       model/apop_ols.c:129-205 */
     APOP_B200_POISSON_REG = 5,  /* Poisson regression (new model, no reference counterpart) */
-    APOP_B200_MODEL_COUNT = 6
+    APOP_B200_EXPONENTIAL = 6,  /* iid Exponential(mu)      model/apop_exponential.c:33-52 */
+    APOP_B200_GAMMA = 7,        /* iid Gamma(a, b)          model/apop_gamma.c:31-62 */
+    APOP_B200_LOGNORMAL = 8,    /* iid Lognormal(mu, sigma) model/apop_normal.c:166-237 */
+    APOP_B200_MODEL_COUNT = 9
 } apop_b200_family;
 
 /* ------------------------------------------------------------------ *
@@ -186,6 +189,13 @@ long double apop_b200_normal_ll(apop_data *d, apop_model *m);       /* replaces 
 void apop_b200_normal_score(apop_data *d, gsl_vector *g, apop_model *m);  /* replaces normal_dlog_likelihood, :108 */
 long double apop_b200_ols_ll(apop_data *d, apop_model *m);          /* replaces ols_log_likelihood, model/apop_ols.c:129 */
 void apop_b200_ols_score(apop_data *d, gsl_vector *g, apop_model *m);     /* replaces ols_score, :175 */
+/* the next iid distributions on the same apop_map_sum shape */
+long double apop_b200_exponential_ll(apop_data *d, apop_model *m);      /* replaces exponential_log_likelihood, model/apop_exponential.c:33 */
+void apop_b200_exponential_score(apop_data *d, gsl_vector *g, apop_model *m);  /* :42 */
+long double apop_b200_gamma_ll(apop_data *d, apop_model *m);            /* replaces gamma_log_likelihood, model/apop_gamma.c:36 */
+void apop_b200_gamma_score(apop_data *d, gsl_vector *g, apop_model *m);        /* :56 */
+long double apop_b200_lognormal_ll(apop_data *d, apop_model *m);        /* replaces lognormal_log_likelihood, model/apop_normal.c:170 */
+void apop_b200_lognormal_score(apop_data *d, gsl_vector *g, apop_model *m);    /* :228 */
 long double apop_b200_poisson_reg_ll(apop_data *d, apop_model *m);  /* new model behind the same API */
 void apop_b200_poisson_reg_score(apop_data *d, gsl_vector *g, apop_model *m);
 

@@ -600,6 +600,100 @@ void oracle_information(int family, const double *X, size_t tda, const double *y
     }
 }
 
+
+/* ---- more iid distributions on the same apop_map_sum shape ---- */
+static ld digamma_l(ld x) { /* gsl_sf_psi stand-in: recurrence up to x >= 12, then the asymptotic series */
+    ld r = 0;
+    while (x < 12) { r -= 1 / x; x += 1; }
+    const ld f = 1 / (x * x);
+    return r + logl(x) - 0.5L / x - f * (1.0L / 12 - f * (1.0L / 120 - f * (1.0L / 252 - f * (1.0L / 240 - f * (1.0L / 132 - f * (691.0L / 32760 - f / 12))))));
+}
+double oracle_digamma(double x) { return (double)digamma_l(x); }
+
+/* exponential_log_likelihood / _dlog_likelihood, model/apop_exponential.c:33-52:
+ * LL = -(sum x)/mu - tsize ln mu;  dLL/dmu = (sum x)/mu^2 - tsize/mu */
+void oracle_exponential(const double *v, size_t vsize, const double *M, size_t tda, size_t m1, size_t m2,
+                        double mu, int mode, long double *ll_out, long double *g_out) {
+    const int tsize = (int)(vsize + m1 * m2);
+    ld sv = 0, sm = 0;
+    for (size_t i = 0; i < vsize; i++) sv += v[i];
+    for (size_t i = 0; i < m1; i++) for (size_t j = 0; j < m2; j++) sm += M[i * tda + j];
+    if (mode == ORACLE_FAITHFUL) {
+        double ll = -(double)(sm + sv) / mu;   /* the two long double sums are added, then rounded */
+        ll -= tsize * log(mu);
+        double dl = (double)(sm + sv);
+        dl /= mu * mu;
+        dl -= tsize / mu;
+        *ll_out = ll; g_out[0] = dl;
+    } else {
+        *ll_out = -(sm + sv) / (ld)mu - (ld)tsize * logl(mu);
+        g_out[0] = (sm + sv) / ((ld)mu * mu) - (ld)tsize / mu;
+    }
+}
+
+/* gamma_log_likelihood / gamma_dlog_likelihood, model/apop_gamma.c:31-62:
+ * LL = sum_{x != 0} [(a-1) ln x - x/b - (lnGamma(a) + a ln b)];
+ * dLL/da = sum (ln x - (psi(a) + ln b)) over ALL cells,  dLL/db = sum (x/b^2 - a/b) */
+void oracle_gamma(const double *v, size_t vsize, const double *M, size_t tda, size_t m1, size_t m2,
+                  double a, double b, int mode, long double *ll_out, long double *g_out) {
+    const size_t n = vsize + m1 * m2;
+    ld ll = 0, g0 = 0, g1 = 0;
+    if (mode == ORACLE_FAITHFUL) {
+        const double c = lgamma(a) + a * log(b), psi_ln = (double)digamma_l(a) + log(b), ab = a / b;
+        ld llv = 0, llm = 0, g0v = 0, g0m = 0, g1v = 0, g1m = 0;
+        for (size_t i = 0; i < n; i++) {
+            const double x = i < vsize ? v[i] : M[((i - vsize) / m2) * tda + (i - vsize) % m2];
+            const double t = x ? ((a - 1) * log(x) - x / b - c) : 0;
+            const double t0 = log(x) - psi_ln, t1 = x / (b * b) - ab;
+            if (i < vsize) { llv += t; g0v += t0; g1v += t1; } else { llm += t; g0m += t0; g1m += t1; }
+        }
+        ll = (double)(llv + llm); g0 = (double)(g0v + g0m); g1 = (double)(g1v + g1m);
+    } else {
+        const ld c = lgammal(a) + (ld)a * logl(b), psi_ln = digamma_l(a) + logl(b);
+        for (size_t i = 0; i < n; i++) {
+            const double x = i < vsize ? v[i] : M[((i - vsize) / m2) * tda + (i - vsize) % m2];
+            if (x) ll += ((ld)a - 1) * logl(x) - x / (ld)b - c;
+            g0 += logl(x) - psi_ln;
+            g1 += x / ((ld)b * b) - (ld)a / b;
+        }
+    }
+    *ll_out = ll; g_out[0] = g0; g_out[1] = g1;
+}
+
+/* lognormal_log_likelihood / _dlog_likelihood, model/apop_normal.c:166-237:
+ * LL = -sum (ln x - mu)^2/(2 sd^2) - sum ln x - tsize ((ln pi + ln 2)/2 + ln sd) */
+void oracle_lognormal(const double *v, size_t vsize, const double *M, size_t tda, size_t m1, size_t m2,
+                      double mu, double sd, int mode, long double *ll_out, long double *g_out) {
+    const size_t n = vsize + m1 * m2;
+    const int tsize = (int)n;
+    ld s1v = 0, s1m = 0, s2v = 0, s2m = 0;
+    for (size_t i = 0; i < n; i++) {
+        const double x = i < vsize ? v[i] : M[((i - vsize) / m2) * tda + (i - vsize) % m2];
+        if (mode == ORACLE_FAITHFUL) {
+            const double l = log(x), d = l - mu;
+            if (i < vsize) { s1v += l; s2v += d * d; } else { s1m += l; s2m += d * d; }
+        } else {
+            const ld l = logl(x), d = l - mu;
+            s1v += l; s2v += d * d;
+        }
+    }
+    if (mode == ORACLE_FAITHFUL) {
+        const double S1 = (double)(s1v + s1m), S2 = (double)(s2v + s2m);
+        ld ll = -S2;
+        ll /= (2 * (sd * sd));
+        ll -= S1;
+        ll -= tsize * ((1.14472988584940017414 + M_LN2) / 2 + log(sd));
+        *ll_out = ll;
+        g_out[0] = (S1 - mu * tsize) / (sd * sd);
+        g_out[1] = S2 / (sd * sd * sd) - tsize / sd;
+    } else {
+        const ld lnpi = 1.14472988584940017414342735135305871L, ln2 = 0.693147180559945309417232121458176568L;
+        *ll_out = -(s2v) / (2 * (ld)sd * sd) - s1v - (ld)tsize * ((lnpi + ln2) / 2 + logl(sd));
+        g_out[0] = (s1v - (ld)mu * tsize) / ((ld)sd * sd);
+        g_out[1] = s2v / ((ld)sd * sd * sd) - (ld)tsize / sd;
+    }
+}
+
 /* ---- structure-faithful timed path ------------ */
 static double now_s(void) {
     struct timespec t;

@@ -97,6 +97,17 @@ void oracle_poisson_reg_score(const double *X, size_t tda, const double *y, size
 void oracle_map_sum(const double *v, size_t vsize, const double *M, size_t tda, size_t m1,
                     size_t m2, int fn, double p0, int mode, long double *out);
 
+/* more iid distributions on the apop_map_sum shape: exponential
+ * (model/apop_exponential.c:33-52), gamma (model/apop_gamma.c:31-62; gsl_sf_psi -> recurrence +
+ * asymptotic series), lognormal (model/apop_normal.c:166-237).  g_out: 1, 2, 2 entries. */
+double oracle_digamma(double x);
+void oracle_exponential(const double *v, size_t vsize, const double *M, size_t tda, size_t m1, size_t m2,
+                        double mu, int mode, long double *ll_out, long double *g_out);
+void oracle_gamma(const double *v, size_t vsize, const double *M, size_t tda, size_t m1, size_t m2,
+                  double a, double b, int mode, long double *ll_out, long double *g_out);
+void oracle_lognormal(const double *v, size_t vsize, const double *M, size_t tda, size_t m1, size_t m2,
+                      double mu, double sd, int mode, long double *ll_out, long double *g_out);
+
 /* observed information -d2LL/db db' for probit / binary logit / poisson_reg
  * (exact mode only; no reference counterpart) */
 void oracle_information(int family, const double *X, size_t tda, const double *y, size_t N,

@@ -158,6 +158,31 @@ def normal_score(v, M, mu, sigma, mode=EXACT):
     return out
 
 
+def _iid(fn, v, M, params, ng, mode):
+    keep, vp, vs, Mp, tda, m1, m2 = _vm(v, M)
+    ll, lp = _ld(1); g, gp = _ld(ng)
+    getattr(lib(), fn)(vp, vs, Mp, tda, m1, m2, *[C.c_double(p) for p in params], C.c_int(mode), lp, gp)
+    return ll[0], g
+
+
+def exponential(v, M, mu, mode=EXACT):
+    """(LL, score) of the iid exponential model"""
+    return _iid("oracle_exponential", v, M, [mu], 1, mode)
+
+
+def gamma(v, M, a, b, mode=EXACT):
+    return _iid("oracle_gamma", v, M, [a, b], 2, mode)
+
+
+def lognormal(v, M, mu, sd, mode=EXACT):
+    return _iid("oracle_lognormal", v, M, [mu, sd], 2, mode)
+
+
+def digamma(x):
+    lib().oracle_digamma.restype = C.c_double
+    return lib().oracle_digamma(C.c_double(x))
+
+
 def map_sum(v, M, fn, p0=0.0, mode=EXACT):
     keep, vp, vs, Mp, tda, m1, m2 = _vm(v, M)
     out, op = _ld(1)

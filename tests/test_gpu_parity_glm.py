@@ -426,3 +426,35 @@ def test_wide_data_beyond_32_columns(b200, oracle, fam, n, k):
     # one fused pass for LL and score (+ the one-off lgamma constant of the Poisson regression)
     assert ab.launch_count() == launches + (2 if fam == "poisson_reg" else 1)
     ab.unpin(d)
+
+
+def test_exponential_gamma_lognormal(b200, oracle):
+    """the next iid models on the map_sum shape: LL and score at fixed
+    parameters against the oracle; parameter-independent sums are reduced once per residency"""
+    ab = b200
+    rng = np.random.default_rng(6)
+    M = rng.gamma(2.5, 1.7, (20011, 5)); v = rng.gamma(2.5, 1.7, 20011)
+    for mat, vec in ((M, None), (M, v)):
+        d = ab.pin(ab.Data(matrix=mat, vector=vec))
+        launches = ab.launch_count()
+        for fam, params, ofn in ((ab.EXPONENTIAL, [3.9], oracle.exponential), (ab.GAMMA, [2.4, 1.8], oracle.gamma),
+                                 (ab.GAMMA, [2.6, 1.5], oracle.gamma)):
+            m = ab.vector_model(params, d)
+            want, gw = ofn(vec, mat, *params)
+            _check_ll(ab.log_likelihood(fam, d, m), want)
+            g = ab.score(fam, d, m)
+            assert np.all(np.abs(g - gw.astype(float)) <= 1e-11 * np.maximum(np.abs(gw.astype(float)), mat.size))
+        assert ab.launch_count() == launches + 1           # one pass serves every parameter value
+        m = ab.vector_model([0.9, 0.7], d)
+        want, gw = oracle.lognormal(vec, mat, 0.9, 0.7)
+        _check_ll(ab.log_likelihood(ab.LOGNORMAL, d, m), want)
+        g = ab.score(ab.LOGNORMAL, d, m)
+        assert np.all(np.abs(g - gw.astype(float)) <= 1e-11 * np.maximum(np.abs(gw.astype(float)), mat.size))
+        ab.unpin(d)
+    Mz = M.copy(); Mz[3, 2] = 0.0                           # a zero cell: finite gamma LL, dLL/da = -inf
+    d = ab.pin(ab.Data(matrix=Mz))
+    m = ab.vector_model([2.4, 1.8], d)
+    want, gw = oracle.gamma(None, Mz, 2.4, 1.8)
+    _check_ll(ab.log_likelihood(ab.GAMMA, d, m), want)
+    assert ab.score(ab.GAMMA, d, m)[0] == -np.inf
+    ab.unpin(d)
