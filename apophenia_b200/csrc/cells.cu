@@ -55,27 +55,43 @@ cells_kernel(const double* __restrict__ tiles, unsigned long long n_rows, unsign
     for (unsigned long long t = gwarp; t < n_tiles; t += nwarps) {
         const double* base = tiles + t * (unsigned long long)cols * TILE_ROWS + lane;
         const bool valid = t * TILE_ROWS + lane < n_rows;
+        // plain sums within the tile (k terms), one compensated add per tile: the FP64 pipe
+        // must stay under 8 bytes per cell of HBM time
+        double s0 = 0.0, s1 = 0.0;
+        int b = 0;
         int j = 0;
-        for (; j + 8 <= k; j += 8) {
-            double x[8];
+        for (; j + 16 <= k; j += 16) {
+            double x[16];
 #pragma unroll
-            for (int u = 0; u < 8; u++) x[u] = ld_stream(base + (j + u) * TILE_ROWS);
+            for (int u = 0; u < 16; u++) x[u] = ld_stream(base + (j + u) * TILE_ROWS);
 #pragma unroll
-            for (int u = 0; u < 8; u++) {
-                double f0, f1; int b = 0;
+            for (int u = 0; u < 16; u++) {
+                double f0, f1;
                 cell_eval<MODE>(x[u], p0, f0, f1, b);
-                if (valid) { m0.add(f0); m1.add(f1); bad += b; }
+                s0 += f0; s1 += f1;
+            }
+        }
+        for (; j + 4 <= k; j += 4) {
+            double x[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) x[u] = ld_stream(base + (j + u) * TILE_ROWS);
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                double f0, f1;
+                cell_eval<MODE>(x[u], p0, f0, f1, b);
+                s0 += f0; s1 += f1;
             }
         }
         for (; j < k; j++) {
-            double f0, f1; int b = 0;
+            double f0, f1;
             cell_eval<MODE>(ld_stream(base + j * TILE_ROWS), p0, f0, f1, b);
-            if (valid) { m0.add(f0); m1.add(f1); bad += b; }
+            s0 += f0; s1 += f1;
         }
+        if (valid) { m0.add(s0); m1.add(s1); bad += b; }
         if (ycol >= 0) {
-            double f0, f1; int b = 0;
-            cell_eval<MODE>(ld_stream(base + ycol * TILE_ROWS), p0, f0, f1, b);
-            if (valid) { v0.add(f0); v1.add(f1); bad += b; }
+            double f0, f1; int by = 0;
+            cell_eval<MODE>(ld_stream(base + ycol * TILE_ROWS), p0, f0, f1, by);
+            if (valid) { v0.add(f0); v1.add(f1); bad += by; }
         }
     }
     __shared__ double red[WARPS][CELLS_NOUT];
