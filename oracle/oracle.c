@@ -705,6 +705,21 @@ int oracle_max_threads(void) { return omp_get_num_procs(); }
 typedef double (*row_fn)(double xb, double y);
 static row_fn volatile probit_fn_ptr = probit_row_faithful;
 
+/* the LL half alone, threaded as apop_map threads it (OMP_for over rows, apop_mapply.m4.c:240) */
+void oracle_probit_ll_omp(const double *X, size_t tda, const double *y, size_t N, size_t k,
+                          const double *beta, int threads, long double *ll_out) {
+    omp_set_num_threads(threads > 0 ? threads : omp_get_num_procs());
+    double *xb = malloc(sizeof(double) * (N ? N : 1));
+    ref_dgemm(X, tda, N, k, beta, 1, 1, xb);
+    double *mapped = malloc(sizeof(double) * (N ? N : 1));
+    row_fn f = probit_fn_ptr;
+#pragma omp parallel for
+    for (size_t i = 0; i < N; i++) mapped[i] = f(xb[i], y[i]);
+    *ll_out = (double)ref_vector_sum(mapped, N);
+    free(mapped);
+    free(xb);
+}
+
 double oracle_time_probit_ll_score(const double *X, size_t tda, const double *y, size_t N,
                                    size_t k, const double *beta, int threads, double *ll_out,
                                    double *g_out, double *sec_ll, double *sec_score) {

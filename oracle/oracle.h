@@ -116,6 +116,8 @@ void oracle_information(int family, const double *X, size_t tda, const double *y
 /* Structure-faithful timed path for the CPU baseline:
  * LL = materialised dgemm + omp row map through a function pointer + serial
  * long double sum; score = dgemm again + serial loop.  Returns seconds. */
+void oracle_probit_ll_omp(const double *X, size_t tda, const double *y, size_t N, size_t k,
+                          const double *beta, int threads, long double *ll_out);
 double oracle_time_probit_ll_score(const double *X, size_t tda, const double *y, size_t N,
                                    size_t k, const double *beta, int threads, double *ll_out,
                                    double *g_out, double *sec_ll, double *sec_score);

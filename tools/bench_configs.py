@@ -152,7 +152,47 @@ def cfg_metropolis(rows=50_000_000, k=24, m=256, periods=200):
             "single_chain_seconds": dt1, "single_chain_steps_per_s": periods / dt1, "acceptance_rate": acc}
 
 
-ALL = {"bootstrap_cov": cfg_bootstrap_cov, "metropolis": cfg_metropolis, "logit8": cfg_logit8, "bootstrap": cfg_bootstrap, "chains": cfg_chains, "poisson": cfg_poisson, "newton": cfg_newton}
+def cfg_config1(rows=1_000_000, k=10):
+    """BASELINE config 1: apop_estimate(probit, BFGS) on 1M x 10 -- the SAME host optimizer (csrc/mle.c)
+    over the restated reference CPU path (oracle/cpu_models.c, all host cores) and over the device entries"""
+    import ctypes as C
+    from apophenia_b200 import abi, host
+    h, lib = host.lib(), abi.load_library()
+    om = C.CDLL(os.path.join(ROOT, "oracle", "liboracle_models.so"))
+    rng = np.random.default_rng(8)
+    beta = rng.uniform(-1, 1, k)
+    X = rng.uniform(-1, 1, (rows, k)); X[:, 0] = 1
+    y = (rng.standard_normal(rows) > -(X @ beta)).astype(float)
+    raw = X.copy(); raw[:, 0] = y
+    settings = dict(method="BFGS cg", tolerance=1e-9, relative_tolerance=True, max_iterations=500)
+    # --- CPU arm
+    d = host.data_from_numpy(raw)
+    m = h.apop_model_copy(host.model_object(abi.PROBIT))
+    ll_addr = C.cast(om.oracle_model_probit_ll, C.c_void_p).value
+    m.contents.log_likelihood = ll_addr
+    h.apop_vtable_add(b"apop_score", C.cast(om.oracle_model_probit_score, C.c_void_p), ll_addr)
+    keep = []
+    host.mle_settings(m, keep=keep, **settings)
+    t0 = time.perf_counter()
+    est_c = h.apop_estimate(d, m)
+    t_cpu = time.perf_counter() - t0
+    rep_c = h.apop_mle_last_report()
+    p_cpu = host.parameters_of(est_c)
+    cpu = {"seconds": t_cpu, "iterations": rep_c.iterations, "passes": rep_c.f_evals, "status": rep_c.status}
+    h.apop_vtable_drop(b"apop_score", ll_addr)
+    # --- device arm (includes prep + pin, i.e. the full apop_estimate as a user calls it)
+    d2 = host.data_from_numpy(raw)
+    t0 = time.perf_counter()
+    est_g, p_gpu, rep_g = host.estimate(abi.PROBIT, d2, **settings)
+    t_gpu = time.perf_counter() - t0
+    return {"config": f"apop_estimate(probit, BFGS), {rows}x{k}: same optimizer, CPU restated path vs B200", "cpu": cpu,
+            "cpu_cores": os.cpu_count(), "gpu": {"seconds_incl_prep_and_pin": t_gpu, "mle_seconds": rep_g["seconds"],
+                                                 "iterations": rep_g["iterations"], "passes": rep_g["f_evals"], "status": rep_g["status"]},
+            "max_rel_param_diff": float(np.max(np.abs(p_gpu - p_cpu) / np.abs(p_cpu))),
+            "speedup_mle": (t_cpu) / rep_g["seconds"]}
+
+
+ALL = {"config1": cfg_config1, "bootstrap_cov": cfg_bootstrap_cov, "metropolis": cfg_metropolis, "logit8": cfg_logit8, "bootstrap": cfg_bootstrap, "chains": cfg_chains, "poisson": cfg_poisson, "newton": cfg_newton}
 
 if __name__ == "__main__":
     ab.init(0)
