@@ -20,10 +20,16 @@ _lp = C.POINTER(C.c_longdouble)
 def build(force=False):
     """Compile liboracle.so with the committed Makefile (gcc -O3 -fopenmp)."""
     so = os.path.join(_HERE, "liboracle.so")
-    src = [os.path.join(_HERE, f) for f in ("oracle.c", "oracle.h", "Makefile")]
+    src = [os.path.join(_HERE, f) for f in ("oracle.c", "oracle.h", "cpu_models.c", "Makefile")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src):
-        subprocess.check_call(["make", "-s", "-C", _HERE, "liboracle.so"])
+        subprocess.check_call(["make", "-s", "-C", _HERE, "all"])
     return so
+
+
+def models_lib():
+    """oracle/cpu_models.c: the oracle behind reference-signature log_likelihood / score entries"""
+    build()
+    return C.CDLL(os.path.join(_HERE, "liboracle_models.so"))
 
 
 def lib():

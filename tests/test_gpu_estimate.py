@@ -90,3 +90,30 @@ def test_metropolis_style_ll_only_calls(b200, oracle):
         assert abs(ll - want) <= 1e-12 * abs(want)
         b = prop
     ab.unpin(d)
+
+
+def test_config1_shape_same_optimizer_two_back_ends(b200, host, oracle):
+    """BASELINE config 1 in small: apop_estimate(probit, BFGS) by the SAME host optimizer over the
+    restated reference CPU path (C entries, oracle/cpu_models.c) and over the device entries:
+    same iteration count, parameters to 1e-8 relative"""
+    from apophenia_b200 import abi
+    h = host.lib()
+    om = oracle.models_lib()
+    X, y, beta = gen_probit_logit_sample(200000, 10, seed=8)
+    raw = X.copy(); raw[:, 0] = y
+    settings = dict(method="BFGS cg", tolerance=1e-9, relative_tolerance=True, max_iterations=500)
+    d = host.data_from_numpy(raw)
+    m = h.apop_model_copy(host.model_object(abi.PROBIT))
+    ll_addr = C.cast(om.oracle_model_probit_ll, C.c_void_p).value
+    m.contents.log_likelihood = ll_addr
+    h.apop_vtable_add(b"apop_score", C.cast(om.oracle_model_probit_score, C.c_void_p), ll_addr)
+    keep = []
+    host.mle_settings(m, keep=keep, **settings)
+    est_c = h.apop_estimate(d, m)
+    rep_c = h.apop_mle_last_report()
+    p_cpu = host.parameters_of(est_c)
+    h.apop_vtable_drop(b"apop_score", ll_addr)
+    est_g, p_gpu, rep_g = host.estimate(abi.PROBIT, host.data_from_numpy(raw), **settings)
+    assert rep_c.status == 0 and rep_g["status"] == 0
+    assert abs(rep_c.iterations - rep_g["iterations"]) <= 2
+    assert np.max(np.abs(p_gpu - p_cpu) / np.abs(p_cpu)) < 1e-8
