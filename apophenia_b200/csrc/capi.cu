@@ -197,6 +197,7 @@ extern "C" int apop_b200_comm_init(int nranks, int rank, const void* id128) {
     if (!nccl_ok(R.nccl.CommInitRank(&R.comm, nranks, id, rank), "ncclCommInitRank")) return 1;
     R.nranks = nranks;
     R.rank = rank;
+    R.comm_epoch++;
     return 0;
 }
 extern "C" int apop_b200_comm_finalize(void) {
@@ -215,6 +216,7 @@ extern "C" int apop_b200_comm_finalize(void) {
     if (R.p2p_local) { cudaFree(R.p2p_local); R.p2p_local = nullptr; }
     R.nranks = 1;
     R.rank = 0;
+    R.comm_epoch++;
     return 0;
 }
 extern "C" int apop_b200_comm_size(void) { return rt().nranks; }
@@ -342,6 +344,7 @@ static bool upload(Resident* r, const apop_data* d) {
         if (!cuda_ok(cudaMalloc(&r->tiles, need * sizeof(double)), "cudaMalloc(resident tiles)")) return false;
     r->n_rows = n; r->k = k; r->has_y = hy; r->has_w = hw; r->cols = cols; r->n_tiles = n_tiles;
     r->memo_valid = false; r->have_lgamma_y = false; r->have_poisson = false; r->have_gamma = false; r->dirty = false;
+    r->n_global_epoch = ~0ull;
     if (!need) return true;
 
     // Staged, pipelined upload.  Chunks of rows are gathered from the caller's (pageable,
@@ -469,6 +472,10 @@ static Resident* acquire(apop_data* d) {
     if (it != R.reg.end()) {
         Resident* r = it->second;
         if (r->dirty && !upload(r, d)) return nullptr;
+        if (r->consts_epoch != R.comm_epoch) {   // cached sums are sums over the ranks of one communicator
+            r->memo_valid = false; r->have_lgamma_y = false; r->have_poisson = false; r->have_gamma = false;
+            r->consts_epoch = R.comm_epoch;
+        }
         return r;
     }
     Resident* r = new Resident();
@@ -645,14 +652,16 @@ static bool eval_cells(Resident* r, int mode, double p0, double* out5, bool matr
 
 // global (all ranks) cell counts of a resident data set
 static bool global_counts(Resident* r, double& n_rows, double& m_cells, double& v_cells) {
-    n_rows = (double)r->n_rows;
-    m_cells = (double)r->n_rows * r->k;
-    v_cells = r->has_y ? (double)r->n_rows : 0.0;
-    if (rt().nranks > 1) {
-        if (!allreduce_scalar(&n_rows)) return false;
-        m_cells = n_rows * r->k;
-        v_cells = r->has_y ? n_rows : 0.0;
+    Runtime& R = rt();
+    if (r->n_global_epoch != R.comm_epoch) {   // one exchange per (data set, communicator), then cached
+        double n = (double)r->n_rows;
+        if (R.nranks > 1 && !allreduce_scalar(&n)) return false;
+        r->n_global = n;
+        r->n_global_epoch = R.comm_epoch;
     }
+    n_rows = r->n_global;
+    m_cells = n_rows * r->k;
+    v_cells = r->has_y ? n_rows : 0.0;
     return true;
 }
 

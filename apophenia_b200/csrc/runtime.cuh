@@ -22,6 +22,10 @@ struct Resident {
     double* tiles = nullptr;
     bool synthetic = false;
     bool dirty = false;      // host copy changed: re-upload before next use
+    // rows of the whole (all ranks) data set, exchanged once per communicator
+    double n_global = 0.0;
+    unsigned long long n_global_epoch = ~0ull;
+    unsigned long long consts_epoch = 0;   // communicator the cached sums below belong to
     bool transient = false;  // uploaded for one call only
     // beta-independent constants, computed on first use
     bool have_lgamma_y = false;
@@ -79,6 +83,7 @@ struct Runtime {
     NcclApi nccl;
     void* comm = nullptr;
     int nranks = 1, rank = 0;
+    unsigned long long comm_epoch = 0;   // bumped whenever the set of ranks changes
     // fused allreduce over NVLink peer memory (CUDA IPC), see common.cuh grid_finalize
     bool p2p_active = false;
     int p2p_slot = 0;
