@@ -1,0 +1,209 @@
+// capi_batched.cu -- the k x k passes (information, normal equations) and the batched-beta path
+// with its resident resample counts.
+#include "capi_internal.cuh"
+
+using namespace apb;
+
+// H = X' diag(w) [X | y] in one pass; out has K*(K+1) doubles, H[j][c] at j*(K+1)+c
+bool eval_xtwx(Resident* r, int mode, const double* beta, const double* aux, std::vector<double>& out) {
+    Runtime& R = rt();
+    const int K = r->k;
+    if (K < 1 || K > MAX_K_REG) return set_error("k = %d columns: the fused kernels cover 1..%d", K, MAX_K_REG);
+    if (!r->has_y) return set_error("the data set has no outcome vector (run the model's prep first)");
+    static int bps_cache[XTWX_MODE_COUNT][MAX_K_REG + 1];
+    int& bps = bps_cache[mode][K];
+    if (!bps) bps = xtwx_blocks_per_sm(mode, K);
+    if (bps <= 0) return set_error("X'WX kernel unavailable for k=%d", K);
+    const int KB = xtwx_kb(K), NC = KB + 1, NOUT = KB * NC;
+    XtwxLaunch L;
+    L.tiles = r->tiles; L.n_rows = r->n_rows; L.n_tiles = r->n_tiles; L.k = K; L.cols = r->cols;
+    L.has_w = (r->has_w && mode == XTWX_GRAM) ? 1 : 0;
+    L.grid = grid_for(bps, r->n_tiles, XTWX_THREADS / 32);
+    if (!ensure_partials((size_t)L.grid * NOUT)) return false;
+    L.partials = R.d_partials; L.ticket = R.d_ticket; L.out = R.d_out; L.stream = R.stream;
+    L.fin = make_fin(NOUT);
+    XtwxParams prm;
+    memset(&prm, 0, sizeof prm);
+    if (beta) memcpy(prm.beta, beta, K * sizeof(double));
+    if (aux) memcpy(prm.aux, aux, 4 * sizeof(double));
+    time_begin();
+    if (!cuda_ok(xtwx_launch(mode, L, prm), "X'WX kernel launch")) return false;
+    time_end_record();
+    R.launches++;
+    if (!reduce_and_fetch(NOUT, L.fin)) return false;
+    time_collect();
+    out.assign((size_t)K * (K + 1), 0.0);
+    for (int j = 0; j < K; j++) {
+        for (int c = 0; c < K; c++) out[(size_t)j * (K + 1) + c] = R.h_out[j * NC + c];
+        out[(size_t)j * (K + 1) + K] = R.h_out[j * NC + KB];
+    }
+    return true;
+}
+
+extern "C" int apop_b200_ols_gram(apop_data* d, double* xtx, double* xty) {
+    LOCK;
+    if (!d || !xtx || !xty) { set_error("apop_b200_ols_gram: NULL argument"); return 1; }
+    Resident* r = acquire(d);
+    if (!r) return 1;
+    std::vector<double> out;
+    const bool ok = eval_xtwx(r, XTWX_GRAM, nullptr, nullptr, out);
+    if (ok) {
+        const int K = r->k;
+        for (int j = 0; j < K; j++) {
+            for (int c = 0; c < K; c++) xtx[j * K + c] = out[(size_t)j * (K + 1) + c];
+            xty[j] = out[(size_t)j * (K + 1) + K];
+        }
+    }
+    release(r);
+    return ok ? 0 : 1;
+}
+
+extern "C" int apop_b200_information(apop_b200_family family, apop_data* d, const double* beta, size_t P, double* H) {
+    LOCK;
+    if (!d || !beta || !H) { set_error("apop_b200_information: NULL argument"); return 1; }
+    Resident* r = acquire(d);
+    if (!r) return 1;
+    bool ok = false;
+    std::vector<double> out;
+    double scale = 1.0;
+    if ((size_t)r->k != P) set_error("apop_b200_information: P = %zu but the data has %d columns (binary-outcome families only)", P, r->k);
+    else if (family == APOP_B200_PROBIT) ok = eval_xtwx(r, XTWX_PROBIT, beta, nullptr, out);
+    else if (family == APOP_B200_LOGIT) ok = eval_xtwx(r, XTWX_LOGIT2, beta, nullptr, out);
+    else if (family == APOP_B200_POISSON_REG) ok = eval_xtwx(r, XTWX_POISSON_REG, beta, nullptr, out);
+    else if (family == APOP_B200_OLS) {
+        // -d2LL/dbeta2 at fixed sigma: X'WX / sigma^2, sigma^2 = sample variance of the errors
+        std::vector<double> mom;
+        double n, mc, vc;
+        if (eval_glm(r, GLM_OLS, beta, P, nullptr, mom) && global_counts(r, n, mc, vc) && eval_xtwx(r, XTWX_GRAM, nullptr, nullptr, out)) {
+            const long double var = ((long double)mom[1] - (long double)mom[0] * mom[0] / n) / (n - 1);
+            scale = (double)(1.0L / var);
+            ok = true;
+        }
+    } else set_error("apop_b200_information: family %d has no k x k information here", (int)family);
+    if (ok)
+        for (size_t j = 0; j < P; j++)
+            for (size_t c = 0; c < P; c++) H[j * P + c] = out[j * (P + 1) + c] * scale;
+    release(r);
+    return ok ? 0 : 1;
+}
+// m parameter vectors in one pass on the DMMA path.  ll[m]; score[P*m] replicate-major.
+extern "C" int apop_b200_ll_score_batched(apop_b200_family family, apop_data* d, const double* B, size_t P, size_t m,
+                                          int use_counts, double* ll, double* score) {
+    LOCK;
+    if (!d || !B || !ll || !m) { set_error("apop_b200_ll_score_batched: NULL argument"); return 1; }
+    GlmFam fam;
+    if (family == APOP_B200_PROBIT) fam = GLM_PROBIT;
+    else if (family == APOP_B200_LOGIT) fam = GLM_LOGIT2;
+    else if (family == APOP_B200_POISSON_REG) fam = GLM_POISSON_REG;
+    else { set_error("batched path: family %d is not a binary-outcome / GLM family", (int)family); return 1; }
+    Resident* r = acquire(d);
+    if (!r) return 1;
+    Runtime& R = rt();
+    bool ok = false;
+    double *dB = nullptr, *dOut = nullptr;
+    do {
+        const int K = r->k;
+        if ((size_t)K != P) { set_error("batched path: P = %zu but the data has %d columns", P, K); break; }
+        if (K < 1 || K > MAX_K_REG || !r->has_y || r->has_w) { set_error("batched path: needs 1..%d columns, an outcome vector and no weights", MAX_K_REG); break; }
+        if (use_counts && (!r->counts || r->counts_m < m)) { set_error("batched path: no resident resample counts for %zu replicates (call apop_b200_bootstrap_counts)", m); break; }
+        if (use_counts && fam == GLM_POISSON_REG) { set_error("batched path: resample counts are not supported for the Poisson regression constant"); break; }
+        const int KB = batched_kb(K), NOUT = 1 + KB;
+        static int mb_env = -1;
+        if (mb_env < 0) { const char* e = getenv("APOP_B200_BATCH_MB"); mb_env = (e && e[0] == '2') ? 2 : 1; }
+        const int mb = mb_env, ctas_per_sm = (mb == 1) ? 2 : 1;   // matches the kernels' launch bounds
+        const int reps_per_cta = (BATCH_THREADS / 32) * mb * 8;
+        const int n_repgroups = (int)((m + reps_per_cta - 1) / reps_per_cta);
+        long long n_rowgroups = (long long)R.num_sms * ctas_per_sm / n_repgroups;
+        if (n_rowgroups < 1) n_rowgroups = 1;
+        if ((unsigned long long)n_rowgroups > r->n_tiles) n_rowgroups = r->n_tiles ? (long long)r->n_tiles : 1;
+        BatchedLaunch L;
+        L.tiles = r->tiles; L.n_rows = r->n_rows; L.n_tiles = r->n_tiles; L.k = K; L.cols = r->cols;
+        L.P = (int)P; L.m = (int)m; L.counts = use_counts ? r->counts : nullptr; L.m_pad = (int)r->counts_m;
+        // binary logit: the two category values (defaults 0, 1)
+        L.aux[0] = 0.0; L.aux[1] = 1.0; L.aux[2] = L.aux[3] = 0.0;
+        const apop_data* pg = category_page(d);
+        if (fam == GLM_LOGIT2 && pg && pg->vector && pg->vector->size >= 2) { L.aux[0] = pg->vector->data[0]; L.aux[1] = pg->vector->data[pg->vector->stride]; }
+        L.n_rowgroups = (int)n_rowgroups; L.grid = (int)(n_rowgroups * n_repgroups);
+        L.want_score = score != nullptr; L.stream = R.stream; L.mb = mb;
+        if (!ensure_partials((size_t)n_rowgroups * m * NOUT)) break;
+        L.partials = R.d_partials;
+        if (!cuda_ok(cudaMalloc(&dB, P * m * sizeof(double)), "cudaMalloc(B)")) break;
+        if (!cuda_ok(cudaMalloc(&dOut, m * NOUT * sizeof(double)), "cudaMalloc(out)")) break;
+        if (!cuda_ok(cudaMemcpyAsync(dB, B, P * m * sizeof(double), cudaMemcpyHostToDevice, R.stream), "H2D B")) break;
+        L.B = dB; L.out = dOut;
+        time_begin();
+        if (!cuda_ok(batched_launch((int)fam, L), "batched kernel launch")) break;
+        time_end_record();
+        R.launches += 2;
+        if (R.comm && R.nranks > 1 &&
+            !nccl_ok(R.nccl.AllReduce(dOut, dOut, m * NOUT, 8, 0, R.comm, R.stream), "ncclAllReduce")) break;
+        std::vector<double> h(m * NOUT);
+        if (!cuda_ok(cudaMemcpyAsync(h.data(), dOut, m * NOUT * sizeof(double), cudaMemcpyDeviceToHost, R.stream), "D2H")) break;
+        if (!cuda_ok(cudaStreamSynchronize(R.stream), "stream sync")) break;
+        time_collect();
+        double lg = 0.0;
+        if (fam == GLM_POISSON_REG && !lgamma_const(r, lg)) break;
+        for (size_t q = 0; q < m; q++) {
+            ll[q] = h[q * NOUT] - lg;
+            if (score) memcpy(score + q * P, h.data() + q * NOUT + 1, P * sizeof(double));
+        }
+        ok = true;
+    } while (0);
+    if (dB) cudaFree(dB);
+    if (dOut) cudaFree(dOut);
+    release(r);
+    return ok ? 0 : 1;
+}
+
+// resident resample counts back to the host as an n_rows x m row-major uint8 matrix (tests)
+extern "C" int apop_b200_counts_download(const apop_data* d, size_t m, unsigned char* out) {
+    LOCK;
+    Runtime& R = rt();
+    auto it = R.reg.find(d);
+    if (it == R.reg.end() || !it->second->counts || it->second->counts_m < m) { set_error("no resident counts"); return 1; }
+    Resident* r = it->second;
+    cudaSetDevice(R.device);
+    const size_t m_pad = r->counts_m, bytes = r->n_tiles * m_pad * TILE_ROWS;
+    std::vector<unsigned char> h(bytes);
+    if (!cuda_ok(cudaMemcpy(h.data(), r->counts, bytes, cudaMemcpyDeviceToHost), "D2H counts")) return 1;
+    for (size_t i = 0; i < r->n_rows; i++) {
+        const int rr = (int)(i & 31);
+        const int pos = ((rr & 7) >> 1) * 8 + (rr >> 3) * 2 + (rr & 1);
+        for (size_t q = 0; q < m; q++) out[i * m + q] = h[((i >> 5) * m_pad + q) * TILE_ROWS + pos];
+    }
+    return 0;
+}
+
+// m exact multinomial resamples of the (global) rows, kept resident next to the data
+extern "C" int apop_b200_bootstrap_counts(apop_data* d, size_t m, uint64_t seed) {
+    LOCK;
+    if (!d || !m) { set_error("apop_b200_bootstrap_counts: NULL argument"); return 1; }
+    if (!require_ready()) return 1;
+    Runtime& R = rt();
+    auto it = R.reg.find(d);
+    if (it == R.reg.end()) { set_error("apop_b200_bootstrap_counts: pin the data set first"); return 1; }
+    Resident* r = it->second;
+    cudaSetDevice(R.device);
+    if (r->counts) { cudaFree(r->counts); r->counts = nullptr; r->counts_m = 0; }
+    const size_t m_pad = (m + 3) / 4 * 4;
+    const size_t bytes = r->n_tiles * m_pad * TILE_ROWS;
+    if (!bytes) return 0;
+    if (!cuda_ok(cudaMalloc(&r->counts, bytes), "cudaMalloc(counts)")) return 1;
+    cudaMemsetAsync(r->counts, 0, bytes, R.stream);
+    // the resample is of the global data set: ranks share seed, each keeps its own rows
+    double n_global = (double)r->n_rows, offset = 0.0;
+    if (R.nranks > 1) {
+        // exclusive prefix of the shard sizes = this rank's first global row
+        std::vector<double> sizes(R.nranks, 0.0);
+        sizes[R.rank] = (double)r->n_rows;
+        if (!allreduce_host(sizes.data(), R.nranks)) return 1;
+        n_global = 0;
+        for (int q = 0; q < R.nranks; q++) { if (q < R.rank) offset += sizes[q]; n_global += sizes[q]; }
+    }
+    if (!cuda_ok(bootstrap_counts_launch(r->counts, r->n_rows, (size_t)offset, (size_t)n_global, (int)m, (int)m_pad, seed, R.stream), "bootstrap counts") ||
+        !cuda_ok(cudaStreamSynchronize(R.stream), "counts sync")) return 1;
+    r->counts_m = m_pad;
+    R.launches++;
+    return 0;
+}
+

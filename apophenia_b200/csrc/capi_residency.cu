@@ -1,0 +1,253 @@
+// capi_residency.cu -- keeping X, y, w in HBM between optimizer iterations: the pipelined
+// upload + re-tiling (apop_b200_pin), the registry keyed by the apop_data address, synthetic
+// device-generated data sets and their download.
+#include "capi_internal.cuh"
+
+using namespace apb;
+
+// --------------------------------------------------------------------------
+//  residency
+// --------------------------------------------------------------------------
+static void data_shape(const apop_data* d, size_t& n, int& k, bool& has_y, bool& has_w) {
+    n = d->matrix ? d->matrix->size1 : (d->vector ? d->vector->size : 0);
+    k = d->matrix ? (int)d->matrix->size2 : 0;
+    has_y = d->vector != nullptr;
+    has_w = d->weights != nullptr;
+}
+
+bool upload(Resident* r, const apop_data* d) {
+    Runtime& R = rt();
+    size_t n;
+    int k;
+    bool hy, hw;
+    data_shape(d, n, k, hy, hw);
+    if (d->matrix && d->vector && d->vector->size != d->matrix->size1)
+        return set_error("vector has %zu entries but the matrix has %zu rows", d->vector->size, d->matrix->size1);
+    if (d->weights && d->weights->size != n) return set_error("weights have %zu entries for %zu rows", d->weights->size, n);
+    if ((d->matrix && n && !d->matrix->data) || (d->vector && n && !d->vector->data))
+        return set_error("data set has no host buffers (device-only synthetic data cannot be re-uploaded)");
+    const int cols = k + (hy ? 1 : 0) + (hw ? 1 : 0);
+    const size_t n_tiles = (n + TILE_ROWS - 1) / TILE_ROWS;
+    const size_t need = n_tiles * (size_t)cols * TILE_ROWS;
+    if (r->tiles && (r->n_tiles * (size_t)r->cols != n_tiles * (size_t)cols)) {
+        cudaFree(r->tiles);
+        r->tiles = nullptr;
+    }
+    if (!r->tiles && need)
+        if (!cuda_ok(cudaMalloc(&r->tiles, need * sizeof(double)), "cudaMalloc(resident tiles)")) return false;
+    r->n_rows = n; r->k = k; r->has_y = hy; r->has_w = hw; r->cols = cols; r->n_tiles = n_tiles;
+    r->memo_valid = false; r->have_lgamma_y = false; r->have_poisson = false; r->have_gamma = false; r->dirty = false;
+    r->n_global_epoch = ~0ull;
+    if (!need) return true;
+
+    // Staged, pipelined upload.  Chunks of rows are gathered from the caller's (pageable,
+    // possibly strided) buffers into one of two pinned staging buffers by a few host threads,
+    // sent with one asynchronous copy each, and re-tiled on the device; the gather of chunk
+    // i+1 overlaps the copy and the transpose of chunk i.
+    size_t chunk = ((size_t)8 << 20) / (size_t)(cols ? cols : 1);   // ~64 MB of doubles per chunk
+    chunk = chunk / TILE_ROWS * TILE_ROWS;
+    if (chunk < TILE_ROWS) chunk = TILE_ROWS;
+    if (chunk > n_tiles * TILE_ROWS) chunk = n_tiles * TILE_ROWS;
+    const size_t chunk_doubles = chunk * (size_t)cols;
+    if (R.pin_cap < chunk_doubles) {
+        for (int b2 = 0; b2 < 2; b2++) {
+            if (R.pin_host[b2]) cudaFreeHost(R.pin_host[b2]);
+            if (R.pin_dev[b2]) cudaFree(R.pin_dev[b2]);
+            R.pin_host[b2] = nullptr; R.pin_dev[b2] = nullptr;
+        }
+        R.pin_cap = 0;
+        bool okb = true;
+        for (int b2 = 0; b2 < 2 && okb; b2++)
+            okb = cuda_ok(cudaHostAlloc(&R.pin_host[b2], chunk_doubles * sizeof(double), cudaHostAllocDefault), "cudaHostAlloc(staging)") &&
+                  cuda_ok(cudaMalloc(&R.pin_dev[b2], chunk_doubles * sizeof(double)), "cudaMalloc(staging)");
+        if (!okb) return false;
+        if (!R.pin_ev[0]) { cudaEventCreateWithFlags(&R.pin_ev[0], cudaEventDisableTiming); cudaEventCreateWithFlags(&R.pin_ev[1], cudaEventDisableTiming); }
+        R.pin_cap = chunk_doubles;
+    }
+    static int n_threads = 0;
+    if (!n_threads) {
+        const char* e = getenv("APOP_B200_PIN_THREADS");
+        n_threads = e ? atoi(e) : 16;
+        const int hw = (int)std::thread::hardware_concurrency();
+        if (hw > 0 && n_threads > hw) n_threads = hw;
+        if (n_threads < 1) n_threads = 1;
+    }
+    bool ok = true;
+    int ci = 0;
+    for (size_t r0 = 0; ok && r0 < n; r0 += chunk, ci++) {
+        const size_t rows = (n - r0 < chunk) ? n - r0 : chunk;
+        const int buf = ci & 1;
+        if (ci >= 2) ok = cuda_ok(cudaEventSynchronize(R.pin_ev[buf]), "pin staging wait");   // chunk ci-2 has left this buffer
+        double* hX = R.pin_host[buf];
+        double* hy_ = hX + rows * (size_t)k;
+        double* hw_ = hy_ + (hy ? rows : 0);
+        auto gather = [&](size_t a0, size_t a1) {   // rows [a0, a1) of this chunk
+            if (k) {
+                if (d->matrix->tda == (size_t)k) memcpy(hX + a0 * k, d->matrix->data + (r0 + a0) * k, (a1 - a0) * k * sizeof(double));
+                else for (size_t i = a0; i < a1; i++) memcpy(hX + i * k, d->matrix->data + (r0 + i) * d->matrix->tda, k * sizeof(double));
+            }
+            if (hy) {
+                if (d->vector->stride == 1) memcpy(hy_ + a0, d->vector->data + r0 + a0, (a1 - a0) * sizeof(double));
+                else for (size_t i = a0; i < a1; i++) hy_[i] = d->vector->data[(r0 + i) * d->vector->stride];
+            }
+            if (hw) {
+                if (d->weights->stride == 1) memcpy(hw_ + a0, d->weights->data + r0 + a0, (a1 - a0) * sizeof(double));
+                else for (size_t i = a0; i < a1; i++) hw_[i] = d->weights->data[(r0 + i) * d->weights->stride];
+            }
+        };
+        const int nt = (rows * (size_t)cols < ((size_t)1 << 17)) ? 1 : n_threads;   // small chunks: not worth a thread
+        if (nt == 1) gather(0, rows);
+        else {
+            std::vector<std::thread> pool;
+            for (int t = 0; t < nt; t++) pool.emplace_back(gather, rows * t / nt, rows * (t + 1) / nt);
+            for (auto& th : pool) th.join();
+        }
+        double* dX = R.pin_dev[buf];
+        double* dy = dX + rows * (size_t)k;
+        double* dw = dy + (hy ? rows : 0);
+        ok = ok && cuda_ok(cudaMemcpyAsync(dX, hX, rows * (size_t)cols * sizeof(double), cudaMemcpyHostToDevice, R.stream), "H2D chunk");
+        ok = ok && cuda_ok(tile_pack(k ? dX : nullptr, hy ? dy : nullptr, hw ? dw : nullptr, rows, k, cols,
+                                     r->tiles + (r0 / TILE_ROWS) * (size_t)cols * TILE_ROWS, R.stream), "tile_pack");
+        ok = ok && cuda_ok(cudaEventRecord(R.pin_ev[buf], R.stream), "event");
+    }
+    ok = ok && cuda_ok(cudaStreamSynchronize(R.stream), "pin sync");
+    return ok;
+}
+
+extern "C" int apop_b200_pin(apop_data* d) {
+    LOCK;
+    if (!d) { set_error("apop_b200_pin: NULL data"); return 1; }
+    if (!require_ready()) return 1;
+    Runtime& R = rt();
+    cudaSetDevice(R.device);
+    auto it = R.reg.find(d);
+    Resident* r = (it != R.reg.end()) ? it->second : new Resident();
+    if (r->synthetic) return 0;
+    if (!upload(r, d)) {
+        if (it == R.reg.end()) free_resident(r);
+        else { free_resident(r); R.reg.erase(it); }
+        d->error = 'a';
+        return 1;
+    }
+    R.reg[d] = r;
+    return 0;
+}
+extern "C" int apop_b200_unpin(apop_data* d) {
+    LOCK;
+    Runtime& R = rt();
+    auto it = R.reg.find(d);
+    if (it == R.reg.end()) return 1;
+    cudaSetDevice(R.device);
+    free_resident(it->second);
+    R.reg.erase(it);
+    return 0;
+}
+extern "C" int apop_b200_invalidate(apop_data* d) {
+    LOCK;
+    auto it = rt().reg.find(d);
+    if (it == rt().reg.end()) return 1;
+    if (it->second->synthetic) return 1;
+    it->second->dirty = true;
+    it->second->memo_valid = false;
+    return 0;
+}
+extern "C" int apop_b200_is_pinned(const apop_data* d) {
+    LOCK;
+    return rt().reg.count(d) ? 1 : 0;
+}
+
+// find the resident copy of d; upload it for this call if it is not pinned
+Resident* acquire(apop_data* d) {
+    if (!require_ready()) return nullptr;
+    Runtime& R = rt();
+    cudaSetDevice(R.device);
+    auto it = R.reg.find(d);
+    if (it != R.reg.end()) {
+        Resident* r = it->second;
+        if (r->dirty && !upload(r, d)) return nullptr;
+        if (r->consts_epoch != R.comm_epoch) {   // cached sums are sums over the ranks of one communicator
+            r->memo_valid = false; r->have_lgamma_y = false; r->have_poisson = false; r->have_gamma = false;
+            r->consts_epoch = R.comm_epoch;
+        }
+        return r;
+    }
+    Resident* r = new Resident();
+    if (!upload(r, d)) { free_resident(r); return nullptr; }
+    if (R.auto_pin) R.reg[d] = r;
+    else r->transient = true;
+    return r;
+}
+void release(Resident* r) {
+    if (r && r->transient) free_resident(r);
+}
+
+extern "C" apop_data* apop_b200_synth(apop_b200_family family, size_t n_rows, size_t k, int ncat,
+                                      const double* beta_true, uint64_t seed, uint64_t row_offset) {
+    LOCK;
+    if (!require_ready()) return nullptr;
+    Runtime& R = rt();
+    cudaSetDevice(R.device);
+    const bool iid = (family == APOP_B200_POISSON || family == APOP_B200_NORMAL);
+    if (family == APOP_B200_LOGIT && ncat < 2) ncat = 2;
+    const int C1 = (family == APOP_B200_LOGIT) ? ncat - 1 : 1;
+    const size_t P = iid ? (family == APOP_B200_NORMAL ? 2 : 1) : k * C1;
+    if (P > SYNTH_MAX_P || C1 > SYNTH_MAX_C1 || k == 0) { set_error("apop_b200_synth: shape out of range"); return nullptr; }
+    SynthParams prm;
+    memset(&prm, 0, sizeof prm);
+    memcpy(prm.beta, beta_true, P * sizeof(double));
+    Resident* r = new Resident();
+    r->n_rows = n_rows; r->k = (int)k; r->has_y = !iid; r->has_w = false;
+    r->cols = (int)k + (iid ? 0 : 1);
+    r->n_tiles = (n_rows + TILE_ROWS - 1) / TILE_ROWS;
+    r->synthetic = true;
+    const size_t need = r->n_tiles * (size_t)r->cols * TILE_ROWS;
+    if (need && !cuda_ok(cudaMalloc(&r->tiles, need * sizeof(double)), "cudaMalloc(synthetic tiles)")) { delete r; return nullptr; }
+    if (!cuda_ok(synth_fill((int)family, n_rows, (int)k, r->cols, ncat, prm, seed, row_offset, r->tiles, R.stream), "synth") ||
+        !cuda_ok(cudaStreamSynchronize(R.stream), "synth sync")) { free_resident(r); return nullptr; }
+    apop_data* d = (apop_data*)calloc(1, sizeof(apop_data));
+    d->matrix = (gsl_matrix*)calloc(1, sizeof(gsl_matrix));
+    d->matrix->size1 = n_rows; d->matrix->size2 = k; d->matrix->tda = k;
+    if (!iid) {
+        d->vector = (gsl_vector*)calloc(1, sizeof(gsl_vector));
+        d->vector->size = n_rows; d->vector->stride = 1;
+    }
+    R.reg[d] = r;
+    return d;
+}
+extern "C" void apop_b200_synth_free(apop_data* d) {
+    if (!d) return;
+    apop_b200_unpin(d);
+    free(d->matrix);
+    free(d->vector);
+    free(d);
+}
+extern "C" int apop_b200_download(const apop_data* d, double* X, double* y, double* w) {
+    LOCK;
+    Runtime& R = rt();
+    auto it = R.reg.find(d);
+    if (it == R.reg.end()) { set_error("apop_b200_download: data set is not resident"); return 1; }
+    Resident* r = it->second;
+    cudaSetDevice(R.device);
+    if (!r->n_rows) return 0;
+    size_t chunk = ((size_t)32 << 20) / (size_t)(r->cols ? r->cols : 1) / TILE_ROWS * TILE_ROWS;
+    if (chunk < TILE_ROWS) chunk = TILE_ROWS;
+    double *Xs = nullptr, *ys = nullptr, *ws = nullptr;
+    bool ok = true;
+    if (r->k && X) ok = ok && cuda_ok(cudaMalloc(&Xs, chunk * r->k * sizeof(double)), "cudaMalloc(staging)");
+    if (r->has_y && y) ok = ok && cuda_ok(cudaMalloc(&ys, chunk * sizeof(double)), "cudaMalloc(staging)");
+    if (r->has_w && w) ok = ok && cuda_ok(cudaMalloc(&ws, chunk * sizeof(double)), "cudaMalloc(staging)");
+    for (size_t r0 = 0; ok && r0 < r->n_rows; r0 += chunk) {
+        const size_t rows = (r->n_rows - r0 < chunk) ? r->n_rows - r0 : chunk;
+        ok = ok && cuda_ok(tile_unpack(r->tiles + (r0 / TILE_ROWS) * (size_t)r->cols * TILE_ROWS, rows, r->k, r->cols,
+                                       r->has_y, r->has_w, Xs, ys, ws, R.stream), "tile_unpack");
+        if (Xs) ok = ok && cuda_ok(cudaMemcpyAsync(X + r0 * r->k, Xs, rows * r->k * sizeof(double), cudaMemcpyDeviceToHost, R.stream), "D2H X");
+        if (ys) ok = ok && cuda_ok(cudaMemcpyAsync(y + r0, ys, rows * sizeof(double), cudaMemcpyDeviceToHost, R.stream), "D2H y");
+        if (ws) ok = ok && cuda_ok(cudaMemcpyAsync(w + r0, ws, rows * sizeof(double), cudaMemcpyDeviceToHost, R.stream), "D2H w");
+        ok = ok && cuda_ok(cudaStreamSynchronize(R.stream), "download sync");
+    }
+    if (Xs) cudaFree(Xs);
+    if (ys) cudaFree(ys);
+    if (ws) cudaFree(ws);
+    return ok ? 0 : 1;
+}
+

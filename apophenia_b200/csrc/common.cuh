@@ -100,14 +100,41 @@ __device__ __forceinline__ void grid_finalize(const double* __restrict__ partial
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    for (int v = threadIdx.x; v < nout; v += blockDim.x) {
-        double s = 0.0, c = 0.0;
-        for (unsigned b = 0; b < gridDim.x; b++) {
-            double e;
-            two_sum(s, __ldcg(partials + (size_t)b * nout + v), s, e);
-            c += e;
+    // partials are summed in a fixed order: G = blockDim/nout thread groups take the blocks
+    // b = g, g+G, ... (two-sum compensated), then the G subtotals are added in group order
+    __shared__ double fin_group[256];
+    const int G = (nout <= 64) ? (int)blockDim.x / nout : 1;
+    if (G > 1 && G * nout <= 256) {
+        if ((int)threadIdx.x < G * nout) {
+            const int v = threadIdx.x % nout, gi = threadIdx.x / nout;
+            double s = 0.0, c = 0.0;
+            for (unsigned b = gi; b < gridDim.x; b += G) {
+                double e;
+                two_sum(s, __ldcg(partials + (size_t)b * nout + v), s, e);
+                c += e;
+            }
+            fin_group[gi * nout + v] = s + c;
         }
-        scratch[v] = s + c;
+        __syncthreads();
+        if ((int)threadIdx.x < nout) {
+            double s = 0.0, c = 0.0;
+            for (int gi = 0; gi < G; gi++) {
+                double e;
+                two_sum(s, fin_group[gi * nout + threadIdx.x], s, e);
+                c += e;
+            }
+            scratch[threadIdx.x] = s + c;
+        }
+    } else {
+        for (int v = threadIdx.x; v < nout; v += blockDim.x) {
+            double s = 0.0, c = 0.0;
+            for (unsigned b = 0; b < gridDim.x; b++) {
+                double e;
+                two_sum(s, __ldcg(partials + (size_t)b * nout + v), s, e);
+                c += e;
+            }
+            scratch[v] = s + c;
+        }
     }
     __syncthreads();
     if (ctx.nranks > 1) {

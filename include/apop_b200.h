@@ -13,7 +13,7 @@
  * -DAPOP_B200_USE_SYSTEM_HEADERS and the structs come from there.  Otherwise
  * the layouts are re-declared here bit-for-bit (public, ABI-stable layouts;
  * apop.m4.h:61-115 and GSL's gsl_block/gsl_vector/gsl_matrix) and checked by
- * static asserts in capi.cu.
+ * static asserts in capi_runtime.cu.
  */
 #ifndef APOP_B200_H
 #define APOP_B200_H
