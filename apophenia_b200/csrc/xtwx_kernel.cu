@@ -102,7 +102,7 @@ xtwx_kernel(const double* __restrict__ tiles, const unsigned long long n_rows, c
 // ---------------------------------------------------------------------------------------
 // Tensor-pipe variant (default): H = (W X)' [X | y] as FP64 DMMA (mma.sync m8n8k4) with the
 // rows of the tile as the contraction dimension.  Each warp stages its tile in shared memory
-// with cp.async (padded columns), computes the row weights with lane = row (x.beta against the
+// (16-byte cp.async into padded columns; a TMA bulk-copy + mbarrier pipeline is selectable), computes the row weights with lane = row (x.beta against the
 // constant bank, then the family's weight), and keeps the X fragments of the tile in registers:
 // fragment (jb, ks) = X[rows ks*4 + q][columns jb*8 + g] serves both as the A operand (scaled by
 // the row weight) of column block jb and as the B operand of column block jb.  Only the upper
@@ -116,7 +116,7 @@ __device__ __forceinline__ void dmma_8x8x4(double& d0, double& d1, double a, dou
 }
 constexpr int XTWX_CS = 36;   // padded column stride of a staged tile (doubles)
 
-template <int KB, int MODE>
+template <int KB, int MODE, bool USE_TMA>
 __global__ void __launch_bounds__(XTWX_THREADS, 3)
 xtwx_dmma_kernel(const double* __restrict__ tiles, const unsigned long long n_rows, const unsigned long long n_tiles,
                  const int K, const int cols, const int has_w, const __grid_constant__ XtwxParams prm,
@@ -132,11 +132,29 @@ xtwx_dmma_kernel(const double* __restrict__ tiles, const unsigned long long n_ro
     extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, q = lane & 3;
-    double* tile = smem + warp * (TILE_D + 32);
-    double* wbuf = tile + TILE_D;
     const unsigned long long gwarp = (unsigned long long)blockIdx.x * WARPS + warp;
     const unsigned long long nwarps = (unsigned long long)gridDim.x * WARPS;
-    const int pf_dst = (lane >> 4) * XTWX_CS + (lane & 15) * 2, pf_src = lane * 2;
+    constexpr int NBUF = USE_TMA ? 2 : 1;   // TMA: the next tile streams in while this one is consumed
+    double* slab = smem + warp * (NBUF * TILE_D + 36);
+    double* wbuf = slab + NBUF * TILE_D;
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(wbuf + 32);
+    if (USE_TMA) {
+        if (lane == 0) { mbar_init(bars, 1); mbar_init(bars + 1, 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    unsigned phase[2] = {0u, 0u};
+    int cur = 0;
+    auto tma_issue = [&](unsigned long long tt, int buf) {   // one bulk copy per (padded) column
+        if (lane == 0) {
+            fence_proxy_async();   // earlier generic reads of this buffer precede the async writes
+            mbar_expect_tx(bars + buf, (unsigned)(cols * TILE_ROWS * sizeof(double)));
+            const double* src = tiles + tt * (unsigned long long)(cols * TILE_ROWS);
+            double* dst = slab + buf * TILE_D;
+            for (int c = 0; c < cols; c++) tma_load_1d(dst + c * XTWX_CS, src + c * TILE_ROWS, TILE_ROWS * sizeof(double), bars + buf);
+        }
+    };
+    if (USE_TMA && gwarp < n_tiles) tma_issue(gwarp, 0);
 
     double acc[NTRI][2], accy[JB][2];
 #pragma unroll
@@ -145,9 +163,15 @@ xtwx_dmma_kernel(const double* __restrict__ tiles, const unsigned long long n_ro
     for (int b = 0; b < JB; b++) accy[b][0] = accy[b][1] = 0.0;
 
     for (unsigned long long t = gwarp; t < n_tiles; t += nwarps) {
-        {   // stage the tile: chunk c = lane + 32 i lies in column (lane >> 4) + 2 i, 16-byte slot lane & 15
-            const double* src = tiles + t * (unsigned long long)(cols * TILE_ROWS) + pf_src;
-            const unsigned sa = (unsigned)__cvta_generic_to_shared(tile + pf_dst);
+        double* tile = slab + (USE_TMA ? cur : 0) * TILE_D;
+        if (USE_TMA) {
+            if (t + nwarps < n_tiles) tma_issue(t + nwarps, cur ^ 1);
+            mbar_wait(bars + cur, phase[cur]);
+            phase[cur] ^= 1u;
+        } else {
+            // stage the tile with 16-byte cp.async: chunk c = lane + 32 i lies in column (lane >> 4) + 2 i
+            const double* src = tiles + t * (unsigned long long)(cols * TILE_ROWS) + lane * 2;
+            const unsigned sa = smem_u32(tile + (lane >> 4) * XTWX_CS + (lane & 15) * 2);
 #pragma unroll
             for (int i = 0; i < (KB + 3) / 2; i++) {
                 const int col = (lane >> 4) + 2 * i;
@@ -156,8 +180,8 @@ xtwx_dmma_kernel(const double* __restrict__ tiles, const unsigned long long n_ro
             }
             asm volatile("cp.async.commit_group;");
             asm volatile("cp.async.wait_group 0;");
+            __syncwarp();
         }
-        __syncwarp();
         // ---- row weights, lane = row
         {
             double xb = 0.0;
@@ -193,6 +217,7 @@ xtwx_dmma_kernel(const double* __restrict__ tiles, const unsigned long long n_ro
             }
         }
         __syncwarp();   // the tile buffer is about to be overwritten
+        if (USE_TMA) cur ^= 1;
     }
 
     // ---- CTA reduction: expand the block triangle into the full H[j][c] layout
@@ -225,27 +250,48 @@ xtwx_dmma_kernel(const double* __restrict__ tiles, const unsigned long long n_ro
     grid_finalize(partials, NOUT, ticket, out, fin, red);
 }
 
+// Staging choice, measured at 100M x 32 (round 1): 16-byte cp.async, single buffer, 12 warps/SM: 5.99 ms;
+// TMA bulk copies (one lane, one mbarrier per warp) single buffer: 6.38 ms; double-buffered TMA
+// (8 warps/SM): 7.7 ms -- the kernel is bound by the latency of its DMMA chains, so warps beat
+// buffers.  cp.async is the default; APOP_B200_XTWX_TMA=1 selects the TMA pipeline.
+static bool xtwx_use_tma() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("APOP_B200_XTWX_TMA"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v == 1;
+}
 template <int KB>
 static size_t xtwx_dmma_smem() {
-    const size_t ring = (size_t)(XTWX_THREADS / 32) * ((MAX_K_REG + 2) * XTWX_CS + 32) * sizeof(double);
+    const size_t ring = (size_t)(XTWX_THREADS / 32) * ((xtwx_use_tma() ? 2 : 1) * (MAX_K_REG + 2) * XTWX_CS + 36) * sizeof(double);
     const size_t red = (size_t)KB * (KB + 1) * sizeof(double);
     return ring > red ? ring : red;
 }
 template <int KB, int MODE>
 static cudaError_t dmma_launch_one(const XtwxLaunch& L, const XtwxParams& prm) {
     const size_t sm = xtwx_dmma_smem<KB>();
-    static bool done = false;
-    if (!done) { cudaFuncSetAttribute(xtwx_dmma_kernel<KB, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); done = true; }
-    xtwx_dmma_kernel<KB, MODE><<<L.grid, XTWX_THREADS, sm, L.stream>>>(L.tiles, L.n_rows, L.n_tiles, L.k, L.cols, L.has_w, prm,
-                                                                      L.partials, L.ticket, L.out, L.fin);
+    if (xtwx_use_tma()) {
+        static bool done = false;
+        if (!done) { cudaFuncSetAttribute(xtwx_dmma_kernel<KB, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); done = true; }
+        xtwx_dmma_kernel<KB, MODE, true><<<L.grid, XTWX_THREADS, sm, L.stream>>>(L.tiles, L.n_rows, L.n_tiles, L.k, L.cols, L.has_w, prm,
+                                                                                L.partials, L.ticket, L.out, L.fin);
+    } else {
+        static bool done = false;
+        if (!done) { cudaFuncSetAttribute(xtwx_dmma_kernel<KB, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); done = true; }
+        xtwx_dmma_kernel<KB, MODE, false><<<L.grid, XTWX_THREADS, sm, L.stream>>>(L.tiles, L.n_rows, L.n_tiles, L.k, L.cols, L.has_w, prm,
+                                                                                 L.partials, L.ticket, L.out, L.fin);
+    }
     return cudaGetLastError();
 }
 template <int KB, int MODE>
 static int dmma_bps_one() {
     const size_t sm = xtwx_dmma_smem<KB>();
-    cudaFuncSetAttribute(xtwx_dmma_kernel<KB, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     int nb = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, xtwx_dmma_kernel<KB, MODE>, XTWX_THREADS, sm);
+    if (xtwx_use_tma()) {
+        cudaFuncSetAttribute(xtwx_dmma_kernel<KB, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, xtwx_dmma_kernel<KB, MODE, true>, XTWX_THREADS, sm);
+    } else {
+        cudaFuncSetAttribute(xtwx_dmma_kernel<KB, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, xtwx_dmma_kernel<KB, MODE, false>, XTWX_THREADS, sm);
+    }
     return nb;
 }
 static bool xtwx_use_fp64_variant() {
