@@ -11,6 +11,7 @@
 #include <cstring>
 #include <dlfcn.h>
 #include <thread>
+#include <chrono>
 
 #define LOCK std::lock_guard<std::recursive_mutex> lock_(apb::rt_mutex())
 

@@ -49,15 +49,20 @@ bool eval_glm(Resident* r, GlmFam fam, const double* beta, size_t P, const doubl
     // index columns by COLS, so only OLS may carry weights
     if (r->has_w && fam != GLM_OLS) return set_error("weights are only used by the OLS family; drop them before pinning");
     const bool wide = K > MAX_K_REG;
+    static int tma_env = -1;
+    if (tma_env < 0) { const char* e = getenv("APOP_B200_GLM_TMA"); tma_env = (e && e[0] == '1') ? 1 : 0; }
+    const bool tma = tma_env && fam == GLM_PROBIT && !has_w && (K == 16 || K == 20 || K == 24 || K == 32);
     static int bps_cache[GLM_FAM_COUNT][MAX_K_REG + 1][2];
     int bps_wide = 0;
     int& bps = wide ? bps_wide : bps_cache[fam][K][has_w ? 1 : 0];
-    if (!bps) bps = wide ? glm_wide_blocks_per_sm(fam, K) : glm_blocks_per_sm(fam, K, has_w);
-    if (bps <= 0) return set_error("kernel for family %d, k=%d is not available on this device", (int)fam, K);
+    if (tma) { static int tb[MAX_K_REG + 1]; if (!tb[K]) tb[K] = glm_tma_blocks_per_sm_probit(K); bps_wide = tb[K]; }
+    int& bps_ref = tma ? bps_wide : bps;
+    if (!bps_ref) bps_ref = wide ? glm_wide_blocks_per_sm(fam, K) : glm_blocks_per_sm(fam, K, has_w);
+    if (bps_ref <= 0) return set_error("kernel for family %d, k=%d is not available on this device", (int)fam, K);
     const int NOUT = MAX_ACC + K;
     GlmLaunch L;
     L.tiles = r->tiles; L.n_rows = r->n_rows; L.n_tiles = r->n_tiles;
-    L.grid = grid_for(bps, r->n_tiles, GLM_THREADS / 32);
+    L.grid = grid_for(bps_ref, r->n_tiles, GLM_THREADS / 32);
     if (!ensure_partials((size_t)L.grid * NOUT)) return false;
     L.partials = R.d_partials; L.ticket = R.d_ticket; L.out = R.d_out; L.stream = R.stream;
     L.fin = make_fin(NOUT);
@@ -70,7 +75,8 @@ bool eval_glm(Resident* r, GlmFam fam, const double* beta, size_t P, const doubl
         if (!cuda_ok(cudaMemcpyAsync(R.d_beta, beta, P * sizeof(double), cudaMemcpyHostToDevice, R.stream), "H2D beta")) return false;
     }
     time_begin();
-    if (!cuda_ok(wide ? glm_wide_launch(fam, K, r->cols, has_w, L, R.d_beta, prm.aux) : glm_launch(fam, K, has_w, L, prm),
+    if (!cuda_ok(tma ? glm_tma_launch_probit(K, L, prm)
+                     : wide ? glm_wide_launch(fam, K, r->cols, has_w, L, R.d_beta, prm.aux) : glm_launch(fam, K, has_w, L, prm),
                  "glm kernel launch")) return false;
     time_end_record();
     R.launches++;

@@ -74,10 +74,17 @@ bool upload(Resident* r, const apop_data* d) {
     }
     bool ok = true;
     int ci = 0;
+    static const bool trace = getenv("APOP_B200_PIN_TRACE") != nullptr;
+    double t_wait = 0.0, t_gather = 0.0;
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto since = [](std::chrono::steady_clock::time_point t0) { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); };
     for (size_t r0 = 0; ok && r0 < n; r0 += chunk, ci++) {
         const size_t rows = (n - r0 < chunk) ? n - r0 : chunk;
         const int buf = ci & 1;
+        auto tw = std::chrono::steady_clock::now();
         if (ci >= 2) ok = cuda_ok(cudaEventSynchronize(R.pin_ev[buf]), "pin staging wait");   // chunk ci-2 has left this buffer
+        t_wait += since(tw);
+        auto tg = std::chrono::steady_clock::now();
         double* hX = R.pin_host[buf];
         double* hy_ = hX + rows * (size_t)k;
         double* hw_ = hy_ + (hy ? rows : 0);
@@ -102,6 +109,7 @@ bool upload(Resident* r, const apop_data* d) {
             for (int t = 0; t < nt; t++) pool.emplace_back(gather, rows * t / nt, rows * (t + 1) / nt);
             for (auto& th : pool) th.join();
         }
+        t_gather += since(tg);
         double* dX = R.pin_dev[buf];
         double* dy = dX + rows * (size_t)k;
         double* dw = dy + (hy ? rows : 0);
@@ -111,6 +119,9 @@ bool upload(Resident* r, const apop_data* d) {
         ok = ok && cuda_ok(cudaEventRecord(R.pin_ev[buf], R.stream), "event");
     }
     ok = ok && cuda_ok(cudaStreamSynchronize(R.stream), "pin sync");
+    if (trace)
+        fprintf(stderr, "[apop_b200 pin] %.3f GB in %.3f s (%d chunks of %zu rows, %d threads): gather %.3f s, waiting for the copy engine %.3f s\n",
+                need * 8e-9, since(t_begin), ci, chunk, n_threads, t_gather, t_wait);
     return ok;
 }
 

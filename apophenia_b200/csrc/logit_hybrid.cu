@@ -1,0 +1,278 @@
+// logit_hybrid.cu -- multinomial logit, default kernel: lane = row for X.B and the soft-max,
+// FP64 DMMA for the score contraction, tiles streamed through a per-warp shared-memory ring.
+//
+// Measured on the B200 (tools/micro/pipes.cu): DFMA and DMMA.8x8x4 issue to the SAME FP64
+// datapath (34 and 37 TFLOP/s alone, 32 TFLOP/s interleaved), so the tensor path buys no
+// extra flops here -- what it buys is shared-memory traffic and issue slots.  Per 32-row tile:
+//   prefetch  the next tile of this warp arrives with 16-byte cp.async (LDGSTS, L1 bypassed)
+//             while the current one is processed; 16-byte chunks of odd columns are XOR-
+//             swizzled (chunk ^ 4) so that BOTH access patterns below are bank-conflict free
+//             without padding;
+//   stage 1   lane = row: x_ij from shared memory (one 256-byte row of banks per column),
+//             C-1 DFMA chains against B in the constant bank -- no padded category, no
+//             cross-lane traffic;
+//   soft-max  lane = row, one_logit_row (model/apop_probit.c:212-229).  Fast path when every
+//             |x.b_c| < 708 (tested on the high words, ALU pipe): log(1 + sum_c exp(xb_c))
+//             directly, which is the reference's max + log(sum exp(xb_c - max) + exp(-max))
+//             without the shift (equal to rounding), with the 17-operation fm_exp_fast; any
+//             other row sends its warp through the reference-shaped shifted form;
+//   stage 3   G^T[c][j] += R^T[c][row] . X[row][j] as DMMA.8x8x4 (M = categories, N = 8
+//             columns, K = 4 rows): the residuals go through an 8 x 32 slab (written lane =
+//             row, read back as A fragments), X fragments are 16-byte shared-memory loads
+//             (rows 2q, 2q+1 of a column), 32 DMMA per tile in 8 independent chains.
+// X and y are read from HBM exactly once: 8(k+1) bytes per row.
+#include "logit_kernel.cuh"
+#include "fastmath.cuh"
+
+namespace apb {
+
+__device__ __forceinline__ void dmma_884(double& d0, double& d1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(d0), "+d"(d1)
+        : "d"(a), "d"(b));
+}
+
+constexpr int HYB_STAGES = 2;
+
+template <int KB, int C1>
+__global__ void __launch_bounds__(LOGIT_THREADS, 3)
+logit_hybrid_kernel(const double* __restrict__ tiles, const unsigned long long n_rows,
+                    const unsigned long long n_tiles, const int K, const __grid_constant__ LogitParams prm,
+                    double* __restrict__ partials, unsigned int* __restrict__ ticket,
+                    double* __restrict__ out, const __grid_constant__ FinalizeCtx fin) {
+    constexpr int WARPS = LOGIT_THREADS / 32;
+    constexpr int JB = KB / 8;
+    constexpr int TILE_D = (KB + 1) * TILE_ROWS;          // staged tile: KB columns (>= K: zero) + y, unpadded
+    constexpr int WARP_D = HYB_STAGES * TILE_D + 8 * TILE_ROWS;
+    constexpr int NOUT = 1 + KB * C1;
+    extern __shared__ __align__(16) double smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, q = lane & 3;
+    double* ring = smem + warp * WARP_D;
+    double* slab = ring + HYB_STAGES * TILE_D;            // R^T[c][row], 8 rows of 32, same swizzle
+    const unsigned long long gwarp = (unsigned long long)blockIdx.x * WARPS + warp;
+    const unsigned long long nwarps = (unsigned long long)gridDim.x * WARPS;
+    const int cols = K + 1;
+
+    // columns K..KB-1 of both stages and the slab rows of the padding categories are zero for the
+    // whole kernel (the prefetch never writes them): no predicate in the loops below
+    for (int i = lane; i < HYB_STAGES * TILE_D; i += 32) {
+        const int col = (i % TILE_D) / TILE_ROWS;
+        if (col >= K && col < KB) ring[i] = 0.0;
+    }
+    for (int i = C1 * TILE_ROWS + lane; i < 8 * TILE_ROWS; i += 32) slab[i] = 0.0;
+    __syncwarp();
+
+    // 16-byte chunk `lane + 32 i` of a resident tile is chunk (lane & 15) of column (lane >> 4) + 2 i:
+    // the column parity, hence the swizzle, is a per-lane constant.  y (resident column K) is staged
+    // at the fixed position KB (even: unswizzled)
+    const int par = lane >> 4;
+    const int pf_x = par * TILE_ROWS + (((lane & 15) ^ (par << 2)) << 1);
+    const int pf_y = KB * TILE_ROWS + (((lane & 15) ^ ((KB & 1) << 2)) << 1);
+    auto prefetch = [&](unsigned long long tt, int stage) {
+        const double* src = tiles + tt * (unsigned long long)(cols * TILE_ROWS) + lane * 2;
+        const unsigned sx = smem_u32(ring + stage * TILE_D + pf_x);
+        const unsigned sy = smem_u32(ring + stage * TILE_D + pf_y);
+#pragma unroll
+        for (int i = 0; i < (KB + 2) / 2; i++) {
+            const int col = par + 2 * i;
+            if (col < K)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sx + i * 2 * TILE_ROWS * 8), "l"(src + i * 64));
+            else if (col == K)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sy), "l"(src + i * 64));
+        }
+        asm volatile("cp.async.commit_group;");
+    };
+    // lane = row view: element (row = lane, column j) sits at j*32 + row_off[j & 1]
+    const int row_off0 = lane, row_off1 = (((lane >> 1) ^ 4) << 1) | (lane & 1);
+    // fragment view: rows nb*8 + 2q + {0,1} of column (or category) n are chunk nb*4 + q of that
+    // column, stored at chunk (nb*4 + q) ^ 4s = (nb ^ s)*4 + q with s = n & 1 (= g & 1 here)
+    int fo[4];
+#pragma unroll
+    for (int nb = 0; nb < 4; nb++) fo[nb] = g * TILE_ROWS + ((((nb ^ (g & 1)) << 2) + q) << 1);
+
+    double G[JB][2], G2[JB][2];
+#pragma unroll
+    for (int jb = 0; jb < JB; jb++) G[jb][0] = G[jb][1] = G2[jb][0] = G2[jb][1] = 0.0;
+    KSum ll;
+
+    int cur = 0;
+    if (gwarp < n_tiles) prefetch(gwarp, 0);
+    for (unsigned long long t = gwarp; t < n_tiles; t += nwarps) {
+        if (t + nwarps < n_tiles) {
+            prefetch(t + nwarps, cur ^ 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+        const double* tile = ring + cur * TILE_D;
+        const double* p0 = tile + row_off0;
+        const double* p1 = tile + row_off1;
+
+        // ---- stage 1: lane = row; x in register blocks of 16 columns so that the shared-memory
+        // latency is paid per block, not per column
+        double xb[C1];
+#pragma unroll
+        for (int c = 0; c < C1; c++) xb[c] = 0.0;
+        constexpr int XBLK = (KB >= 16) ? 16 : 8;
+#pragma unroll
+        for (int j0 = 0; j0 < KB; j0 += XBLK) {
+            double xv[XBLK];
+#pragma unroll
+            for (int u = 0; u < XBLK; u++) xv[u] = (((j0 + u) & 1) ? p1 : p0)[(j0 + u) * TILE_ROWS];
+#pragma unroll
+            for (int u = 0; u < XBLK; u++)
+#pragma unroll
+                for (int c = 0; c < C1; c++) xb[c] = fma(xv[u], prm.B[(j0 + u) * C1 + c], xb[c]);
+        }
+        const double y = ((KB & 1) ? p1 : p0)[KB * TILE_ROWS];
+        // find_index (model/apop_probit.c:206-210): first category equal to y, at most C1 steps
+        int idx = C1;
+#pragma unroll
+        for (int c = C1 - 1; c >= 0; c--) idx = (y == prm.cats[c]) ? c : idx;
+        const bool valid = t * TILE_ROWS + lane < n_rows;
+
+        // ---- soft-max
+        bool fast = true;
+#pragma unroll
+        for (int c = 0; c < C1; c++) fast = fast && fm_exp_fast_ok(xb[c]);
+        // the log of the LL term is not needed by the score: only its argument is fixed here, and the
+        // (long, serial) fm_log chain is issued after the barrier, among the DMMAs of stage 3
+        double e[C1], num = 0.0, inv, lsum, lbase;
+        if (__all_sync(0xffffffffu, fast)) {
+            double sum = 1.0;                      // the numeraire's exp(0)
+#pragma unroll
+            for (int c = 0; c < C1; c++) {
+                e[c] = fm_exp_fast(xb[c]);
+                sum += e[c];
+                num = (idx == c + 1) ? xb[c] : num;
+            }
+            lsum = sum; lbase = 0.0;
+            inv = fm_rcp(sum);
+        } else {
+            double mx = xb[0];
+#pragma unroll
+            for (int c = 1; c < C1; c++) mx = fmax(mx, xb[c]);
+            double sum = 0.0;
+#pragma unroll
+            for (int c = 0; c < C1; c++) {
+                e[c] = fm_exp(xb[c] - mx);
+                sum += e[c];
+                num = (idx == c + 1) ? xb[c] : num;
+            }
+            const double e0 = fm_exp(-mx);         // the numeraire's exp(0 - max)
+            // when exp(-max) overflows the reference takes log-sum-exp = max - max:
+            // lbase + log(lsum) = 0 with lsum = 1
+            const bool over = mx < -700.0;
+            lsum = over ? 1.0 : sum + e0; lbase = over ? 0.0 : mx;
+            // probabilities for the score: overflow of e0 means p_c = 0 for every free category
+            inv = over ? 0.0 : fm_rcp(sum + e0);
+        }
+        // (the slab's previous contents were read before the barrier that ended the last iteration)
+        inv = valid ? inv : 0.0;
+#pragma unroll
+        for (int c = 0; c < C1; c++) {
+            const double ind = (valid && idx == c + 1) ? 1.0 : 0.0;
+            slab[c * TILE_ROWS + ((c & 1) ? row_off1 : row_off0)] = fma(-e[c], inv, ind);
+        }
+        __syncwarp();
+
+        // ---- stage 3: A fragments R^T[c = g][rows nb*8 + 2q + {0,1}]; X fragments with the same rows
+        double R[4][2];
+#pragma unroll
+        for (int nb = 0; nb < 4; nb++) {
+            const double2 r2 = *reinterpret_cast<const double2*>(slab + fo[nb]);
+            R[nb][0] = r2.x; R[nb][1] = r2.y;
+        }
+        ll.add(valid ? num - (lbase + fm_log(lsum)) : 0.0);
+#pragma unroll
+        for (int jb = 0; jb < JB; jb++) {
+#pragma unroll
+            for (int nb = 0; nb < 4; nb++) {
+                const double2 x2 = *reinterpret_cast<const double2*>(tile + jb * 8 * TILE_ROWS + fo[nb]);
+                dmma_884(G[jb][0], G[jb][1], R[nb][0], x2.x);
+                dmma_884(G2[jb][0], G2[jb][1], R[nb][1], x2.y);
+            }
+        }
+        __syncwarp();                              // every lane is done with this stage before it is refilled
+        cur ^= 1;
+    }
+
+    // ---- CTA reduction: lane (g, q) holds G^T[c = g][j = jb*8 + 2q + {0,1}]
+#pragma unroll
+    for (int jb = 0; jb < JB; jb++) { G[jb][0] += G2[jb][0]; G[jb][1] += G2[jb][1]; }
+    __syncthreads();                               // the rings are free: reuse as WARPS x NOUT scratch
+    const double llw = warp_sum(ll.value());
+    if (lane == 0) smem[warp * NOUT] = llw;
+    if (g < C1) {
+#pragma unroll
+        for (int jb = 0; jb < JB; jb++) {
+            smem[warp * NOUT + 1 + (jb * 8 + 2 * q) * C1 + g] = G[jb][0];
+            smem[warp * NOUT + 1 + (jb * 8 + 2 * q + 1) * C1 + g] = G[jb][1];
+        }
+    }
+    __syncthreads();
+    double* scratch = smem + WARPS * NOUT;
+    for (int v = threadIdx.x; v < NOUT; v += LOGIT_THREADS) {
+        double s = 0.0;
+#pragma unroll
+        for (int wv = 0; wv < WARPS; wv++) s += smem[wv * NOUT + v];
+        partials[(size_t)blockIdx.x * NOUT + v] = s;
+    }
+    grid_finalize(partials, NOUT, ticket, out, fin, scratch);
+}
+
+template <int KB>
+static constexpr size_t hyb_smem() {
+    return (size_t)(LOGIT_THREADS / 32) * (HYB_STAGES * (KB + 1) * TILE_ROWS + 8 * TILE_ROWS) * sizeof(double);
+}
+template <int KB, int C1>
+static cudaError_t hyb_launch_one(const LogitLaunch& L, const LogitParams& prm) {
+    static_assert((size_t)(LOGIT_THREADS / 32) * (1 + KB * C1) + (1 + KB * C1) <= hyb_smem<KB>() / sizeof(double), "reduction scratch must fit the rings");
+    static bool done = false;
+    if (!done) { cudaFuncSetAttribute(logit_hybrid_kernel<KB, C1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hyb_smem<KB>()); done = true; }
+    logit_hybrid_kernel<KB, C1><<<L.grid, LOGIT_THREADS, hyb_smem<KB>(), L.stream>>>(L.tiles, L.n_rows, L.n_tiles, L.k, prm, L.partials, L.ticket, L.out, L.fin);
+    return cudaGetLastError();
+}
+template <int KB, int C1>
+static int hyb_bps_one() {
+    cudaFuncSetAttribute(logit_hybrid_kernel<KB, C1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hyb_smem<KB>());
+    int nb = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, logit_hybrid_kernel<KB, C1>, LOGIT_THREADS, hyb_smem<KB>());
+    return nb;
+}
+
+#define APB_HYB_C(KB)                          \
+    switch (c1) {                              \
+    case 2: return APB_OP(KB, 2);              \
+    case 3: return APB_OP(KB, 3);              \
+    case 4: return APB_OP(KB, 4);              \
+    case 5: return APB_OP(KB, 5);              \
+    case 6: return APB_OP(KB, 6);              \
+    case 7: return APB_OP(KB, 7);              \
+    default: break;                            \
+    }
+cudaError_t logit_hybrid_launch(int c1, const LogitLaunch& L, const LogitParams& prm) {
+#define APB_OP(KB, C) hyb_launch_one<KB, C>(L, prm)
+    switch (logit_kb(L.k)) {
+    case 8: APB_HYB_C(8) break;
+    case 16: APB_HYB_C(16) break;
+    case 24: APB_HYB_C(24) break;
+    case 32: APB_HYB_C(32) break;
+    }
+#undef APB_OP
+    return cudaErrorInvalidValue;
+}
+int logit_hybrid_blocks_per_sm(int k, int c1) {
+#define APB_OP(KB, C) hyb_bps_one<KB, C>()
+    switch (logit_kb(k)) {
+    case 8: APB_HYB_C(8) break;
+    case 16: APB_HYB_C(16) break;
+    case 24: APB_HYB_C(24) break;
+    case 32: APB_HYB_C(32) break;
+    }
+#undef APB_OP
+    return 0;
+}
+
+}  // namespace apb

@@ -19,6 +19,7 @@
 #include "logit_kernel.cuh"
 #include "fastmath.cuh"
 #include <stdlib.h>
+#include <string.h>
 
 namespace apb {
 
@@ -393,13 +394,21 @@ static int bps_one() {
     }
 int logit_kb(int k) { return k <= 8 ? 8 : k <= 16 ? 16 : k <= 24 ? 24 : 32; }
 
-static bool use_smem_variant() {
+// 0 = hybrid (default, logit_hybrid.cu), 1 = FP64-pipe kernel above, 2 = all-DMMA kernel above;
+// APOP_B200_LOGIT_VARIANT=hybrid|fp64|dmma selects (kept for A/B measurements)
+static int logit_variant() {
     static int v = -1;
-    // the FP64-pipe kernel is the default; APOP_B200_LOGIT_DMMA=1 selects the tensor-pipe variant
-    if (v < 0) { const char* e = getenv("APOP_B200_LOGIT_DMMA"); v = (e && e[0] == '1') ? 0 : 1; }
-    return v == 1;
+    if (v < 0) {
+        const char* e = getenv("APOP_B200_LOGIT_VARIANT");
+        v = (e && !strcmp(e, "fp64")) ? 1 : (e && !strcmp(e, "dmma")) ? 2 : 0;
+        const char* d = getenv("APOP_B200_LOGIT_DMMA");
+        if (!e && d && d[0] == '1') v = 2;
+    }
+    return v;
 }
+static bool use_smem_variant() { return logit_variant() == 1; }
 cudaError_t logit_launch(int c1, const LogitLaunch& L, const LogitParams& prm) {
+    if (logit_variant() == 0) return logit_hybrid_launch(c1, L, prm);
     if (!use_smem_variant() && c1 >= 1 && c1 <= LOGIT_MAX_C1) {
         switch (logit_kb(L.k)) {
         case 8: return dmma_launch_one<8>(c1, L, prm);
@@ -419,6 +428,7 @@ cudaError_t logit_launch(int c1, const LogitLaunch& L, const LogitParams& prm) {
     return cudaErrorInvalidValue;
 }
 int logit_blocks_per_sm(int k, int c1) {
+    if (logit_variant() == 0) return logit_hybrid_blocks_per_sm(k, c1);
     if (!use_smem_variant() && c1 >= 1 && c1 <= LOGIT_MAX_C1) {
         switch (logit_kb(k)) {
         case 8: return dmma_bps_one<8>(c1);

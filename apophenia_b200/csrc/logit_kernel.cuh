@@ -26,6 +26,9 @@ struct LogitLaunch {
     FinalizeCtx fin;
 };
 int logit_kb(int k);
+// logit_hybrid.cu: the default kernel (lane = row X.B and soft-max, DMMA score, cp.async ring)
+cudaError_t logit_hybrid_launch(int c1, const LogitLaunch& L, const LogitParams& prm);
+int logit_hybrid_blocks_per_sm(int k, int c1);
 cudaError_t logit_launch(int c1, const LogitLaunch& L, const LogitParams& prm);
 int logit_blocks_per_sm(int k, int c1);
 }  // namespace apb

@@ -3,6 +3,8 @@
 #include "../apophenia_b200/csrc/families.cuh"
 extern "C" {
 double t_fm_exp(double x) { return apb::fm_exp(x); }
+double t_fm_exp_fast(double x) { return apb::fm_exp_fast(x); }
+int t_fm_exp_fast_ok(double x) { return apb::fm_exp_fast_ok(x) ? 1 : 0; }
 double t_fm_log(double z) { return apb::fm_log(z); }
 double t_fm_erfcx(double x) { return apb::fm_erfcx_pos(x); }
 void t_probit_row(double xb, double y, double* ll, double* d) { apb::RowOut o = apb::FamProbit::eval(xb, y, 1.0, nullptr); *ll = o.s[0]; *d = o.d; }

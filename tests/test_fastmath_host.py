@@ -20,7 +20,7 @@ def fm():
     subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-o", so,
                            os.path.join(ROOT, "tests", "fastmath_host.cpp")])
     L = C.CDLL(so)
-    for f in ("t_fm_exp", "t_fm_log", "t_fm_erfcx"):
+    for f in ("t_fm_exp", "t_fm_exp_fast", "t_fm_log", "t_fm_erfcx"):
         getattr(L, f).restype = C.c_double
         getattr(L, f).argtypes = [C.c_double]
     dp = C.POINTER(C.c_double)
@@ -48,6 +48,19 @@ def test_exp_log_erfcx(fm):
     for x in np.concatenate([rng.uniform(0, 30, 5000), 10 ** rng.uniform(-12, 3, 1000), [0.0]]):
         want = mp.erfc(mp.mpf(float(x))) * mp.exp(mp.mpf(float(x)) ** 2)
         assert _rel(fm.t_fm_erfcx(x), want) < 8e-16
+
+
+def test_exp_fast(fm):
+    """the unclamped exponential of the multinomial soft-max: same accuracy as fm_exp wherever its
+    guard (|x| < 708, decided on the high word) lets it run"""
+    fm.t_fm_exp_fast_ok.argtypes = [C.c_double]
+    rng = np.random.default_rng(3)
+    for x in np.concatenate([rng.uniform(-708, 708, 4000), rng.uniform(-3, 3, 3000),
+                             [0.0, 707.999999, -707.999999, 1e-300, -1e-300, 5e-324]]):
+        assert fm.t_fm_exp_fast_ok(x) == 1
+        assert _rel(fm.t_fm_exp_fast(x), mp.exp(mp.mpf(float(x)))) < 3e-16
+    for x in (708.0, -708.0, 709.5, -745.0, 1e6, -1e300, np.inf, -np.inf, np.nan):
+        assert fm.t_fm_exp_fast_ok(x) == 0
 
 
 def test_gauss_tail(fm):
