@@ -23,6 +23,7 @@
 // X and y are read from HBM exactly once: 8(k+1) bytes per row.
 #include "logit_kernel.cuh"
 #include "fastmath.cuh"
+#include <stdlib.h>
 
 namespace apb {
 
@@ -32,10 +33,9 @@ __device__ __forceinline__ void dmma_884(double& d0, double& d1, double a, doubl
         : "d"(a), "d"(b));
 }
 
-constexpr int HYB_STAGES = 2;
 
-template <int KB, int C1>
-__global__ void __launch_bounds__(LOGIT_THREADS, 3)
+template <int KB, int C1, int HYB_STAGES>
+__global__ void __launch_bounds__(LOGIT_THREADS, HYB_STAGES == 2 ? 3 : 4)
 logit_hybrid_kernel(const double* __restrict__ tiles, const unsigned long long n_rows,
                     const unsigned long long n_tiles, const int K, const __grid_constant__ LogitParams prm,
                     double* __restrict__ partials, unsigned int* __restrict__ ticket,
@@ -75,6 +75,7 @@ logit_hybrid_kernel(const double* __restrict__ tiles, const unsigned long long n
         const unsigned sy = smem_u32(ring + stage * TILE_D + pf_y);
 #pragma unroll
         for (int i = 0; i < (KB + 2) / 2; i++) {
+            // (a branch-free, predicated form of this loop costs 48 more registers and measured 11 % slower)
             const int col = par + 2 * i;
             if (col < K)
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sx + i * 2 * TILE_ROWS * 8), "l"(src + i * 64));
@@ -99,7 +100,7 @@ logit_hybrid_kernel(const double* __restrict__ tiles, const unsigned long long n
     int cur = 0;
     if (gwarp < n_tiles) prefetch(gwarp, 0);
     for (unsigned long long t = gwarp; t < n_tiles; t += nwarps) {
-        if (t + nwarps < n_tiles) {
+        if (HYB_STAGES == 2 && t + nwarps < n_tiles) {
             prefetch(t + nwarps, cur ^ 1);
             asm volatile("cp.async.wait_group 1;" ::: "memory");
         } else
@@ -138,18 +139,19 @@ logit_hybrid_kernel(const double* __restrict__ tiles, const unsigned long long n
         for (int c = 0; c < C1; c++) fast = fast && fm_exp_fast_ok(xb[c]);
         // the log of the LL term is not needed by the score: only its argument is fixed here, and the
         // (long, serial) fm_log chain is issued after the barrier, among the DMMAs of stage 3
-        double e[C1], num = 0.0, inv, lsum, lbase;
-        if (__all_sync(0xffffffffu, fast)) {
+        double e[C1], num = 0.0, inv, lsum, lbase = 0.0;
+        {
             double sum = 1.0;                      // the numeraire's exp(0)
 #pragma unroll
             for (int c = 0; c < C1; c++) {
-                e[c] = fm_exp_fast(xb[c]);
+                e[c] = fm_exp_fast(xb[c]);         // garbage (never a trap) where the guard fails
                 sum += e[c];
                 num = (idx == c + 1) ? xb[c] : num;
             }
-            lsum = sum; lbase = 0.0;
+            lsum = sum;
             inv = fm_rcp(sum);
-        } else {
+        }
+        if (!__all_sync(0xffffffffu, fast)) {      // rare: the reference-shaped shifted form for the whole warp
             double mx = xb[0];
 #pragma unroll
             for (int c = 1; c < C1; c++) mx = fmax(mx, xb[c]);
@@ -158,7 +160,6 @@ logit_hybrid_kernel(const double* __restrict__ tiles, const unsigned long long n
             for (int c = 0; c < C1; c++) {
                 e[c] = fm_exp(xb[c] - mx);
                 sum += e[c];
-                num = (idx == c + 1) ? xb[c] : num;
             }
             const double e0 = fm_exp(-mx);         // the numeraire's exp(0 - max)
             // when exp(-max) overflows the reference takes log-sum-exp = max - max:
@@ -184,7 +185,7 @@ logit_hybrid_kernel(const double* __restrict__ tiles, const unsigned long long n
             const double2 r2 = *reinterpret_cast<const double2*>(slab + fo[nb]);
             R[nb][0] = r2.x; R[nb][1] = r2.y;
         }
-        ll.add(valid ? num - (lbase + fm_log(lsum)) : 0.0);
+        ll.add(valid ? num - (lbase + fm_log_normal(lsum)) : 0.0);
 #pragma unroll
         for (int jb = 0; jb < JB; jb++) {
 #pragma unroll
@@ -195,7 +196,8 @@ logit_hybrid_kernel(const double* __restrict__ tiles, const unsigned long long n
             }
         }
         __syncwarp();                              // every lane is done with this stage before it is refilled
-        cur ^= 1;
+        if (HYB_STAGES == 2) cur ^= 1;
+        else if (t + nwarps < n_tiles) prefetch(t + nwarps, 0);   // single buffer: latency hidden across warps only
     }
 
     // ---- CTA reduction: lane (g, q) holds G^T[c = g][j = jb*8 + 2q + {0,1}]
@@ -222,25 +224,36 @@ logit_hybrid_kernel(const double* __restrict__ tiles, const unsigned long long n
     grid_finalize(partials, NOUT, ticket, out, fin, scratch);
 }
 
-template <int KB>
+static int hyb_stages() {
+    static int v = 0;
+    if (!v) { const char* e = getenv("APOP_B200_LOGIT_STAGES"); v = (e && e[0] == '1') ? 1 : 2; }
+    return v;
+}
+template <int KB, int ST>
 static constexpr size_t hyb_smem() {
-    return (size_t)(LOGIT_THREADS / 32) * (HYB_STAGES * (KB + 1) * TILE_ROWS + 8 * TILE_ROWS) * sizeof(double);
+    return (size_t)(LOGIT_THREADS / 32) * (ST * (KB + 1) * TILE_ROWS + 8 * TILE_ROWS) * sizeof(double);
+}
+template <int KB, int C1, int ST>
+static cudaError_t hyb_launch_st(const LogitLaunch& L, const LogitParams& prm) {
+    static_assert((size_t)(LOGIT_THREADS / 32) * (1 + KB * C1) + (1 + KB * C1) <= hyb_smem<KB, ST>() / sizeof(double), "reduction scratch must fit the rings");
+    static bool done = false;
+    if (!done) { cudaFuncSetAttribute(logit_hybrid_kernel<KB, C1, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hyb_smem<KB, ST>()); done = true; }
+    logit_hybrid_kernel<KB, C1, ST><<<L.grid, LOGIT_THREADS, hyb_smem<KB, ST>(), L.stream>>>(L.tiles, L.n_rows, L.n_tiles, L.k, prm, L.partials, L.ticket, L.out, L.fin);
+    return cudaGetLastError();
+}
+template <int KB, int C1, int ST>
+static int hyb_bps_st() {
+    cudaFuncSetAttribute(logit_hybrid_kernel<KB, C1, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hyb_smem<KB, ST>());
+    int nb = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, logit_hybrid_kernel<KB, C1, ST>, LOGIT_THREADS, hyb_smem<KB, ST>());
+    return nb;
 }
 template <int KB, int C1>
 static cudaError_t hyb_launch_one(const LogitLaunch& L, const LogitParams& prm) {
-    static_assert((size_t)(LOGIT_THREADS / 32) * (1 + KB * C1) + (1 + KB * C1) <= hyb_smem<KB>() / sizeof(double), "reduction scratch must fit the rings");
-    static bool done = false;
-    if (!done) { cudaFuncSetAttribute(logit_hybrid_kernel<KB, C1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hyb_smem<KB>()); done = true; }
-    logit_hybrid_kernel<KB, C1><<<L.grid, LOGIT_THREADS, hyb_smem<KB>(), L.stream>>>(L.tiles, L.n_rows, L.n_tiles, L.k, prm, L.partials, L.ticket, L.out, L.fin);
-    return cudaGetLastError();
+    return hyb_stages() == 1 ? hyb_launch_st<KB, C1, 1>(L, prm) : hyb_launch_st<KB, C1, 2>(L, prm);
 }
 template <int KB, int C1>
-static int hyb_bps_one() {
-    cudaFuncSetAttribute(logit_hybrid_kernel<KB, C1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hyb_smem<KB>());
-    int nb = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, logit_hybrid_kernel<KB, C1>, LOGIT_THREADS, hyb_smem<KB>());
-    return nb;
-}
+static int hyb_bps_one() { return hyb_stages() == 1 ? hyb_bps_st<KB, C1, 1>() : hyb_bps_st<KB, C1, 2>(); }
 
 #define APB_HYB_C(KB)                          \
     switch (c1) {                              \
