@@ -16,8 +16,10 @@ LIB_PATH = os.path.join(_PKG, "libapop_b200.so")
 HOSTMINI_PATH = os.path.join(_PKG, "libapop_hostmini.so")
 
 PROBIT, LOGIT, POISSON, NORMAL, OLS, POISSON_REG, EXPONENTIAL, GAMMA, LOGNORMAL = range(9)
+BERNOULLI, BETA, ZIPF, DIRICHLET, TDIST, YULE = range(9, 15)
 FAMILY_NAMES = {PROBIT: "probit", LOGIT: "logit", POISSON: "poisson", NORMAL: "normal", OLS: "ols",
-                POISSON_REG: "poisson_reg", EXPONENTIAL: "exponential", GAMMA: "gamma", LOGNORMAL: "lognormal"}
+                POISSON_REG: "poisson_reg", EXPONENTIAL: "exponential", GAMMA: "gamma", LOGNORMAL: "lognormal",
+                BERNOULLI: "bernoulli", BETA: "beta", ZIPF: "zipf", DIRICHLET: "dirichlet", TDIST: "t", YULE: "yule"}
 MAP_IDENTITY, MAP_DEV, MAP_DEV2, MAP_POISSON, MAP_LOG, MAP_EXP = range(6)
 
 
@@ -121,6 +123,16 @@ SIGNATURES = {
     "apop_b200_gamma_score": (None, [_PD, _PV, _PM]),
     "apop_b200_lognormal_ll": (C.c_longdouble, [_PD, _PM]),
     "apop_b200_lognormal_score": (None, [_PD, _PV, _PM]),
+    "apop_b200_bernoulli_ll": (C.c_longdouble, [_PD, _PM]),
+    "apop_b200_bernoulli_score": (None, [_PD, _PV, _PM]),
+    "apop_b200_beta_ll": (C.c_longdouble, [_PD, _PM]),
+    "apop_b200_beta_score": (None, [_PD, _PV, _PM]),
+    "apop_b200_zipf_ll": (C.c_longdouble, [_PD, _PM]),
+    "apop_b200_dirichlet_ll": (C.c_longdouble, [_PD, _PM]),
+    "apop_b200_dirichlet_score": (None, [_PD, _PV, _PM]),
+    "apop_b200_t_ll": (C.c_longdouble, [_PD, _PM]),
+    "apop_b200_yule_ll": (C.c_longdouble, [_PD, _PM]),
+    "apop_b200_yule_score": (None, [_PD, _PV, _PM]),
     "apop_b200_poisson_reg_ll": (C.c_longdouble, [_PD, _PM]),
     "apop_b200_poisson_reg_score": (None, [_PD, _PV, _PM]),
     "apop_b200_map_sum": (C.c_double, [_PD, C.c_int, C.c_double, C.c_char]),

@@ -11,14 +11,14 @@ import numpy as np
 
 from . import abi
 from .abi import (B200Error, Data, Model, PROBIT, LOGIT, POISSON, NORMAL, OLS, POISSON_REG,  # noqa: F401
-                  EXPONENTIAL, GAMMA, LOGNORMAL,
+                  EXPONENTIAL, GAMMA, LOGNORMAL, BERNOULLI, BETA, ZIPF, DIRICHLET, TDIST, YULE,
                   MAP_IDENTITY, MAP_DEV, MAP_DEV2, MAP_POISSON, MAP_LOG, MAP_EXP)
 
 __all__ = ["init", "finalize", "pin", "unpin", "invalidate", "is_pinned", "log_likelihood", "score",
            "ll_score", "map_sum", "synth", "SynthData", "launch_count", "last_pass_ms", "pass_timer_reset",
            "pass_timer", "probit_model", "logit_model", "vector_model", "Data", "Model", "B200Error",
            "PROBIT", "LOGIT", "POISSON", "NORMAL", "OLS", "POISSON_REG", "EXPONENTIAL", "GAMMA", "LOGNORMAL",
-           "comm_init_from_torch",
+           "BERNOULLI", "BETA", "ZIPF", "DIRICHLET", "TDIST", "YULE", "comm_init_from_torch",
            "comm_finalize", "set_auto_pin", "last_error", "information", "ols_gram",
            "dot", "col_sums", "probit_start", "ll_score_batched", "bootstrap_counts", "counts_download",
            "MAP_IDENTITY", "MAP_DEV", "MAP_DEV2", "MAP_POISSON", "MAP_LOG", "MAP_EXP"]
@@ -84,11 +84,15 @@ def pass_timer():
 
 _LL = {PROBIT: "apop_b200_probit_ll", LOGIT: "apop_b200_logit_ll", POISSON: "apop_b200_poisson_ll",
        NORMAL: "apop_b200_normal_ll", OLS: "apop_b200_ols_ll", POISSON_REG: "apop_b200_poisson_reg_ll",
-       EXPONENTIAL: "apop_b200_exponential_ll", GAMMA: "apop_b200_gamma_ll", LOGNORMAL: "apop_b200_lognormal_ll"}
+       EXPONENTIAL: "apop_b200_exponential_ll", GAMMA: "apop_b200_gamma_ll", LOGNORMAL: "apop_b200_lognormal_ll",
+       BERNOULLI: "apop_b200_bernoulli_ll", BETA: "apop_b200_beta_ll", ZIPF: "apop_b200_zipf_ll",
+       DIRICHLET: "apop_b200_dirichlet_ll", TDIST: "apop_b200_t_ll", YULE: "apop_b200_yule_ll"}
 _SC = {PROBIT: "apop_b200_probit_score", LOGIT: "apop_b200_logit_score", POISSON: "apop_b200_poisson_score",
        NORMAL: "apop_b200_normal_score", OLS: "apop_b200_ols_score",
        POISSON_REG: "apop_b200_poisson_reg_score", EXPONENTIAL: "apop_b200_exponential_score",
-       GAMMA: "apop_b200_gamma_score", LOGNORMAL: "apop_b200_lognormal_score"}
+       GAMMA: "apop_b200_gamma_score", LOGNORMAL: "apop_b200_lognormal_score",
+       BERNOULLI: "apop_b200_bernoulli_score", BETA: "apop_b200_beta_score", DIRICHLET: "apop_b200_dirichlet_score",
+       YULE: "apop_b200_yule_score"}
 
 
 def _ptr(obj):

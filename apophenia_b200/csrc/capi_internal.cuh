@@ -33,7 +33,7 @@ void time_begin();
 void time_end_record();
 void time_collect();
 bool eval_glm(apb::Resident* r, apb::GlmFam fam, const double* beta, size_t P, const double* aux, std::vector<double>& out);
-bool eval_cells(apb::Resident* r, int mode, double p0, double* out5, bool matrix = true);
+bool eval_cells(apb::Resident* r, int mode, double p0, double* out5, bool matrix = true, double p1 = 0.0, double p2 = 0.0);
 bool eval_logit(apb::Resident* r, const std::vector<double>& B, size_t C1, const std::vector<double>& cats, std::vector<double>& out);
 bool eval_xtwx(apb::Resident* r, int mode, const double* beta, const double* aux, std::vector<double>& out);
 bool global_counts(apb::Resident* r, double& n_rows, double& m_cells, double& v_cells);

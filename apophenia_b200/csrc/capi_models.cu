@@ -87,14 +87,14 @@ bool eval_glm(Resident* r, GlmFam fam, const double* beta, size_t P, const doubl
     return true;
 }
 
-bool eval_cells(Resident* r, int mode, double p0, double* out5, bool matrix) {
+bool eval_cells(Resident* r, int mode, double p0, double* out5, bool matrix, double p1, double p2) {
     Runtime& R = rt();
     const int grid = grid_for(8, r->n_tiles, CELLS_THREADS / 32);
     if (!ensure_partials((size_t)grid * CELLS_NOUT)) return false;
     const FinalizeCtx fin = make_fin(CELLS_NOUT);
     time_begin();
     if (!cuda_ok(cells_launch(mode, r->tiles, r->n_rows, r->n_tiles, matrix ? r->k : 0, r->has_y ? r->k : -1, r->cols, p0, R.d_partials,
-                              R.d_ticket, R.d_out, grid, R.stream, fin), "cells kernel launch")) return false;
+                              R.d_ticket, R.d_out, grid, R.stream, fin, p1, p2), "cells kernel launch")) return false;
     time_end_record();
     R.launches++;
     if (!reduce_and_fetch(CELLS_NOUT, fin)) return false;
@@ -619,7 +619,7 @@ extern "C" int apop_b200_dot(apop_data* d, const double* B, size_t k, size_t c, 
 // ---- prep reductions on the device --------------------------------------
 extern "C" int apop_b200_col_sums(apop_data* d, int mode, double* out) {
     LOCK;
-    if (!d || !out || mode < 0 || mode > 2) { set_error("apop_b200_col_sums: bad argument"); return 1; }
+    if (!d || !out || mode < 0 || mode > 3) { set_error("apop_b200_col_sums: bad argument"); return 1; }
     Resident* r = acquire(d);
     if (!r) return 1;
     Runtime& R = rt();

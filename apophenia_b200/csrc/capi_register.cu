@@ -20,6 +20,12 @@ static Entry entry_of(apop_b200_family f) {
     case APOP_B200_EXPONENTIAL: return {apop_b200_exponential_ll, apop_b200_exponential_score};
     case APOP_B200_GAMMA: return {apop_b200_gamma_ll, apop_b200_gamma_score};
     case APOP_B200_LOGNORMAL: return {apop_b200_lognormal_ll, apop_b200_lognormal_score};
+    case APOP_B200_BERNOULLI: return {apop_b200_bernoulli_ll, apop_b200_bernoulli_score};
+    case APOP_B200_BETA: return {apop_b200_beta_ll, apop_b200_beta_score};
+    case APOP_B200_ZIPF: return {apop_b200_zipf_ll, nullptr};         // no analytic score in the reference: numeric gradient over the device LL
+    case APOP_B200_DIRICHLET: return {apop_b200_dirichlet_ll, apop_b200_dirichlet_score};
+    case APOP_B200_T: return {apop_b200_t_ll, nullptr};
+    case APOP_B200_YULE: return {apop_b200_yule_ll, apop_b200_yule_score};
     default: return {nullptr, nullptr};
     }
 }
@@ -39,6 +45,7 @@ extern "C" int apop_b200_register(apop_model* model, apop_b200_family family) {
     if (!saved_ll().count(model)) saved_ll()[model] = model->log_likelihood;
     model->log_likelihood = e.ll;
     // hash = address of log_likelihood (apop.m4.h:532)
+    if (!e.score) return 0;   // apop_score then falls back to the numeric gradient (apop_model.m4.c:296-299)
     return add("apop_score", (void*)e.score, (unsigned long)apop_score_hash(model));
 }
 extern "C" int apop_b200_unregister(apop_model* model) {

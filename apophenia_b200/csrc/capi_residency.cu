@@ -36,7 +36,7 @@ bool upload(Resident* r, const apop_data* d) {
     if (!r->tiles && need)
         if (!cuda_ok(cudaMalloc(&r->tiles, need * sizeof(double)), "cudaMalloc(resident tiles)")) return false;
     r->n_rows = n; r->k = k; r->has_y = hy; r->has_w = hw; r->cols = cols; r->n_tiles = n_tiles;
-    r->memo_valid = false; r->have_lgamma_y = false; r->have_poisson = false; r->have_gamma = false; r->dirty = false;
+    r->memo_valid = false; r->have_lgamma_y = false; r->have_poisson = false; r->have_gamma = false; r->consts.clear(); r->dirty = false;
     r->n_global_epoch = ~0ull;
     if (!need) return true;
 
@@ -177,7 +177,7 @@ Resident* acquire(apop_data* d) {
         Resident* r = it->second;
         if (r->dirty && !upload(r, d)) return nullptr;
         if (r->consts_epoch != R.comm_epoch) {   // cached sums are sums over the ranks of one communicator
-            r->memo_valid = false; r->have_lgamma_y = false; r->have_poisson = false; r->have_gamma = false;
+            r->memo_valid = false; r->have_lgamma_y = false; r->have_poisson = false; r->have_gamma = false; r->consts.clear();
             r->consts_epoch = R.comm_epoch;
         }
         return r;

@@ -12,8 +12,17 @@
 
 namespace apb {
 
+// psi(x), x > 0: recurrence up to x >= 12, then the asymptotic series (the stand-in for gsl_sf_psi
+// that oracle/oracle.c uses, here in double)
+__device__ __forceinline__ double digamma_pos(double x) {
+    double r = 0.0;
+    while (x < 12.0) { r -= 1.0 / x; x += 1.0; }
+    const double f = 1.0 / (x * x);
+    return r + log(x) - 0.5 / x - f * (1.0 / 12 - f * (1.0 / 120 - f * (1.0 / 252 - f * (1.0 / 240 - f * (1.0 / 132 - f * (691.0 / 32760 - f / 12))))));
+}
+
 template <int MODE>
-__device__ __forceinline__ void cell_eval(double x, double p0, double& f0, double& f1, int& bad) {
+__device__ __forceinline__ void cell_eval(double x, double p0, double p1, double p2, double& f0, double& f1, int& bad) {
     if (MODE == CELLS_NORMAL) {
         const double d = x - p0;
         f0 = d;
@@ -36,6 +45,21 @@ __device__ __forceinline__ void cell_eval(double x, double p0, double& f0, doubl
         f1 = (l - p0) * (l - p0);
     } else if (MODE == CELLS_LOG) {
         f0 = log(x); f1 = 0.0;
+    } else if (MODE == CELLS_NONZERO) {
+        f0 = (x != 0.0) ? 1.0 : 0.0; f1 = 0.0;
+    } else if (MODE == CELLS_BETA) {
+        const bool in = !(x < 0.0 || x > 1.0);     // betamap's test, NaN cells pass it as they do there
+        bad += in ? 0 : 1;
+        f0 = in ? log(x) : 0.0;
+        f1 = in ? log(1.0 - x) : 0.0;
+    } else if (MODE == CELLS_BETA_RAW) {
+        f0 = log(x); f1 = log(1.0 - x);
+    } else if (MODE == CELLS_T) {
+        const double z = (x - p0) / p1;
+        f0 = log(1.0 + z * z / p2); f1 = 0.0;
+    } else if (MODE == CELLS_YULE) {
+        f0 = ((x >= 1.0) ? lgamma(x) : 0.0) - lgamma(x + p0);
+        f1 = -digamma_pos(x + p0);
     } else {  // CELLS_EXP
         f0 = exp(x); f1 = 0.0;
     }
@@ -44,7 +68,7 @@ __device__ __forceinline__ void cell_eval(double x, double p0, double& f0, doubl
 template <int MODE>
 __global__ void __launch_bounds__(CELLS_THREADS)
 cells_kernel(const double* __restrict__ tiles, unsigned long long n_rows, unsigned long long n_tiles,
-             int k, int ycol, int cols, double p0, double* __restrict__ partials,
+             int k, int ycol, int cols, double p0, double p1, double p2, double* __restrict__ partials,
              unsigned int* __restrict__ ticket, double* __restrict__ out, const __grid_constant__ FinalizeCtx fin) {
     constexpr int WARPS = CELLS_THREADS / 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -67,7 +91,7 @@ cells_kernel(const double* __restrict__ tiles, unsigned long long n_rows, unsign
 #pragma unroll
             for (int u = 0; u < 16; u++) {
                 double f0, f1;
-                cell_eval<MODE>(x[u], p0, f0, f1, b);
+                cell_eval<MODE>(x[u], p0, p1, p2, f0, f1, b);
                 s0 += f0; s1 += f1;
             }
         }
@@ -78,19 +102,19 @@ cells_kernel(const double* __restrict__ tiles, unsigned long long n_rows, unsign
 #pragma unroll
             for (int u = 0; u < 4; u++) {
                 double f0, f1;
-                cell_eval<MODE>(x[u], p0, f0, f1, b);
+                cell_eval<MODE>(x[u], p0, p1, p2, f0, f1, b);
                 s0 += f0; s1 += f1;
             }
         }
         for (; j < k; j++) {
             double f0, f1;
-            cell_eval<MODE>(ld_stream(base + j * TILE_ROWS), p0, f0, f1, b);
+            cell_eval<MODE>(ld_stream(base + j * TILE_ROWS), p0, p1, p2, f0, f1, b);
             s0 += f0; s1 += f1;
         }
         if (valid) { m0.add(s0); m1.add(s1); bad += b; }
         if (ycol >= 0) {
             double f0, f1; int by = 0;
-            cell_eval<MODE>(ld_stream(base + ycol * TILE_ROWS), p0, f0, f1, by);
+            cell_eval<MODE>(ld_stream(base + ycol * TILE_ROWS), p0, p1, p2, f0, f1, by);
             if (valid) { v0.add(f0); v1.add(f1); bad += by; }
         }
     }
@@ -113,11 +137,11 @@ cells_kernel(const double* __restrict__ tiles, unsigned long long n_rows, unsign
 
 cudaError_t cells_launch(int mode, const double* tiles, size_t n_rows, size_t n_tiles, int k,
                          int ycol, int cols, double p0, double* partials, unsigned int* ticket,
-                         double* out, int grid, cudaStream_t st, const FinalizeCtx& fin) {
+                         double* out, int grid, cudaStream_t st, const FinalizeCtx& fin, double p1, double p2) {
 #define APB_CELLS(M)                                                                          \
     case M:                                                                                   \
         cells_kernel<M><<<grid, CELLS_THREADS, 0, st>>>(tiles, n_rows, n_tiles, k, ycol,         \
-                                                        cols, p0, partials, ticket, out, fin); \
+                                                        cols, p0, p1, p2, partials, ticket, out, fin); \
         break;
     switch (mode) {
         APB_CELLS(CELLS_IDENTITY)
@@ -127,6 +151,11 @@ cudaError_t cells_launch(int mode, const double* tiles, size_t n_rows, size_t n_
         APB_CELLS(CELLS_EXP)
         APB_CELLS(CELLS_GAMMA)
         APB_CELLS(CELLS_LOGNORMAL)
+        APB_CELLS(CELLS_NONZERO)
+        APB_CELLS(CELLS_BETA)
+        APB_CELLS(CELLS_BETA_RAW)
+        APB_CELLS(CELLS_T)
+        APB_CELLS(CELLS_YULE)
     default: return cudaErrorInvalidValue;
     }
 #undef APB_CELLS
@@ -136,7 +165,8 @@ cudaError_t cells_launch(int mode, const double* tiles, size_t n_rows, size_t n_
 // ---------------------------------------------------------------------------------------
 // Per-column sums over the rows: the O(N k) prep reductions either side of the path
 // (SURVEY 8(f) rank 2).  mode 0: sum ln|x| over non-zero cells -- probit_prep's start point
-// exp(mean ln|x_ij|) (model/apop_probit.c:65-80); mode 1: sum x; mode 2: sum x^2.
+// exp(mean ln|x_ij|) (model/apop_probit.c:65-80); mode 1: sum x; mode 2: sum x^2; mode 3: sum ln x
+// (the column sums of dirichlet_dlog_likelihood, model/apop_dirichlet.c:28-38).
 // ---------------------------------------------------------------------------------------
 template <int KB>
 __global__ void __launch_bounds__(CELLS_THREADS)
@@ -161,7 +191,8 @@ colsums_kernel(const double* __restrict__ tiles, unsigned long long n_rows, unsi
             double f;
             if (mode == 0) f = (x[j] != 0.0) ? fm_log(fabs(x[j])) : 0.0;
             else if (mode == 1) f = x[j];
-            else f = x[j] * x[j];
+            else if (mode == 2) f = x[j] * x[j];
+            else f = (valid && j < K) ? log(x[j]) : 0.0;   // plain ln x (dirichlet); padding rows and columns hold zeros
             acc[j] += valid ? f : 0.0;
         }
     }

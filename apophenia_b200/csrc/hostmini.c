@@ -402,6 +402,14 @@ static apop_model poisson_reg_obj = {.name = "Poisson regression", .vsize = -1, 
 static apop_model exponential_obj = {.name = "Exponential distribution", .vsize = 1, .dsize = 1};
 static apop_model gamma_obj = {.name = "Gamma distribution", .vsize = 2, .dsize = 1};
 static apop_model lognormal_obj = {.name = "Lognormal distribution", .vsize = 2, .dsize = 1};
+static apop_model bernoulli_obj = {.name = "Bernoulli distribution", .vsize = 1, .dsize = 1};
+static apop_model beta_obj = {.name = "Beta distribution", .vsize = 2, .dsize = 1};
+static apop_model zipf_obj = {.name = "Zipf distribution", .vsize = 1, .dsize = 1};
+static apop_model dirichlet_obj = {.name = "Dirichlet distribution", .vsize = -1, .dsize = -1};
+static apop_model t_obj = {.name = "t distribution", .vsize = 3, .dsize = 1};
+static apop_model yule_obj = {.name = "Yule distribution", .vsize = 1, .dsize = 1};
+apop_model *apop_bernoulli = &bernoulli_obj, *apop_beta = &beta_obj, *apop_zipf = &zipf_obj, *apop_dirichlet = &dirichlet_obj,
+           *apop_t_distribution = &t_obj, *apop_yule = &yule_obj;
 apop_model *apop_exponential = &exponential_obj, *apop_gamma = &gamma_obj, *apop_lognormal = &lognormal_obj;
 apop_model *apop_probit = &probit_obj, *apop_logit = &logit_obj, *apop_poisson = &poisson_obj,
            *apop_normal = &normal_obj, *apop_ols = &ols_obj, *apop_poisson_regression = &poisson_reg_obj;

@@ -34,6 +34,8 @@ struct Resident {
     double pois[CELLS_NOUT];
     bool have_gamma = false;   // sum x, sum ln x over non-zero cells, zero-cell count (exponential / gamma)
     double gam[CELLS_NOUT];
+    // parameter-independent cell / column sums of the other iid families, keyed by kernel mode
+    std::unordered_map<int, std::vector<double>> consts;
     // last evaluation (f then df at the same beta costs one pass)
     bool memo_valid = false;
     int memo_fam = -1;

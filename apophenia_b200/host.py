@@ -127,7 +127,9 @@ def metropolis(data_ptr, model_ptr, periods=6000, burnin=0.05, target_accept_rat
 
 _MODEL_SYMS = {abi.PROBIT: "apop_probit", abi.LOGIT: "apop_logit", abi.POISSON: "apop_poisson",
                abi.NORMAL: "apop_normal", abi.OLS: "apop_ols", abi.POISSON_REG: "apop_poisson_regression",
-               abi.EXPONENTIAL: "apop_exponential", abi.GAMMA: "apop_gamma", abi.LOGNORMAL: "apop_lognormal"}
+               abi.EXPONENTIAL: "apop_exponential", abi.GAMMA: "apop_gamma", abi.LOGNORMAL: "apop_lognormal",
+               abi.BERNOULLI: "apop_bernoulli", abi.BETA: "apop_beta", abi.ZIPF: "apop_zipf",
+               abi.DIRICHLET: "apop_dirichlet", abi.TDIST: "apop_t_distribution", abi.YULE: "apop_yule"}
 
 
 def model_object(family):

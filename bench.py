@@ -307,11 +307,44 @@ def run_e2e(ab, args, fam, beta_true, world, rank, barrier, dist, torch):
         dt, pin_s = float(t[0]), float(t[1])
     assert np.isfinite(ll) and np.all(np.isfinite(g))
     ab.unpin(d)
+    # the whole job as a user runs it: host apop_data -> pin -> MLE (BFGS) -> estimates, every byte of
+    # X and y crossing PCIe inside the timed region
+    fit = None
+    if fam == 0 and not args.no_fit:
+        fit = run_fit_from_host(ab, d, k, barrier)
     return {"value": n * world * steps / dt, "unit": UNIT, "h2d_bytes_per_step": beta_true.size * 8 + 32,
             "d2h_bytes_per_step": (3 + beta_true.size) * 8, "rows_per_gpu": n, "ms_per_step": 1e3 * dt / steps,
             "api": "apop_b200_<family>_ll + apop_b200_<family>_score on a pinned host apop_data",
-            "cold": {"pin_seconds": pin_s, "h2d_bytes": n * (k + 1) * 8,
-                     "first_pass_rows_per_s": n * world / (pin_s + dt / steps)}}
+            "resident": "X and y stay in HBM between optimizer iterations (BASELINE.json north_star); per step only "
+                        "beta goes down and [LL|score] comes back",
+            "cold": {"pin_seconds": pin_s, "h2d_bytes": n * (k + 1) * 8, "pin_GBps": n * (k + 1) * 8e-9 / pin_s,
+                     "first_pass_rows_per_s": n * world / (pin_s + dt / steps)},
+            "fit_from_host": fit}
+
+
+def run_fit_from_host(ab, d, k, barrier):
+    """pin + apop_maximum_likelihood (BFGS) on a host apop_data, timed as one job"""
+    from apophenia_b200 import abi, host
+    h, lib = host.lib(), abi.load_library()
+    barrier()
+    t0 = time.perf_counter()
+    ab.pin(d)
+    t_pin = time.perf_counter() - t0
+    start = ab.probit_start(d, k)
+    m = h.apop_model_copy(host.model_object(abi.PROBIT))
+    abi.check(lib.apop_b200_register(m, abi.PROBIT), "apop_b200_register")
+    m.contents.parameters = h.apop_data_alloc(k, 1, 0)
+    m.contents.data = d.ptr
+    keep = []
+    host.mle_settings(m, method="BFGS cg", tolerance=1e-9, relative_tolerance=True, max_iterations=200,
+                      starting_pt=start, keep=keep)
+    h.apop_maximum_likelihood(d.ptr, m)
+    barrier()
+    dt = time.perf_counter() - t0
+    rep = h.apop_mle_last_report()
+    ab.unpin(d)
+    return {"seconds_total": dt, "seconds_pin": t_pin, "status": rep.status, "passes": rep.f_evals,
+            "iterations": rep.iterations}
 
 
 def run_time_to_fit(ab, data, args, beta_true, barrier):

@@ -105,7 +105,13 @@ typedef enum {
     APOP_B200_EXPONENTIAL = 6,  /* iid Exponential(mu)      model/apop_exponential.c:33-52 */
     APOP_B200_GAMMA = 7,        /* iid Gamma(a, b)          model/apop_gamma.c:31-62 */
     APOP_B200_LOGNORMAL = 8,    /* iid Lognormal(mu, sigma) model/apop_normal.c:166-237 */
-    APOP_B200_MODEL_COUNT = 9
+    APOP_B200_BERNOULLI = 9,    /* iid Bernoulli(p)         model/apop_bernoulli.c:13-23 */
+    APOP_B200_BETA = 10,        /* iid Beta(alpha, beta)    model/apop_beta.c:47-75 */
+    APOP_B200_ZIPF = 11,        /* iid Zipf(a)              model/apop_zipf.c:31-40 */
+    APOP_B200_DIRICHLET = 12,   /* rows ~ Dirichlet(alpha)  model/apop_dirichlet.c:13-38 */
+    APOP_B200_T = 13,           /* iid Student t(mu, sigma, df)  model/apop_t.c:25-38 */
+    APOP_B200_YULE = 14,        /* iid Yule(a)              model/apop_yule.c:30-60 */
+    APOP_B200_MODEL_COUNT = 15
 } apop_b200_family;
 
 /* ------------------------------------------------------------------ *
@@ -196,6 +202,16 @@ long double apop_b200_gamma_ll(apop_data *d, apop_model *m);            /* repla
 void apop_b200_gamma_score(apop_data *d, gsl_vector *g, apop_model *m);        /* :56 */
 long double apop_b200_lognormal_ll(apop_data *d, apop_model *m);        /* replaces lognormal_log_likelihood, model/apop_normal.c:170 */
 void apop_b200_lognormal_score(apop_data *d, gsl_vector *g, apop_model *m);    /* :228 */
+long double apop_b200_bernoulli_ll(apop_data *d, apop_model *m);        /* replaces bernoulli_log_likelihood, model/apop_bernoulli.c:18 */
+void apop_b200_bernoulli_score(apop_data *d, gsl_vector *g, apop_model *m);    /* new: the reference registers none (numeric gradient) */
+long double apop_b200_beta_ll(apop_data *d, apop_model *m);             /* replaces beta_log_likelihood, model/apop_beta.c:57 */
+void apop_b200_beta_score(apop_data *d, gsl_vector *g, apop_model *m);         /* replaces beta_dlog_likelihood, :67 */
+long double apop_b200_zipf_ll(apop_data *d, apop_model *m);             /* replaces zipf_log_likelihood, model/apop_zipf.c:31 (no score in the reference) */
+long double apop_b200_dirichlet_ll(apop_data *d, apop_model *m);        /* replaces dirichlet_log_likelihood, model/apop_dirichlet.c:19 */
+void apop_b200_dirichlet_score(apop_data *d, gsl_vector *g, apop_model *m);    /* replaces dirichlet_dlog_likelihood, :28 */
+long double apop_b200_t_ll(apop_data *d, apop_model *m);                /* replaces apop_tdist_llike, model/apop_t.c:32 (no score in the reference) */
+long double apop_b200_yule_ll(apop_data *d, apop_model *m);             /* replaces yule_log_likelihood, model/apop_yule.c:40 */
+void apop_b200_yule_score(apop_data *d, gsl_vector *g, apop_model *m);         /* replaces yule_dlog_likelihood, :50 */
 long double apop_b200_poisson_reg_ll(apop_data *d, apop_model *m);  /* new model behind the same API */
 void apop_b200_poisson_reg_score(apop_data *d, gsl_vector *g, apop_model *m);
 

@@ -694,6 +694,186 @@ void oracle_lognormal(const double *v, size_t vsize, const double *M, size_t tda
     }
 }
 
+/* ---- Bernoulli, Beta, Zipf, Dirichlet, Student t, Yule ----
+ * Each follows the reference's own per-cell callback and apop_map_sum order (vector cells, then
+ * matrix cells, each summed serially in long double, the two sums added: apop_mapply.m4.c:485-517).
+ * FAITHFUL keeps the reference's double callbacks; EXACT evaluates every cell in long double. */
+#define CELL(i) ((i) < vsize ? v[i] : M[(((i) - vsize) / m2) * tda + ((i) - vsize) % m2])
+
+/* bernie_ll, model/apop_bernoulli.c:13-23: x ? log(p) : log(1-p).  The closed-form score
+ * n1/p - n0/(1-p) is not in the reference (numeric gradient there). */
+void oracle_bernoulli(const double *v, size_t vsize, const double *M, size_t tda, size_t m1, size_t m2,
+                      double p, int mode, long double *ll_out, long double *g_out) {
+    const size_t n = vsize + m1 * m2;
+    ld sv = 0, sm = 0, n1 = 0;
+    for (size_t i = 0; i < n; i++) {
+        const double x = CELL(i);
+        const ld t = (mode == ORACLE_FAITHFUL) ? (ld)(x ? log(p) : log(1 - p)) : (x ? logl(p) : log1pl(-(ld)p));
+        if (i < vsize) sv += t; else sm += t;
+        n1 += (x != 0);
+    }
+    *ll_out = (mode == ORACLE_FAITHFUL) ? (ld)(double)(sv + sm) : sv + sm;
+    g_out[0] = n1 / (ld)p - ((ld)n - n1) / (1 - (ld)p);
+}
+
+/* betamap / beta_log_likelihood / beta_dlog_likelihood, model/apop_beta.c:47-75.
+ * gsl_sf_lnbeta(a,b) -> lgamma(a) + lgamma(b) - lgamma(a+b) */
+void oracle_beta(const double *v, size_t vsize, const double *M, size_t tda, size_t m1, size_t m2,
+                 double a, double b, int mode, long double *ll_out, long double *g_out) {
+    const size_t n = vsize + m1 * m2;
+    ld sv = 0, sm = 0, lv = 0, lm = 0, l1v = 0, l1m = 0;
+    for (size_t i = 0; i < n; i++) {
+        const double x = CELL(i);
+        ld t, lx, l1x;
+        if (mode == ORACLE_FAITHFUL) {
+            t = (x < 0 || x > 1) ? 0 : (a - 1) * log(x) + (b - 1) * log(1 - x);
+            lx = log(x); l1x = log(1 - x);
+        } else {
+            t = (x < 0 || x > 1) ? 0 : ((ld)a - 1) * logl(x) + ((ld)b - 1) * log1pl(-(ld)x);
+            lx = logl(x); l1x = log1pl(-(ld)x);
+        }
+        if (i < vsize) { sv += t; lv += lx; l1v += l1x; } else { sm += t; lm += lx; l1m += l1x; }
+    }
+    if (mode == ORACLE_FAITHFUL) {
+        const double lnbeta = lgamma(a) + lgamma(b) - lgamma(a + b);
+        *ll_out = (double)(sv + sm) - lnbeta * (double)n;
+        g_out[0] = (double)(lv + lm) + ((double)digamma_l(a + b) - (double)digamma_l(a)) * (double)n;
+        g_out[1] = (double)(l1v + l1m) + ((double)digamma_l(a + b) - (double)digamma_l(b)) * (double)n;
+    } else {
+        const ld lnbeta = lgammal(a) + lgammal(b) - lgammal((ld)a + b);
+        *ll_out = (sv + sm) - lnbeta * (ld)n;
+        g_out[0] = (lv + lm) + (digamma_l((ld)a + b) - digamma_l(a)) * (ld)n;
+        g_out[1] = (l1v + l1m) + (digamma_l((ld)a + b) - digamma_l(b)) * (ld)n;
+    }
+}
+
+/* gsl_sf_zeta stand-in for s > 1: direct sum to N, integral tail and five Euler-Maclaurin terms */
+static ld zeta_l(ld s) {
+    const int N = 40;
+    ld sum = 0;
+    for (int k = N - 1; k >= 1; k--) sum += powl(k, -s);
+    const ld n = N;
+    sum += powl(n, 1 - s) / (s - 1) + 0.5L * powl(n, -s);
+    const ld b[5] = {1.0L / 6, -1.0L / 30, 1.0L / 42, -1.0L / 30, 5.0L / 66};
+    ld rising = s, fact = 2, npow = powl(n, -s - 1);
+    for (int j = 1; j <= 5; j++) {
+        sum += b[j - 1] / fact * rising * npow;
+        rising *= (s + 2 * j - 1) * (s + 2 * j);
+        fact *= (2 * j + 1) * (2 * j + 2);
+        npow /= n * n;
+    }
+    return sum;
+}
+double oracle_zeta(double s) { return (double)zeta_l(s); }
+
+/* zipf_log_likelihood, model/apop_zipf.c:31-40: like = -map_sum(log) * bb; like -= log(zeta(bb)) * tsize */
+void oracle_zipf(const double *v, size_t vsize, const double *M, size_t tda, size_t m1, size_t m2,
+                 double bb, int mode, long double *ll_out, long double *g_out) {
+    const size_t n = vsize + m1 * m2;
+    ld sv = 0, sm = 0;
+    for (size_t i = 0; i < n; i++) {
+        const double x = CELL(i);
+        const ld t = (mode == ORACLE_FAITHFUL) ? (ld)log(x) : logl(x);
+        if (i < vsize) sv += t; else sm += t;
+    }
+    if (mode == ORACLE_FAITHFUL) {
+        double like = -(double)(sv + sm) * bb;
+        like -= log((double)zeta_l(bb)) * (double)n;
+        *ll_out = like;
+    } else
+        *ll_out = -(sv + sm) * (ld)bb - logl(zeta_l(bb)) * (ld)n;
+    g_out[0] = NAN;   /* no score in the reference */
+}
+
+/* dirichletlnmap / dirichlet_log_likelihood / dirichlet_dlog_likelihood, model/apop_dirichlet.c:13-38;
+ * gsl_ran_dirichlet_lnpdf(K, alpha, theta) = sum (alpha_i - 1) ln theta_i + lnGamma(sum alpha) - sum lnGamma(alpha_i).
+ * Matrix rows only (part = 'r'); g has m2 entries. */
+void oracle_dirichlet(const double *M, size_t tda, size_t m1, size_t m2, const double *alpha, int mode,
+                      long double *ll_out, long double *g_out) {
+    ld total = 0, asum = 0;
+    for (size_t j = 0; j < m2; j++) asum += alpha[j];
+    for (size_t i = 0; i < m1; i++) {
+        if (mode == ORACLE_FAITHFUL) {
+            double lp = 0, sa = 0;
+            for (size_t j = 0; j < m2; j++) lp += (alpha[j] - 1) * log(M[i * tda + j]);
+            for (size_t j = 0; j < m2; j++) sa += alpha[j];
+            lp += lgamma(sa);
+            for (size_t j = 0; j < m2; j++) lp -= lgamma(alpha[j]);
+            total += lp;
+        } else {
+            ld lp = 0;
+            for (size_t j = 0; j < m2; j++) lp += ((ld)alpha[j] - 1) * logl(M[i * tda + j]);
+            lp += lgammal(asum);
+            for (size_t j = 0; j < m2; j++) lp -= lgammal(alpha[j]);
+            total += lp;
+        }
+    }
+    *ll_out = total;
+    for (size_t j = 0; j < m2; j++) {
+        ld s = 0;
+        for (size_t i = 0; i < m1; i++) s += (mode == ORACLE_FAITHFUL) ? (ld)log(M[i * tda + j]) : logl(M[i * tda + j]);
+        g_out[j] = (mode == ORACLE_FAITHFUL)
+                       ? (ld)((double)s + (double)m1 * (double)digamma_l(asum) - (double)m1 * (double)digamma_l(alpha[j]))
+                       : s + (ld)m1 * digamma_l(asum) - (ld)m1 * digamma_l(alpha[j]);
+    }
+}
+
+/* one_t / apop_tdist_llike, model/apop_t.c:25-38: sum log(gsl_ran_tdist_pdf((x-mu)/sigma, df)) - tsize log(sigma);
+ * gsl_ran_tdist_pdf(x, nu) = exp(lnGamma((nu+1)/2) - lnGamma(nu/2)) / sqrt(pi nu) * pow(1 + x^2/nu, -(nu+1)/2) */
+void oracle_tdist(const double *v, size_t vsize, const double *M, size_t tda, size_t m1, size_t m2,
+                  double mu, double sigma, double df, int mode, long double *ll_out, long double *g_out) {
+    const size_t n = vsize + m1 * m2;
+    ld sv = 0, sm = 0;
+    const double lg1 = lgamma(df / 2), lg2 = lgamma((df + 1) / 2);
+    const ld cst = lgammal(((ld)df + 1) / 2) - lgammal((ld)df / 2) - 0.5L * logl(3.14159265358979323846264338327950288L * df);
+    for (size_t i = 0; i < n; i++) {
+        const double x = CELL(i);
+        ld t;
+        if (mode == ORACLE_FAITHFUL) {
+            const double z = (x - mu) / sigma;
+            t = log((exp(lg2 - lg1) / sqrt(M_PI * df)) * pow((1 + z * z / df), -((df + 1) / 2)));
+        } else {
+            const ld z = ((ld)x - mu) / sigma;
+            t = cst - ((ld)df + 1) / 2 * log1pl(z * z / df);
+        }
+        if (i < vsize) sv += t; else sm += t;
+    }
+    *ll_out = (mode == ORACLE_FAITHFUL) ? (ld)((double)(sv + sm) - (double)n * log(sigma)) : (sv + sm) - (ld)n * logl(sigma);
+    g_out[0] = NAN;   /* no score in the reference */
+}
+
+/* yule apply_me / dapply_me / yule_log_likelihood / yule_dlog_likelihood, model/apop_yule.c:30-60 */
+void oracle_yule(const double *v, size_t vsize, const double *M, size_t tda, size_t m1, size_t m2,
+                 double bb, int mode, long double *ll_out, long double *g_out) {
+    const size_t n = vsize + m1 * m2;
+    ld sv = 0, sm = 0, dv = 0, dm = 0;
+    for (size_t i = 0; i < n; i++) {
+        const double x = CELL(i);
+        ld t, dt;
+        if (mode == ORACLE_FAITHFUL) {
+            const double ln_k = (x >= 1) ? lgamma(x) : 0, ln_bb_k = lgamma(x + bb);
+            t = ln_k - ln_bb_k;
+            dt = -(double)digamma_l(x + bb);
+        } else {
+            t = ((x >= 1) ? lgammal(x) : 0) - lgammal((ld)x + bb);
+            dt = -digamma_l((ld)x + bb);
+        }
+        if (i < vsize) { sv += t; dv += dt; } else { sm += t; dm += dt; }
+    }
+    if (mode == ORACLE_FAITHFUL) {
+        const ld ln_bb = lgamma(bb), ln_bb_less_1 = log(bb - 1);
+        const double likelihood = (double)(sv + sm);
+        *ll_out = likelihood + (ln_bb_less_1 + ln_bb) * (ld)n;
+        double d_bb = (double)(dv + dm);
+        d_bb += (double)((1 / ((ld)bb - 1) + (ld)(double)digamma_l(bb)) * (ld)n);
+        g_out[0] = d_bb;
+    } else {
+        *ll_out = (sv + sm) + (logl((ld)bb - 1) + lgammal(bb)) * (ld)n;
+        g_out[0] = (dv + dm) + (1 / ((ld)bb - 1) + digamma_l(bb)) * (ld)n;
+    }
+}
+#undef CELL
+
 /* ---- structure-faithful timed path ------------ */
 static double now_s(void) {
     struct timespec t;

@@ -101,6 +101,19 @@ void oracle_map_sum(const double *v, size_t vsize, const double *M, size_t tda, 
  * (model/apop_exponential.c:33-52), gamma (model/apop_gamma.c:31-62; gsl_sf_psi -> recurrence +
  * asymptotic series), lognormal (model/apop_normal.c:166-237).  g_out: 1, 2, 2 entries. */
 double oracle_digamma(double x);
+void oracle_bernoulli(const double *v, size_t vsize, const double *M, size_t tda, size_t m1, size_t m2,
+                      double p, int mode, long double *ll_out, long double *g_out);
+void oracle_beta(const double *v, size_t vsize, const double *M, size_t tda, size_t m1, size_t m2,
+                 double a, double b, int mode, long double *ll_out, long double *g_out);
+void oracle_zipf(const double *v, size_t vsize, const double *M, size_t tda, size_t m1, size_t m2,
+                 double bb, int mode, long double *ll_out, long double *g_out);
+void oracle_dirichlet(const double *M, size_t tda, size_t m1, size_t m2, const double *alpha, int mode,
+                      long double *ll_out, long double *g_out);
+void oracle_tdist(const double *v, size_t vsize, const double *M, size_t tda, size_t m1, size_t m2,
+                  double mu, double sigma, double df, int mode, long double *ll_out, long double *g_out);
+void oracle_yule(const double *v, size_t vsize, const double *M, size_t tda, size_t m1, size_t m2,
+                 double bb, int mode, long double *ll_out, long double *g_out);
+double oracle_zeta(double s);
 void oracle_exponential(const double *v, size_t vsize, const double *M, size_t tda, size_t m1, size_t m2,
                         double mu, int mode, long double *ll_out, long double *g_out);
 void oracle_gamma(const double *v, size_t vsize, const double *M, size_t tda, size_t m1, size_t m2,

@@ -184,6 +184,40 @@ def lognormal(v, M, mu, sd, mode=EXACT):
     return _iid("oracle_lognormal", v, M, [mu, sd], 2, mode)
 
 
+def bernoulli(v, M, p, mode=EXACT):
+    """(LL, [closed-form score]) of the iid Bernoulli model"""
+    return _iid("oracle_bernoulli", v, M, [p], 1, mode)
+
+
+def beta(v, M, a, b, mode=EXACT):
+    return _iid("oracle_beta", v, M, [a, b], 2, mode)
+
+
+def zipf(v, M, bb, mode=EXACT):
+    return _iid("oracle_zipf", v, M, [bb], 1, mode)
+
+
+def tdist(v, M, mu, sigma, df, mode=EXACT):
+    return _iid("oracle_tdist", v, M, [mu, sigma, df], 1, mode)
+
+
+def yule(v, M, bb, mode=EXACT):
+    return _iid("oracle_yule", v, M, [bb], 1, mode)
+
+
+def dirichlet(M, alpha, mode=EXACT):
+    keep, vp, vs, Mp, tda, m1, m2 = _vm(None, M)
+    a = np.ascontiguousarray(alpha, dtype=np.float64)
+    ll, lp = _ld(1); g, gp = _ld(a.size)
+    lib().oracle_dirichlet(Mp, tda, m1, m2, a.ctypes.data_as(C.POINTER(C.c_double)), C.c_int(mode), lp, gp)
+    return ll[0], g
+
+
+def zeta(s):
+    lib().oracle_zeta.restype = C.c_double
+    return lib().oracle_zeta(C.c_double(s))
+
+
 def digamma(x):
     lib().oracle_digamma.restype = C.c_double
     return lib().oracle_digamma(C.c_double(x))

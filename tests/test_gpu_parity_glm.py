@@ -458,3 +458,60 @@ def test_exponential_gamma_lognormal(b200, oracle):
     _check_ll(ab.log_likelihood(ab.GAMMA, d, m), want)
     assert ab.score(ab.GAMMA, d, m)[0] == -np.inf
     ab.unpin(d)
+
+
+@pytest.mark.gpu
+def test_bernoulli_beta_zipf_dirichlet_t_yule(b200, oracle):
+    """the remaining iid models of SURVEY 8(f) rank 3 through the reference-signature entries: LL (and
+    score where the reference has one, plus the new Bernoulli score) at fixed parameters against the oracle"""
+    ab = b200
+    rng = np.random.default_rng(12)
+
+    def check(fam, mat, vec, params, ofn, has_score=True, one_pass=True, launches_per_call=0):
+        d = ab.pin(ab.Data(matrix=mat, vector=vec))
+        launches = ab.launch_count()
+        for prm in params:
+            m = ab.vector_model(prm, d)
+            want, gw = ofn(vec, mat, *prm)
+            _check_ll(ab.log_likelihood(fam, d, m), want)
+            if has_score:
+                g = ab.score(fam, d, m)
+                gwf = gw.astype(float)
+                assert np.all(np.abs(g - gwf) <= 1e-11 * np.maximum(np.abs(gwf), mat.size)), (g, gwf)
+        if one_pass:
+            assert ab.launch_count() == launches + 1           # parameter-independent sums: one pass per residency
+        else:
+            assert ab.launch_count() == launches + len(params)  # LL and score at one parameter share a pass
+        ab.unpin(d)
+
+    M = rng.beta(2.0, 3.0, (20011, 5)); v = rng.beta(2.0, 3.0, 20011)
+    check(ab.BETA, M, None, [[2.2, 3.1], [1.7, 2.9]], oracle.beta)
+    check(ab.BETA, M, v, [[2.2, 3.1]], oracle.beta)
+    b = (rng.uniform(size=(30001, 3)) < 0.3) * 2.0
+    check(ab.BERNOULLI, b, None, [[0.31], [0.5]], oracle.bernoulli)
+    Z = rng.zipf(2.3, (20000, 4)).astype(float)
+    check(ab.ZIPF, Z, None, [[2.1], [1.5]], oracle.zipf, has_score=False)
+    T = rng.standard_t(5, (20011, 4)) * 2 + 1
+    check(ab.TDIST, T, None, [[0.9, 2.1, 5.5], [1.0, 2.0, 4.0]], oracle.tdist, has_score=False, one_pass=False)
+    Y = rng.zipf(2.5, (20000, 3)).astype(float)
+    check(ab.YULE, Y, Y[:, 0].copy(), [[2.4], [3.3]], oracle.yule, one_pass=False)
+    # Dirichlet: rows of the matrix
+    D = rng.dirichlet([1.5, 2.5, 3.0, 0.8], 30011)
+    d = ab.pin(ab.Data(matrix=D))
+    launches = ab.launch_count()
+    for a in ([1.4, 2.6, 3.1, 0.9], [1.0, 1.0, 1.0, 1.0]):
+        m = ab.vector_model(a, d)
+        want, gw = oracle.dirichlet(D, a)
+        _check_ll(ab.log_likelihood(ab.DIRICHLET, d, m), want)
+        g = ab.score(ab.DIRICHLET, d, m)
+        assert np.all(np.abs(g - gw.astype(float)) <= 1e-11 * np.maximum(np.abs(gw.astype(float)), D.shape[0]))
+    assert ab.launch_count() == launches + 1
+    ab.unpin(d)
+    # beta: a cell outside [0,1] drops out of the LL but poisons the unguarded score sums, as in the reference
+    Mo = M.copy(); Mo[5, 1] = 1.5
+    d = ab.pin(ab.Data(matrix=Mo))
+    m = ab.vector_model([2.2, 3.1], d)
+    want, gw = oracle.beta(None, Mo, 2.2, 3.1)
+    _check_ll(ab.log_likelihood(ab.BETA, d, m), want)
+    assert np.isnan(ab.score(ab.BETA, d, m)[1])
+    ab.unpin(d)
