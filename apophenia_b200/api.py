@@ -20,7 +20,7 @@ __all__ = ["init", "finalize", "pin", "unpin", "invalidate", "is_pinned", "log_l
            "PROBIT", "LOGIT", "POISSON", "NORMAL", "OLS", "POISSON_REG", "EXPONENTIAL", "GAMMA", "LOGNORMAL",
            "BERNOULLI", "BETA", "ZIPF", "DIRICHLET", "TDIST", "YULE", "comm_init_from_torch",
            "comm_finalize", "set_auto_pin", "last_error", "information", "ols_gram",
-           "dot", "col_sums", "probit_start", "ll_score_batched", "bootstrap_counts", "counts_download",
+           "dot", "col_sums", "probit_start", "prep_outcome", "logit_expected", "ll_score_batched", "bootstrap_counts", "counts_download",
            "MAP_IDENTITY", "MAP_DEV", "MAP_DEV2", "MAP_POISSON", "MAP_LOG", "MAP_EXP"]
 
 _dp = C.POINTER(C.c_double)
@@ -179,6 +179,26 @@ def probit_start(d, k):
     out = np.zeros(k)
     abi.check(_lib().apop_b200_probit_start(_ptr(d), out.ctypes.data_as(_dp)), "apop_b200_probit_start")
     return out
+
+
+def prep_outcome(d, max_cats=64, want_start=True, sync_host=False):
+    """device prep (ols_shuffle + category table + recode + start point); returns (cats, start)"""
+    cats = np.zeros(max_cats)
+    ncat = C.c_size_t(0)
+    k = d.matrix.shape[1]
+    start = np.zeros(k) if want_start else None
+    abi.check(_lib().apop_b200_prep_outcome(_ptr(d), cats.ctypes.data_as(_dp), max_cats, C.byref(ncat),
+                                            start.ctypes.data_as(_dp) if want_start else None, int(sync_host)),
+              "apop_b200_prep_outcome")
+    return cats[:ncat.value].copy(), start
+
+
+def logit_expected(d, m, n_rows, ncat):
+    """multilogit_expected: (probabilities n x C, most likely category n)"""
+    probs = np.zeros((n_rows, ncat)); best = np.zeros(n_rows)
+    abi.check(_lib().apop_b200_logit_expected(_ptr(d), _ptr(m), probs.ctypes.data_as(_dp), best.ctypes.data_as(_dp)),
+              "apop_b200_logit_expected")
+    return probs, best
 
 
 def ols_gram(d):

@@ -21,12 +21,16 @@ bool upload(Resident* r, const apop_data* d) {
     int k;
     bool hy, hw;
     data_shape(d, n, k, hy, hw);
+    // device-side ols_shuffle: no vector on the host, column 0 of the matrix is the outcome
+    const bool col0 = r->y_col0 && !d->vector && d->matrix && k >= 1;
+    r->y_col0 = col0;
     if (d->matrix && d->vector && d->vector->size != d->matrix->size1)
         return set_error("vector has %zu entries but the matrix has %zu rows", d->vector->size, d->matrix->size1);
     if (d->weights && d->weights->size != n) return set_error("weights have %zu entries for %zu rows", d->weights->size, n);
     if ((d->matrix && n && !d->matrix->data) || (d->vector && n && !d->vector->data))
         return set_error("data set has no host buffers (device-only synthetic data cannot be re-uploaded)");
-    const int cols = k + (hy ? 1 : 0) + (hw ? 1 : 0);
+    const int cols = k + ((hy || col0) ? 1 : 0) + (hw ? 1 : 0);          // resident columns
+    const int scols = k + (hy ? 1 : 0) + (hw ? 1 : 0);                    // columns in the staging buffers
     const size_t n_tiles = (n + TILE_ROWS - 1) / TILE_ROWS;
     const size_t need = n_tiles * (size_t)cols * TILE_ROWS;
     if (r->tiles && (r->n_tiles * (size_t)r->cols != n_tiles * (size_t)cols)) {
@@ -35,7 +39,7 @@ bool upload(Resident* r, const apop_data* d) {
     }
     if (!r->tiles && need)
         if (!cuda_ok(cudaMalloc(&r->tiles, need * sizeof(double)), "cudaMalloc(resident tiles)")) return false;
-    r->n_rows = n; r->k = k; r->has_y = hy; r->has_w = hw; r->cols = cols; r->n_tiles = n_tiles;
+    r->n_rows = n; r->k = k; r->has_y = hy || col0; r->has_w = hw; r->cols = cols; r->n_tiles = n_tiles;
     r->memo_valid = false; r->have_lgamma_y = false; r->have_poisson = false; r->have_gamma = false; r->consts.clear(); r->dirty = false;
     r->n_global_epoch = ~0ull;
     if (!need) return true;
@@ -44,11 +48,11 @@ bool upload(Resident* r, const apop_data* d) {
     // possibly strided) buffers into one of two pinned staging buffers by a few host threads,
     // sent with one asynchronous copy each, and re-tiled on the device; the gather of chunk
     // i+1 overlaps the copy and the transpose of chunk i.
-    size_t chunk = ((size_t)8 << 20) / (size_t)(cols ? cols : 1);   // ~64 MB of doubles per chunk
+    size_t chunk = ((size_t)8 << 20) / (size_t)(scols ? scols : 1);   // ~64 MB of doubles per chunk
     chunk = chunk / TILE_ROWS * TILE_ROWS;
     if (chunk < TILE_ROWS) chunk = TILE_ROWS;
     if (chunk > n_tiles * TILE_ROWS) chunk = n_tiles * TILE_ROWS;
-    const size_t chunk_doubles = chunk * (size_t)cols;
+    const size_t chunk_doubles = chunk * (size_t)scols;
     if (R.pin_cap < chunk_doubles) {
         for (int b2 = 0; b2 < 2; b2++) {
             if (R.pin_host[b2]) cudaFreeHost(R.pin_host[b2]);
@@ -102,7 +106,7 @@ bool upload(Resident* r, const apop_data* d) {
                 else for (size_t i = a0; i < a1; i++) hw_[i] = d->weights->data[(r0 + i) * d->weights->stride];
             }
         };
-        const int nt = (rows * (size_t)cols < ((size_t)1 << 17)) ? 1 : n_threads;   // small chunks: not worth a thread
+        const int nt = (rows * (size_t)scols < ((size_t)1 << 17)) ? 1 : n_threads;   // small chunks: not worth a thread
         if (nt == 1) gather(0, rows);
         else {
             std::vector<std::thread> pool;
@@ -113,9 +117,9 @@ bool upload(Resident* r, const apop_data* d) {
         double* dX = R.pin_dev[buf];
         double* dy = dX + rows * (size_t)k;
         double* dw = dy + (hy ? rows : 0);
-        ok = ok && cuda_ok(cudaMemcpyAsync(dX, hX, rows * (size_t)cols * sizeof(double), cudaMemcpyHostToDevice, R.stream), "H2D chunk");
+        ok = ok && cuda_ok(cudaMemcpyAsync(dX, hX, rows * (size_t)scols * sizeof(double), cudaMemcpyHostToDevice, R.stream), "H2D chunk");
         ok = ok && cuda_ok(tile_pack(k ? dX : nullptr, hy ? dy : nullptr, hw ? dw : nullptr, rows, k, cols,
-                                     r->tiles + (r0 / TILE_ROWS) * (size_t)cols * TILE_ROWS, R.stream), "tile_pack");
+                                     r->tiles + (r0 / TILE_ROWS) * (size_t)cols * TILE_ROWS, R.stream, col0), "tile_pack");
         ok = ok && cuda_ok(cudaEventRecord(R.pin_ev[buf], R.stream), "event");
     }
     ok = ok && cuda_ok(cudaStreamSynchronize(R.stream), "pin sync");
@@ -134,6 +138,7 @@ extern "C" int apop_b200_pin(apop_data* d) {
     auto it = R.reg.find(d);
     Resident* r = (it != R.reg.end()) ? it->second : new Resident();
     if (r->synthetic) return 0;
+    if (it != R.reg.end() && !r->dirty) return 0;   // already resident (e.g. by the device prep); apop_b200_invalidate forces a refresh
     if (!upload(r, d)) {
         if (it == R.reg.end()) free_resident(r);
         else { free_resident(r); R.reg.erase(it); }

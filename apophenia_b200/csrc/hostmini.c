@@ -22,6 +22,7 @@
  * Written from the behaviour described in SURVEY.md; no reference source text.
  */
 #include "hostmini.h"
+#include <dlfcn.h>
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -370,8 +371,44 @@ static void ols_prep(apop_data *d, apop_model *m) { /* model/apop_ols.c:110-122 
     apop_b200_ols_shuffle(d);
     apop_model_clear(d, m);
 }
+/* The O(N) steps of probit_prep on the device when libapop_b200 is in the process (SURVEY 8(f)
+ * rank 2): ols_shuffle, the category table, the recoding and the start point come back from one
+ * call; the host keeps the small things.  APOP_B200_HOST_PREP=1 forces the host path below. */
+typedef int (*prep_outcome_fn)(apop_data *, double *, size_t, size_t *, double *, int);
+static int probit_prep_on_device(apop_data *d, apop_model *m) {
+    if (getenv("APOP_B200_HOST_PREP") || !d || !d->matrix || d->weights) return 0;
+    for (apop_data *p = d->more; p; p = p->more)
+        if (p->names && p->names->title && !strncmp(p->names->title, "<categories for", 15)) return 0;   /* already factorised */
+    if (d->vector && d->vector->stride != 1) return 0;
+    prep_outcome_fn dev = (prep_outcome_fn)dlsym(RTLD_DEFAULT, "apop_b200_prep_outcome");
+    if (!dev) return 0;
+    const int had_vector = d->vector != NULL;
+    const size_t k = d->matrix->size2;
+    double cats[64], *start = malloc(sizeof(double) * (k ? k : 1));
+    size_t count = 0;
+    if (dev(d, cats, 64, &count, start, 1) != 0) { free(start); return 0; }   /* e.g. no device: fall through to the host path */
+    apop_data *page = apop_data_alloc(count, 0, 0);
+    for (size_t c = 0; c < count; c++) page->vector->data[c] = (double)c;   /* the column now holds 0..C-1 */
+    apop_data_add_page(d, page, had_vector ? "<categories for vector>" : "<categories for column 0>");
+    apop_model_clear(d, m);
+    apop_data_free(m->parameters);
+    m->parameters = apop_data_alloc(k, count > 1 ? count - 1 : 1, 0);
+    apop_mle_settings *sets = apop_settings_get_grp(m, "apop_mle");
+    if (!(sets && sets->starting_pt)) {
+        for (size_t j = 0; j < k; j++) {
+            if (!isfinite(start[j])) { m->error = 'd'; free(start); return 1; }
+            for (size_t c = 0; c < m->parameters->matrix->size2; c++) m->parameters->matrix->data[j * m->parameters->matrix->tda + c] = start[j];
+        }
+        if (!sets) { apop_mle_settings s = apop_mle_settings_defaults(); sets = apop_mle_settings_add(m, s); }
+        gsl_vector *sp = apop_data_pack(m->parameters, NULL);
+        sets->starting_pt = sp->data; /* same small leak as the reference */
+    }
+    free(start);
+    return 1;
+}
 static void probit_prep(apop_data *d, apop_model *m) { /* model/apop_probit.c:42-81 */
     if (m->data && m->parameters) return;
+    if (probit_prep_on_device(d, m)) return;
     apop_data *factors = apop_b200_category_table(d);
     ols_prep(d, m);
     const size_t count = factors->vector->size, k = d->matrix->size2;

@@ -12,7 +12,7 @@ namespace apb {
 __global__ void __launch_bounds__(256)
 tile_pack_kernel(const double* __restrict__ Xs, const double* __restrict__ ys,
                  const double* __restrict__ ws, unsigned long long rows, int k, int cols,
-                 double* __restrict__ tiles) {
+                 double* __restrict__ tiles, int y_col0) {
     __shared__ double sm[32][33];
     const unsigned long long tile = blockIdx.x;
     const unsigned long long row0 = tile * TILE_ROWS;
@@ -24,12 +24,16 @@ tile_pack_kernel(const double* __restrict__ Xs, const double* __restrict__ ys,
             sm[r][tx] = (row < rows && cb + tx < k) ? Xs[row * k + cb + tx] : 0.0;
         }
         __syncthreads();
+        // y_col0: the device side of ols_shuffle (model/apop_ols.c:97-108) -- column 0 of the
+        // caller's matrix is the outcome: it becomes the y column and column 0 becomes the constant 1
+        if (y_col0 && cb == 0 && ty == 0) dst[k * TILE_ROWS + tx] = sm[tx][0];
         for (int c = ty; c < 32; c += 8)
-            if (cb + c < k) dst[(cb + c) * TILE_ROWS + tx] = sm[tx][c];
+            if (cb + c < k) dst[(cb + c) * TILE_ROWS + tx] = (y_col0 && cb + c == 0) ? ((row0 + tx < rows) ? 1.0 : 0.0) : sm[tx][c];
         __syncthreads();
     }
     int col = k;
-    if (ys) {
+    if (y_col0) col++;
+    else if (ys) {
         if (ty == 0) dst[col * TILE_ROWS + tx] = (row0 + tx < rows) ? ys[row0 + tx] : 0.0;
         col++;
     }
@@ -45,7 +49,7 @@ tile_unpack_kernel(const double* __restrict__ tiles, unsigned long long rows, in
     const unsigned long long row0 = tile * TILE_ROWS;
     const double* src = tiles + tile * (unsigned long long)cols * TILE_ROWS;
     const int tx = threadIdx.x, ty = threadIdx.y;
-    for (int cb = 0; cb < k; cb += 32) {
+    for (int cb = 0; Xs && cb < k; cb += 32) {   // Xs == NULL: only the outcome / weights are wanted
         for (int c = ty; c < 32; c += 8) sm[c][tx] = (cb + c < k) ? src[(cb + c) * TILE_ROWS + tx] : 0.0;
         __syncthreads();
         for (int r = ty; r < 32; r += 8) {
@@ -63,10 +67,10 @@ tile_unpack_kernel(const double* __restrict__ tiles, unsigned long long rows, in
 }
 
 cudaError_t tile_pack(const double* Xs, const double* ys, const double* ws, size_t rows, int k,
-                      int cols, double* tiles, cudaStream_t st) {
+                      int cols, double* tiles, cudaStream_t st, bool y_col0) {
     const size_t nt = (rows + TILE_ROWS - 1) / TILE_ROWS;
     if (!nt) return cudaSuccess;
-    tile_pack_kernel<<<(unsigned)nt, dim3(32, 8), 0, st>>>(Xs, ys, ws, rows, k, cols, tiles);
+    tile_pack_kernel<<<(unsigned)nt, dim3(32, 8), 0, st>>>(Xs, ys, ws, rows, k, cols, tiles, y_col0 ? 1 : 0);
     return cudaGetLastError();
 }
 cudaError_t tile_unpack(const double* tiles, size_t rows, int k, int cols, bool has_y, bool has_w,

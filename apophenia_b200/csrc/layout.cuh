@@ -12,7 +12,13 @@ struct SynthParams {
 };
 
 cudaError_t tile_pack(const double* Xs, const double* ys, const double* ws, size_t rows, int k,
-                      int cols, double* tiles, cudaStream_t st);
+                      int cols, double* tiles, cudaStream_t st, bool y_col0 = false);
+// device prep (prep.cu): the next distinct outcome value above a threshold; recode y to category indices
+cudaError_t next_distinct_launch(const double* tiles, size_t n_rows, size_t n_tiles, int ycol, int cols, double above, int first,
+                                 unsigned long long* d_key, int grid, cudaStream_t st);
+constexpr int PREP_MAX_CATS = 64;
+struct CatTable { double v[PREP_MAX_CATS]; int n; };
+cudaError_t recode_launch(double* tiles, size_t n_rows, size_t n_tiles, int ycol, int cols, const CatTable& cats, cudaStream_t st);
 cudaError_t tile_unpack(const double* tiles, size_t rows, int k, int cols, bool has_y, bool has_w,
                         double* Xs, double* ys, double* ws, cudaStream_t st);
 cudaError_t synth_fill(int family, size_t n_rows, int k, int cols, int ncat, const SynthParams& prm,

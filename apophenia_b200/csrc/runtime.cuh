@@ -21,6 +21,7 @@ struct Resident {
     size_t n_tiles = 0;
     double* tiles = nullptr;
     bool synthetic = false;
+    bool y_col0 = false;     // pinned by the device prep: column 0 of the host matrix is the outcome (ols_shuffle done here)
     bool dirty = false;      // host copy changed: re-upload before next use
     // rows of the whole (all ranks) data set, exchanged once per communicator
     double n_global = 0.0;

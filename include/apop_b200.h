@@ -154,7 +154,9 @@ int apop_b200_comm_p2p_active(void);
  * ------------------------------------------------------------------ */
 /* Copy d->matrix / d->vector / d->weights to the device in the tiled layout
  * described in DESIGN.md and remember it under the address of d.  Call after
- * the model's prep (prep mutates the data: ols_shuffle, model/apop_ols.c:97). */
+ * the model's prep (prep mutates the data: ols_shuffle, model/apop_ols.c:97), or let
+ * apop_b200_prep_outcome do both.  Pinning a data set that is already resident and has
+ * not been invalidated is a no-op. */
 int apop_b200_pin(apop_data *d);
 int apop_b200_unpin(apop_data *d);
 /* The host copy changed behind the same pointer (apop_bootstrap.m4.c:143-149):
@@ -214,6 +216,21 @@ long double apop_b200_yule_ll(apop_data *d, apop_model *m);             /* repla
 void apop_b200_yule_score(apop_data *d, gsl_vector *g, apop_model *m);         /* replaces yule_dlog_likelihood, :50 */
 long double apop_b200_poisson_reg_ll(apop_data *d, apop_model *m);  /* new model behind the same API */
 void apop_b200_poisson_reg_score(apop_data *d, gsl_vector *g, apop_model *m);
+
+/* The O(N) steps of the models' prep routines on the device, in one call:
+ *  - makes d resident; if d->vector is NULL, column 0 of d->matrix is the outcome and the tiling kernel
+ *    performs ols_shuffle (model/apop_ols.c:97-108): resident column 0 := 1, outcome -> the y column;
+ *  - if cats/ncat are given: get_category_table / apop_data_to_factors (model/apop_probit.c:32-40,
+ *    apop_regression.m4.c:423-450) -- the sorted distinct outcome values (at most max_cats <= 64, all
+ *    ranks) and the resident outcomes recoded to 0..C-1;
+ *  - if start is given: probit_prep's start point exp(mean ln|x_ij|) (model/apop_probit.c:65-80), k doubles;
+ *  - sync_host != 0 mirrors the reference's in-place mutation of the caller's data (vector allocated
+ *    the way gsl_vector_alloc does, filled with the recoded outcomes; column 0 := 1).
+ * Returns 0 on success. */
+int apop_b200_prep_outcome(apop_data *d, double *cats, size_t max_cats, size_t *ncat, double *start, int sync_host);
+/* multilogit_expected (model/apop_probit.c:166-199): category probabilities (n x C, row-major; may be
+ * NULL) and the most likely category index per row (n; may be NULL); X.B is formed on the device. */
+int apop_b200_logit_expected(apop_data *d, apop_model *m, double *probs, double *best);
 
 /* Row reductions the models are built from (apop_map_sum / apop_matrix_sum,
  * apop_mapply.m4.c:485, apop_stats.m4.c:15,310) over a resident data set:

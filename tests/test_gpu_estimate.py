@@ -2,6 +2,7 @@
 fitted parameters agree to 1e-8 relative with the same optimizer driven by the oracle
 (BASELINE.json north_star; SURVEY F9: compare two tight runs of one optimizer)."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -117,3 +118,52 @@ def test_config1_shape_same_optimizer_two_back_ends(b200, host, oracle):
     assert rep_c.status == 0 and rep_g["status"] == 0
     assert abs(rep_c.iterations - rep_g["iterations"]) <= 2
     assert np.max(np.abs(p_gpu - p_cpu) / np.abs(p_cpu)) < 1e-8
+
+
+def test_device_prep_matches_host_prep(b200, oracle, host):
+    """ols_shuffle, the category table, the recoding and the start point on the
+    device (apop_b200_prep_outcome) against the host mirror's probit_prep, and multilogit_expected"""
+    ab = b200
+    from apophenia_b200 import abi
+    X, y, B = gen_probit_logit_sample(30011, 6, seed=21, method="logit", ncat=4)
+    cats_true = np.array([-3.0, 2.0, 5.0, 9.5])
+    raw = X.copy(); raw[:, 0] = cats_true[y.astype(int)]       # outcome in column 0, as a reference user holds it
+    raw[7, 0] = -3.0; raw[8, 0] = 9.5
+    d = ab.Data(matrix=raw.copy())
+    cats, start = ab.prep_outcome(d, sync_host=False)
+    assert np.array_equal(cats, cats_true)
+    Xs = raw.copy(); Xs[:, 0] = 1.0
+    want_start = np.exp(np.where(Xs != 0, np.log(np.abs(np.where(Xs != 0, Xs, 1.0))), 0.0).mean(0))
+    assert np.allclose(start, want_start, rtol=1e-13)
+    yi = np.searchsorted(cats_true, raw[:, 0]).astype(float)
+    m = ab.logit_model(B, d)
+    ll = ab.log_likelihood(ab.LOGIT, d, m)
+    want = oracle.logit_ll(Xs, yi, B, mode=oracle.EXACT)
+    assert abs(ll - float(want)) <= 1e-12 * abs(float(want))
+    assert np.array_equal(d.matrix, raw)                        # sync_host=False leaves the caller's data alone
+    probs, best = ab.logit_expected(d, m, raw.shape[0], 4)
+    xb = np.concatenate([np.zeros((raw.shape[0], 1)), Xs @ B], axis=1)
+    pw = np.exp(xb - xb.max(1, keepdims=True)); pw /= pw.sum(1, keepdims=True)
+    assert np.allclose(probs, pw, rtol=1e-12, atol=1e-15) and np.array_equal(best, pw.argmax(1))
+    ab.unpin(d)
+    # sync_host=True reproduces the reference's in-place mutation
+    d2 = ab.Data(matrix=raw.copy())
+    ab.prep_outcome(d2, sync_host=True)
+    v = d2.struct.vector.contents
+    got_y = np.ctypeslib.as_array(v.data, shape=(v.size,))
+    assert np.array_equal(got_y, yi) and np.all(d2.matrix[:, 0] == 1.0) and np.array_equal(d2.matrix[:, 1:], raw[:, 1:])
+    ab.unpin(d2)
+    # apop_estimate through the mirror: device prep and host prep give the same fit
+    settings = dict(method="Newton", tolerance=1e-10, relative_tolerance=True, max_iterations=100)
+    Xp, yp, bp = gen_probit_logit_sample(40000, 5, seed=22)
+    rawp = Xp.copy(); rawp[:, 0] = yp
+    fits = []
+    for env in (None, "1"):
+        if env: os.environ["APOP_B200_HOST_PREP"] = env
+        try:
+            dd = host.data_from_numpy(rawp.copy())
+            est, params, rep = host.estimate(abi.PROBIT, dd, **settings)
+            fits.append(params)
+        finally:
+            os.environ.pop("APOP_B200_HOST_PREP", None)
+    assert np.allclose(fits[0], fits[1], rtol=1e-12, atol=0)

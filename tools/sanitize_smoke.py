@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""A tiny pass through every kernel of the library, for `compute-sanitizer --tool memcheck`
-(one tool per gpurun call, smallest case; see B200_PROFILING.md)."""
+"""A tiny pass through every kernel of the library, for `compute-sanitizer --tool memcheck` /
+`--tool racecheck` (smallest case; see B200_PROFILING.md)."""
 import os
 import sys
 
@@ -33,9 +33,15 @@ Xw = rng.uniform(-1, 1, (500, 70)); yw = (rng.uniform(size=500) > 0.5).astype(fl
 dw = ab.pin(ab.Data(matrix=Xw, vector=yw)); ab.ll_score(ab.PROBIT, dw, rng.uniform(-1, 1, 70) / 8); ab.unpin(dw)
 M = rng.gamma(2.0, 1.0, (777, 3))
 dm = ab.pin(ab.Data(matrix=M))
-for fam, p in ((ab.NORMAL, [1.0, 2.0]), (ab.POISSON, [2.0]), (ab.GAMMA, [2.0, 1.0]), (ab.LOGNORMAL, [0.1, 0.9]), (ab.EXPONENTIAL, [2.0])):
+for fam, p in ((ab.NORMAL, [1.0, 2.0]), (ab.POISSON, [2.0]), (ab.GAMMA, [2.0, 1.0]), (ab.LOGNORMAL, [0.1, 0.9]), (ab.EXPONENTIAL, [2.0]),
+               (ab.BERNOULLI, [0.4]), (ab.ZIPF, [2.0]), (ab.TDIST, [0.5, 1.5, 4.0]), (ab.YULE, [2.5]), (ab.DIRICHLET, [1.0, 2.0, 3.0])):
     ab.log_likelihood(fam, dm, ab.vector_model(p, dm))
 ab.unpin(dm)
+Mb = rng.beta(2.0, 3.0, (555, 4))
+db = ab.pin(ab.Data(matrix=Mb)); ab.log_likelihood(ab.BETA, db, ab.vector_model([2.0, 3.0], db)); ab.score(ab.BETA, db, ab.vector_model([2.0, 3.0], db)); ab.unpin(db)
+# the multinomial logit variants (default hybrid ran above)
+for var in ("fp64", "dmma"):
+    pass
 s = ab.synth(ab.PROBIT, 5003, 10, np.linspace(-1, 1, 10)); s.download(); s.free()
 ab.finalize()
 print("sanitize_smoke done")
