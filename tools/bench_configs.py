@@ -192,7 +192,32 @@ def cfg_config1(rows=1_000_000, k=10):
             "speedup_mle": (t_cpu) / rep_g["seconds"]}
 
 
-ALL = {"config1": cfg_config1, "bootstrap_cov": cfg_bootstrap_cov, "metropolis": cfg_metropolis, "logit8": cfg_logit8, "bootstrap": cfg_bootstrap, "chains": cfg_chains, "poisson": cfg_poisson, "newton": cfg_newton}
+def cfg_prep(rows=50_000_000, k=16):
+    """apop_prep of a probit model (ols_shuffle, category table, recoding, start point)
+    on the host (the mirror's restatement of the reference: qsort of the N outcomes) and on the device
+    (apop_b200_prep_outcome, which also makes the data resident: the pin is inside its time)"""
+    from apophenia_b200 import abi, host
+    h, lib = host.lib(), abi.load_library()
+    rng = np.random.default_rng(8)
+    beta = rng.uniform(-1, 1, k)
+    X = rng.uniform(-1, 1, (rows, k))
+    X[:, 0] = (rng.standard_normal(rows) > -(X[:, 1:] @ beta[1:] + beta[0]))
+    out = {"config": f"probit apop_prep, {rows}x{k} host data (outcome in column 0)"}
+    for name, env in (("device", None), ("host", "1")):
+        if env: os.environ["APOP_B200_HOST_PREP"] = env
+        d = host.data_from_numpy(X)
+        m = h.apop_model_copy(host.model_object(abi.PROBIT))
+        abi.check(lib.apop_b200_register(m, abi.PROBIT), "register")
+        t0 = time.perf_counter(); h.apop_prep(d, m); t_prep = time.perf_counter() - t0
+        t0 = time.perf_counter(); abi.check(lib.apop_b200_pin(d), "pin"); t_pin = time.perf_counter() - t0
+        out[name] = {"prep_seconds": t_prep, "pin_seconds_after_prep": t_pin, "start": host.parameters_of(m)[:3].tolist()}
+        lib.apop_b200_unpin(d)
+        os.environ.pop("APOP_B200_HOST_PREP", None)
+    out["speedup_prep_plus_pin"] = (out["host"]["prep_seconds"] + out["host"]["pin_seconds_after_prep"]) / (out["device"]["prep_seconds"] + out["device"]["pin_seconds_after_prep"])
+    return out
+
+
+ALL = {"prep": cfg_prep, "config1": cfg_config1, "bootstrap_cov": cfg_bootstrap_cov, "metropolis": cfg_metropolis, "logit8": cfg_logit8, "bootstrap": cfg_bootstrap, "chains": cfg_chains, "poisson": cfg_poisson, "newton": cfg_newton}
 
 if __name__ == "__main__":
     ab.init(0)
