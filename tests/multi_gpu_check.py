@@ -67,6 +67,32 @@ def main():
     dl = ab.pin(ab.Data(matrix=Xl[lo:hi], vector=yl[lo:hi]))
     ml = ab.logit_model(B, dl)
     checks.append(abs(ab.log_likelihood(ab.LOGIT, dl, ml) - float(o.logit_ll(Xl, yl, B, mode=o.EXACT))) <= 1e-12 * abs(float(o.logit_ll(Xl, yl, B, mode=o.EXACT))))
+    # the cfg2 shape of the hybrid kernel (k = 32, C = 8): score too, identical on every rank
+    Xh, yh, Bh = gen_probit_logit_sample(50001, 32, seed=4, method="logit", ncat=8)
+    lo2, hi2 = shard_range(50001, world, rank)
+    dh = ab.pin(ab.Data(matrix=Xh[lo2:hi2], vector=yh[lo2:hi2]))
+    llh, gh = ab.ll_score(ab.LOGIT, dh, Bh.ravel())
+    geh, sch = o.logit_score(Xh, yh, Bh, mode=o.EXACT)
+    checks.append(abs(llh - float(o.logit_ll(Xh, yh, Bh, mode=o.EXACT))) <= 1e-12 * abs(llh))
+    checks.append(bool(np.all(np.abs(gh - geh.astype(float).ravel()) <= 1e-12 * sch.astype(float).ravel())))
+    checks.append(same_everywhere(np.concatenate([[llh], gh]), world))
+    # an iid family with cached parameter-independent sums, and the device prep: the category
+    # table is the union over ranks (the last category only occurs in the last rank's shard)
+    rngb = np.random.default_rng(5)
+    Mb = rngb.beta(2.0, 3.0, (30000, 3))
+    lo3, hi3 = shard_range(30000, world, rank)
+    db = ab.pin(ab.Data(matrix=Mb[lo3:hi3]))
+    wb, gwb = o.beta(None, Mb, 2.2, 3.1)
+    mb = ab.vector_model([2.2, 3.1], db)
+    checks.append(abs(ab.log_likelihood(ab.BETA, db, mb) - float(wb)) <= 1e-12 * abs(float(wb)))
+    checks.append(bool(np.all(np.abs(ab.score(ab.BETA, db, mb) - gwb.astype(float)) <= 1e-11 * Mb.size)))
+    raw = Xl.copy(); cat_vals = np.array([-1.0, 0.5, 2.0, 7.0, 11.0]); yl2 = yl.copy(); yl2[: n - 10][yl2[: n - 10] == 4] = 3
+    raw[:, 0] = cat_vals[yl2.astype(int)]
+    dr = ab.Data(matrix=raw[lo:hi].copy())
+    cats, start = ab.prep_outcome(dr)
+    checks.append(bool(np.array_equal(cats, cat_vals)))
+    Xs = raw.copy(); Xs[:, 0] = 1.0
+    checks.append(abs(ab.log_likelihood(ab.LOGIT, dr, ab.logit_model(B, dr)) - float(o.logit_ll(Xs, yl2, B, mode=o.EXACT))) <= 1e-12 * abs(float(o.logit_ll(Xs, yl2, B, mode=o.EXACT))))
     Bs = beta[None, :] + 0.01 * np.arange(5)[:, None]
     llb, gb = ab.ll_score_batched(ab.PROBIT, d, Bs)
     checks.append(all(abs(llb[r] - float(o.probit_ll(X, y, Bs[r], o.EXACT))) <= 1e-12 * abs(llb[r]) for r in range(5)))
