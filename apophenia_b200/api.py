@@ -20,7 +20,7 @@ __all__ = ["init", "finalize", "pin", "unpin", "invalidate", "is_pinned", "log_l
            "PROBIT", "LOGIT", "POISSON", "NORMAL", "OLS", "POISSON_REG", "EXPONENTIAL", "GAMMA", "LOGNORMAL",
            "BERNOULLI", "BETA", "ZIPF", "DIRICHLET", "TDIST", "YULE", "comm_init_from_torch",
            "comm_finalize", "set_auto_pin", "last_error", "information", "ols_gram",
-           "dot", "col_sums", "probit_start", "prep_outcome", "logit_expected", "ll_score_batched", "bootstrap_counts", "counts_download",
+           "dot", "col_sums", "probit_start", "prep_outcome", "logit_expected", "text_to_host", "text_to_resident", "ll_score_batched", "bootstrap_counts", "counts_download",
            "MAP_IDENTITY", "MAP_DEV", "MAP_DEV2", "MAP_POISSON", "MAP_LOG", "MAP_EXP"]
 
 _dp = C.POINTER(C.c_double)
@@ -181,11 +181,22 @@ def probit_start(d, k):
     return out
 
 
+def text_to_host(path, has_row_names=False, has_col_names=True, delimiters=None):
+    """apop_text_to_data's matrix for a numeric file, parsed by the library's multi-threaded reader"""
+    out = _dp(); n = C.c_size_t(0); k = C.c_size_t(0)
+    abi.check(_lib().apop_b200_text_to_host(str(path).encode(), int(has_row_names), int(has_col_names),
+                                            delimiters.encode() if delimiters else None, C.byref(out), C.byref(n), C.byref(k)),
+              "apop_b200_text_to_host")
+    a = np.ctypeslib.as_array(out, shape=(n.value, k.value)).copy() if n.value else np.zeros((0, k.value))
+    C.CDLL(None).free(out)
+    return a
+
+
 def prep_outcome(d, max_cats=64, want_start=True, sync_host=False):
     """device prep (ols_shuffle + category table + recode + start point); returns (cats, start)"""
     cats = np.zeros(max_cats)
     ncat = C.c_size_t(0)
-    k = d.matrix.shape[1]
+    k = d.matrix.shape[1] if getattr(d, "matrix", None) is not None else d.k
     start = np.zeros(k) if want_start else None
     abi.check(_lib().apop_b200_prep_outcome(_ptr(d), cats.ctypes.data_as(_dp), max_cats, C.byref(ncat),
                                             start.ctypes.data_as(_dp) if want_start else None, int(sync_host)),
@@ -272,6 +283,23 @@ class SynthData:
 
 def synth(family, n_rows, k, beta_true, ncat=2, seed=8, row_offset=0):
     return SynthData(family, n_rows, k, beta_true, ncat, seed, row_offset)
+
+
+class TextData(SynthData):
+    """A numeric text file ingested straight into the resident layout (apop_b200_text_to_resident)."""
+
+    def __init__(self, path, has_row_names=False, has_col_names=True, delimiters=None, outcome_col0=False):
+        self._p = _lib().apop_b200_text_to_resident(str(path).encode(), int(has_row_names), int(has_col_names),
+                                                    delimiters.encode() if delimiters else None, int(outcome_col0))
+        if not self._p:
+            raise B200Error("apop_b200_text_to_resident failed: " + abi.last_error())
+        m = self._p.contents.matrix.contents
+        self.n_rows, self.k, self.has_y = int(m.size1), int(m.size2), bool(outcome_col0)
+        self.family, self.ncat = None, 0
+
+
+def text_to_resident(path, has_row_names=False, has_col_names=True, delimiters=None, outcome_col0=False):
+    return TextData(path, has_row_names, has_col_names, delimiters, outcome_col0)
 
 
 # ---- multi-GPU plumbing: torch.distributed carries the NCCL id ----------------------

@@ -53,7 +53,10 @@ static int prep_outcome_locked(apop_data* d, double* cats_out, size_t max_cats, 
 extern "C" int apop_b200_prep_outcome(apop_data* d, double* cats_out, size_t max_cats, size_t* ncat, double* start, int sync_host) {
     LOCK;
     const int rc = prep_outcome_locked(d, cats_out, max_cats, ncat, start, sync_host);
-    if (rc != 0 && d) apop_b200_unpin(d);   // never leave a half-prepared resident copy behind
+    if (rc != 0 && d) {                     // never leave a half-prepared resident copy of HOST data behind
+        auto it = rt().reg.find(d);
+        if (it != rt().reg.end() && !it->second->synthetic) apop_b200_unpin(d);
+    }
     return rc;
 }
 static int prep_outcome_locked(apop_data* d, double* cats_out, size_t max_cats, size_t* ncat, double* start, int sync_host) {
@@ -65,15 +68,21 @@ static int prep_outcome_locked(apop_data* d, double* cats_out, size_t max_cats, 
     // ---- residency, with ols_shuffle (model/apop_ols.c:97-108) done by the tiling kernel
     auto it = R.reg.find(d);
     Resident* r = (it != R.reg.end()) ? it->second : new Resident();
-    if (r->synthetic) { set_error("apop_b200_prep_outcome: synthetic data sets are generated already prepared"); return 1; }
-    r->y_col0 = (d->vector == nullptr);
-    if (!upload(r, d)) {
-        free_resident(r);
-        if (it != R.reg.end()) R.reg.erase(it);
-        d->error = 'a';
-        return 1;
+    if (r->synthetic) {
+        // device-only data (apop_b200_text_to_resident with the outcome in column 0, apop_b200_synth):
+        // already tiled and shuffled, and there is no host copy to mirror anything into
+        if (!r->has_y) { set_error("apop_b200_prep_outcome: the device-only data set has no outcome column (ingest it with outcome_col0)"); return 1; }
+        sync_host = 0;
+    } else {
+        r->y_col0 = (d->vector == nullptr);
+        if (!upload(r, d)) {
+            free_resident(r);
+            if (it != R.reg.end()) R.reg.erase(it);
+            d->error = 'a';
+            return 1;
+        }
+        R.reg[d] = r;
     }
-    R.reg[d] = r;
     const bool shuffled = r->y_col0;
     // ---- category table (get_category_table / apop_data_to_factors) and recoding
     std::vector<double> cats;

@@ -232,6 +232,24 @@ int apop_b200_prep_outcome(apop_data *d, double *cats, size_t max_cats, size_t *
  * NULL) and the most likely category index per row (n; may be NULL); X.B is formed on the device. */
 int apop_b200_logit_expected(apop_data *d, apop_model *m, double *probs, double *best);
 
+/* Ingest: a delimited numeric text file straight into the resident layout,
+ * replacing apop_text_to_data (apop_conversions.m4.c:600-690) + apop_b200_pin without the apop_data
+ * detour.  The file is mmap'ed, cut at line boundaries, parsed by the host threads into pinned staging
+ * and tiled on the device group by group.  Rules of the reference's text format
+ * (apop_conversions.m4.c:339-403) that are honoured: delimiter set (NULL = "|,\t"), '#' comments, blank
+ * lines, white space around fields, has_col_names (1/'y': the first non-blank line is skipped),
+ * has_row_names (1/'y': the first field of every row is skipped), an empty field = NaN unless the
+ * delimiter closing it is a space or tab, text fields = 0, strtod number syntax.  Quoted fields,
+ * backslash escapes and fixed-width fields are refused.  outcome_col0 != 0: column 0 is the outcome
+ * (ols_shuffle while tiling).  Returns a device-only header (sizes set, data pointers NULL) that is
+ * resident; free it with apop_b200_synth_free.  NULL on error. */
+apop_data *apop_b200_text_to_resident(const char *path, int has_row_names, int has_col_names,
+                                      const char *delimiters, int outcome_col0);
+/* The same reader into host memory (what apop_text_to_data leaves in ->matrix): *out is a malloc'ed
+ * row-major n x k buffer owned by the caller.  Needs no device. */
+int apop_b200_text_to_host(const char *path, int has_row_names, int has_col_names, const char *delimiters,
+                           double **out, size_t *n_rows, size_t *k);
+
 /* Row reductions the models are built from (apop_map_sum / apop_matrix_sum,
  * apop_mapply.m4.c:485, apop_stats.m4.c:15,310) over a resident data set:
  * sum over every cell of vector+matrix of f(x; param). */

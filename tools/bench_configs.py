@@ -217,7 +217,35 @@ def cfg_prep(rows=50_000_000, k=16):
     return out
 
 
-ALL = {"prep": cfg_prep, "config1": cfg_config1, "bootstrap_cov": cfg_bootstrap_cov, "metropolis": cfg_metropolis, "logit8": cfg_logit8, "bootstrap": cfg_bootstrap, "chains": cfg_chains, "poisson": cfg_poisson, "newton": cfg_newton}
+def cfg_ingest(rows=2_000_000, k=16):
+    """a numeric CSV straight into the resident layout (apop_b200_text_to_resident)
+    against reading it into host memory first (pandas' C parser standing in for apop_text_to_data, which
+    parses one character at a time and reallocs once per row) and pinning the result"""
+    import tempfile
+    import pandas as pd
+    rng = np.random.default_rng(8)
+    X = np.round(rng.uniform(-1, 1, (rows, k)), 6)
+    X[:, 0] = (rng.uniform(size=rows) > 0.5)
+    path = os.path.join(tempfile.mkdtemp(), "ingest.csv")
+    pd.DataFrame(X, columns=[f"c{j}" for j in range(k)]).to_csv(path, index=False, float_format="%.6f")
+    size = os.path.getsize(path)
+    with open(path, "rb") as f:            # warm the page cache for both arms
+        while f.read(1 << 26): pass
+    t0 = time.perf_counter(); d = ab.text_to_resident(path, outcome_col0=True); t_dev = time.perf_counter() - t0
+    Xd, yd = d.download(); d.free()
+    t0 = time.perf_counter(); H = ab.text_to_host(path); t_host_reader = time.perf_counter() - t0
+    t0 = time.perf_counter(); df = pd.read_csv(path).to_numpy(); t_pandas = time.perf_counter() - t0
+    dd = ab.Data(matrix=df)
+    t0 = time.perf_counter(); ab.pin(dd); t_pin = time.perf_counter() - t0
+    ab.unpin(dd)
+    ok = bool(np.array_equal(H, X) and np.array_equal(Xd[:, 1:], X[:, 1:]) and np.array_equal(yd, X[:, 0]) and np.array_equal(df, X))
+    os.remove(path)
+    return {"config": f"text ingest, {rows}x{k} CSV ({size / 1e6:.0f} MB)", "file_to_resident_seconds": t_dev, "text_MBps": size / 1e6 / t_dev,
+            "library_reader_to_host_seconds": t_host_reader, "pandas_read_csv_seconds": t_pandas, "pin_seconds": t_pin,
+            "speedup_vs_pandas_plus_pin": (t_pandas + t_pin) / t_dev, "identical": ok}
+
+
+ALL = {"ingest": cfg_ingest, "prep": cfg_prep, "config1": cfg_config1, "bootstrap_cov": cfg_bootstrap_cov, "metropolis": cfg_metropolis, "logit8": cfg_logit8, "bootstrap": cfg_bootstrap, "chains": cfg_chains, "poisson": cfg_poisson, "newton": cfg_newton}
 
 if __name__ == "__main__":
     ab.init(0)
