@@ -6,10 +6,6 @@
 namespace apb {
 constexpr int LOGIT_THREADS = 128;
 constexpr int LOGIT_MAX_C1 = 7;  // up to 8 outcome categories
-constexpr int LOGIT_CS = 36;      // padded column stride (doubles) of a tile staged in shared memory
-constexpr int LOGIT_TILE_DOUBLES = (MAX_K_REG + 1) * LOGIT_CS;
-constexpr int LOGIT_XS = 34;      // row stride of the 8 x 32 category-major exchange slab
-constexpr int LOGIT_WARP_DOUBLES = 2 * LOGIT_TILE_DOUBLES + 8 * LOGIT_XS;
 struct LogitParams {
     double B[MAX_K_REG * LOGIT_MAX_C1];  // k x (C-1), row-major (parameters->matrix), zero padded to KB rows
     double cats[8];                      // the first C-1 sorted category values (factor page vector)
@@ -29,6 +25,9 @@ int logit_kb(int k);
 // logit_hybrid.cu: the default kernel (lane = row X.B and soft-max, DMMA score, cp.async ring)
 cudaError_t logit_hybrid_launch(int c1, const LogitLaunch& L, const LogitParams& prm);
 int logit_hybrid_blocks_per_sm(int k, int c1);
+// logit_mma.cu: both contractions as DMMA, lane = row soft-max in between
+cudaError_t logit_mma_launch(int c1, const LogitLaunch& L, const LogitParams& prm);
+int logit_mma_blocks_per_sm(int k, int c1);
 cudaError_t logit_launch(int c1, const LogitLaunch& L, const LogitParams& prm);
 int logit_blocks_per_sm(int k, int c1);
 }  // namespace apb
