@@ -151,7 +151,8 @@ def workload_config(args, world):
     return {"workload": f"{fam} fused LL+score pass, {args.rows} rows x {args.k} cols per GPU "
                         f"(target 100M x 32 probit MLE of BASELINE.json north_star)",
             "rows_per_gpu": args.rows, "k": args.k, "global_rows": args.rows * world,
-            "parallelism": f"row-sharded dp{world}, one NCCL allreduce of [LL|score] per pass",
+            "parallelism": f"row-sharded dp{world}; [LL|score] summed over ranks once per pass, inside the reduction "
+                           f"kernel over NVLink peer memory (APOP_B200_ALLREDUCE=nccl: one ncclAllReduce instead)",
             "l2": "inputs (>= 26 GB per pass) far exceed the 126 MB L2; no flush needed"}
 
 

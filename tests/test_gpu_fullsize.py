@@ -1,0 +1,116 @@
+"""BASELINE.json's full sizes, through properties that do not need an oracle pass over the whole
+data set: additivity of LL and score over a row partition (the same rows generated as one resident
+set and as two shards -- different grids, different reduction orders), agreement with the oracle on
+windows of the data (any window of the counter-based synthetic generator can be re-created on its
+own), a vanishing score and a positive-definite information at the fitted parameters, and batched
+replicates against single passes."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _additive(ab, fam, n, k, beta, ncat=2, rtol=1e-12):
+    full = ab.synth(fam, n, k, beta, ncat=ncat, seed=8)
+    ll, g = ab.ll_score(fam, full, beta)
+    full.free()
+    cut = (n // 3) // 32 * 32 + 17                       # an unaligned cut: the second shard starts mid-tile
+    parts = []
+    for lo, hi in ((0, cut), (cut, n)):
+        s = ab.synth(fam, hi - lo, k, beta, ncat=ncat, seed=8, row_offset=lo)
+        parts.append(ab.ll_score(fam, s, beta))
+        s.free()
+    ll2 = parts[0][0] + parts[1][0]
+    g2 = parts[0][1] + parts[1][1]
+    assert abs(ll - ll2) <= rtol * abs(ll), (ll, ll2)
+    # a score component is a sum of O(n) terms of size <= 1 that nearly cancel at beta_true: compare on that scale
+    assert np.max(np.abs(g - g2)) <= rtol * n, np.max(np.abs(g - g2))
+    return ll, g
+
+
+def _window_matches_oracle(ab, oracle, fam, n, k, beta, lo, rows, ncat=2):
+    s = ab.synth(fam, rows, k, beta, ncat=ncat, seed=8, row_offset=lo)
+    X, y = s.download()
+    ll, g = ab.ll_score(fam, s, beta)
+    s.free()
+    if fam == ab.PROBIT:
+        want = oracle.probit_ll(X, y, beta, oracle.EXACT); ge, scale = oracle.probit_score(X, y, beta, oracle.EXACT)
+    elif fam == ab.POISSON_REG:
+        want = oracle.poisson_reg_ll(X, y, beta, oracle.EXACT); ge, scale = oracle.poisson_reg_score(X, y, beta, oracle.EXACT)
+    else:
+        B = beta.reshape(k, -1)
+        want = oracle.logit_ll(X, y, B, mode=oracle.EXACT); ge, scale = oracle.logit_score(X, y, B, mode=oracle.EXACT)
+        ge, scale = ge.ravel(), scale.ravel()
+    assert abs(ll - float(want)) <= 1e-12 * abs(float(want))
+    assert np.all(np.abs(g - ge.astype(float)) <= 1e-12 * scale.astype(float))
+
+
+def test_probit_100Mx32(b200, oracle):
+    """the north-star shape: 26.4 GB resident, additivity, oracle windows, and the fit"""
+    ab = b200
+    n, k = 100_000_000, 32
+    rng = np.random.default_rng(8)
+    beta = rng.uniform(-1, 1, k)
+    ll, g = _additive(ab, ab.PROBIT, n, k, beta)
+    assert np.isfinite(ll) and ll < 0
+    for lo in (0, 49_999_983, n - 40_001):                # head, an unaligned middle, the tail of the data set
+        _window_matches_oracle(ab, oracle, ab.PROBIT, n, k, beta, lo, 40_001)
+    # the MLE on the full data: score ~ 0 on the scale of its terms, information positive definite,
+    # estimates within a few standard errors of the generating parameters
+    from apophenia_b200 import abi, host
+    full = ab.synth(ab.PROBIT, n, k, beta, seed=8)
+    h, lib = host.lib(), abi.load_library()
+    m = h.apop_model_copy(host.model_object(abi.PROBIT))
+    abi.check(lib.apop_b200_register(m, abi.PROBIT), "register")
+    m.contents.parameters = h.apop_data_alloc(k, 1, 0)
+    m.contents.data = full.ptr
+    keep = []
+    host.mle_settings(m, method="Newton", tolerance=1e-10, relative_tolerance=True, max_iterations=50,
+                      starting_pt=ab.probit_start(full, k), keep=keep)
+    h.apop_maximum_likelihood(full.ptr, m)
+    est = host.parameters_of(m)
+    ll_hat, g_hat = ab.ll_score(ab.PROBIT, full, est)
+    H = ab.information(ab.PROBIT, full, est)
+    full.free()
+    assert ll_hat >= ll and np.max(np.abs(g_hat)) <= 1e-9 * abs(ll_hat)
+    se = np.sqrt(np.diag(np.linalg.inv(H)))
+    assert np.all(np.linalg.eigvalsh(H) > 0) and np.all(np.abs(est - beta) < 6 * se)
+
+
+def test_logit8_20Mx32(b200, oracle):
+    """BASELINE config 2: multinomial logit, C = 8"""
+    ab = b200
+    n, k, C = 20_000_000, 32, 8
+    rng = np.random.default_rng(8)
+    B = rng.uniform(-1, 1, k * (C - 1))
+    _additive(ab, ab.LOGIT, n, k, B, ncat=C)
+    for lo in (0, 9_999_991, n - 20_011):
+        _window_matches_oracle(ab, oracle, ab.LOGIT, n, k, B, lo, 20_011, ncat=C)
+
+
+def test_poisson_shard_50Mx16(b200, oracle):
+    """BASELINE config 3: one GPU's shard of the 400M x 16 Poisson regression"""
+    ab = b200
+    n, k = 50_000_000, 16
+    rng = np.random.default_rng(8)
+    beta = rng.uniform(-1, 1, k) / np.sqrt(k)
+    _additive(ab, ab.POISSON_REG, n, k, beta)
+    _window_matches_oracle(ab, oracle, ab.POISSON_REG, n, k, beta, 25_000_007, 50_003)
+
+
+def test_batched_configs_4_and_5(b200, oracle):
+    """BASELINE configs 4 and 5: 1000 bootstrap replicates on 5M x 20 and 256 chains on 50M x 24 --
+    a few replicates of the batched pass against single passes over the same resident data"""
+    ab = b200
+    rng = np.random.default_rng(8)
+    for fam, n, k, m, score in ((ab.PROBIT, 5_000_000, 20, 1000, True), (ab.LOGIT, 50_000_000, 24, 256, False)):
+        beta = rng.uniform(-1, 1, k)
+        s = ab.synth(fam, n, k, beta, seed=8)
+        Bs = beta[None, :] + 0.01 * rng.standard_normal((m, k))
+        llb, gb = ab.ll_score_batched(fam, s, Bs, want_score=score)
+        for r in (0, m // 2, m - 1):
+            ll1, g1 = ab.ll_score(fam, s, Bs[r])
+            assert abs(llb[r] - ll1) <= 1e-12 * abs(ll1)
+            if score:
+                assert np.max(np.abs(gb[r] - g1)) <= 1e-12 * n
+        s.free()
