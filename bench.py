@@ -127,7 +127,7 @@ def run_reference(args):
     X = rng.uniform(-1, 1, (n, k)); X[:, 0] = 1.0
     beta = rng.uniform(-1, 1, k)
     y = (rng.standard_normal(n) > -(X @ beta)).astype(np.float64)
-    threads = o.max_threads()
+    threads = max(o.max_threads(), os.cpu_count() or 1)   # torchrun exports OMP_NUM_THREADS=1: use every host core anyway
     for _ in range(max(args.warmup, 1)):
         cpu_reference_pass(o, X[: n // 8], y[: n // 8], beta, threads)
     t0 = time.perf_counter()
@@ -392,7 +392,7 @@ def run_cpu_baseline(ab, args, fam, beta_true):
     src = ab.synth(fam, n, k, beta_true, seed=8, row_offset=0)
     X, y = src.download()
     src.free()
-    threads = o.max_threads()
+    threads = max(o.max_threads(), os.cpu_count() or 1)
     o.time_probit_ll_score(X[: n // 10], y[: n // 10], beta_true, threads)  # warm-up
     best = None
     t_total = 0.0
