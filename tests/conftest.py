@@ -52,3 +52,18 @@ def gen_probit_logit_sample(n, k, seed=8, method="probit", ncat=2):
         y = (rng.uniform(size=(n, 1)) > np.cumsum(p, axis=1)).sum(1).astype(np.float64)
         y = np.minimum(y, ncat - 1)
     return X, y, beta
+
+
+def amash_design():
+    """The design matrix of eg/logit.c over tests/golden/amash.json, outcome in column 0 as the reference
+    holds it before prep: [vote factor, ideology, log(contribs+10), party dummy].  apop_data_to_factors
+    numbers the sorted distinct texts (Aye = 0, No = 1); apop_data_to_dummies drops the first sorted
+    category (Democrat) and appends one column for Republican."""
+    import json
+    import os
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "amash.json")))
+    rows = g["rows"]
+    votes = sorted({r["vote"] for r in rows}); parties = sorted({r["party"] for r in rows})
+    assert votes == ["Aye", "No"] and parties == ["Democrat", "Republican"]
+    raw = np.array([[votes.index(r["vote"]), r["ideology"], np.log(r["contribs"] + 10), parties.index(r["party"])] for r in rows], dtype=np.float64)
+    return raw

@@ -7,7 +7,9 @@ Carried over (SURVEY.md 8(c) "Golden fixtures"):
   * NIST StRD Pontius and Wampler1 data (tests/pontius.dat, tests/wampler1.dat) with
     the certified values asserted in tests/nist_tests.c:20-47;
   * NIST NumAcc4 (tests/numacc4.dat) with tests/nist_tests.c:49-55's certified mean/variance;
-  * the small exact apop_map_sum / apop_dot cases of tests/test_apop.c:1037-1044, :527-550.
+  * the small exact apop_map_sum / apop_dot cases of tests/test_apop.c:1037-1044, :527-550;
+  * the real-data logit example: tests/amash_vote_analysis.csv (422 House votes on the Amash amendment,
+    public data compiled by govtrack.us) as eg/logit.c:14-18 uses it -- vote ~ ideology + log(contribs+10) + party.
 Only numbers are copied (public NIST data and test constants), no source text.
 """
 import json
@@ -57,7 +59,20 @@ def nist():
     }
 
 
+def amash():
+    rows = []
+    for ln in open(os.path.join(REF, "tests", "amash_vote_analysis.csv")).read().splitlines():
+        f = ln.strip().split(",")
+        if len(f) == 5 and f[0].isdigit():
+            rows.append({"id": int(f[0]), "party": f[1], "ideology": float(f[2]), "vote": f[3], "contribs": float(f[4])})
+    assert len(rows) == 422
+    return {"rows": rows, "source": "tests/amash_vote_analysis.csv; model of eg/logit.c:14-23: select 0, ideology, "
+                                    "log(contribs+10), vote, party; apop_data_to_factors (vote -> column 0); "
+                                    "apop_data_to_dummies(.col=1, .type='t', .append='y') (party); apop_estimate(d, apop_logit)"}
+
+
 if __name__ == "__main__":
     json.dump(fake_logit(), open(os.path.join(HERE, "fake_logit.json"), "w"), indent=1)
     json.dump(nist(), open(os.path.join(HERE, "nist_strd.json"), "w"))
-    print("wrote fake_logit.json, nist_strd.json")
+    json.dump(amash(), open(os.path.join(HERE, "amash.json"), "w"))
+    print("wrote fake_logit.json, nist_strd.json, amash.json")

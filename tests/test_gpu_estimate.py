@@ -167,3 +167,33 @@ def test_device_prep_matches_host_prep(b200, oracle, host):
         finally:
             os.environ.pop("APOP_B200_HOST_PREP", None)
     assert np.allclose(fits[0], fits[1], rtol=1e-12, atol=0)
+
+
+def test_amash_logit_real_data_on_device(b200, oracle, host):
+    """eg/logit.c on the real 422-row data set: the device-driven fit (device prep included) against
+    the oracle-driven fit of the same optimizer, and LL / score / information at the optimum"""
+    from apophenia_b200 import abi
+    from conftest import amash_design
+    ab = b200
+    h = host.lib()
+    raw = amash_design()
+    # (the reference's start point exp(mean ln|x|) saturates every probability on this data -- log
+    # contributions are ~9 -- so the same line-search optimizer runs on both sides)
+    settings = dict(method="BFGS cg", tolerance=1e-10)
+    est, p_dev, rep = host.estimate(abi.LOGIT, host.data_from_numpy(raw.copy()), **settings)
+    assert rep["status"] == 0
+    keep = []
+    m = _install_oracle_model(host, oracle, 1, keep)
+    host.mle_settings(m, method="BFGS cg", tolerance=1e-10, keep=keep)
+    est_o = h.apop_estimate(host.data_from_numpy(raw.copy()), m)
+    p_orc = host.parameters_of(est_o)
+    h.apop_vtable_drop(b"apop_score", m.contents.log_likelihood)
+    assert np.max(np.abs(p_dev - p_orc) / np.abs(p_orc)) < 1e-8
+    y = raw[:, 0].copy(); X = raw.copy(); X[:, 0] = 1.0
+    d = ab.pin(ab.Data(matrix=X, vector=y))
+    ll, g = ab.ll_score(ab.LOGIT, d, p_dev)
+    want = float(oracle.logit_ll(X, y, p_dev.reshape(4, 1), mode=oracle.EXACT))
+    assert abs(ll - want) <= 1e-12 * abs(want) and np.max(np.abs(g)) < 1e-6
+    H = ab.information(ab.LOGIT, d, p_dev)
+    assert np.allclose(H, oracle.information(1, X, y, p_dev).astype(float), rtol=1e-11)
+    ab.unpin(d)

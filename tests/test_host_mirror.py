@@ -140,6 +140,26 @@ def test_fake_logit_through_the_mirror(host, oracle, method):
     h.apop_vtable_drop(b"apop_score", m.contents.log_likelihood)
 
 
+def test_amash_logit_through_the_mirror(host, oracle):
+    """eg/logit.c end to end on the real data: prep turns the outcome column into factor indices and
+    shuffles it out, then apop_maximum_likelihood; compared with scipy on the same likelihood"""
+    from conftest import amash_design
+    from scipy import optimize
+    h = host.lib()
+    raw = amash_design()
+    d = host.data_from_numpy(raw.copy())
+    keep = []
+    m = _install_oracle_model(host, oracle, 1, keep)
+    host.mle_settings(m, method="BFGS cg", tolerance=1e-9, keep=keep)
+    est = h.apop_estimate(d, m)
+    assert h.apop_mle_last_report().status == 0
+    y = raw[:, 0].copy(); X = raw.copy(); X[:, 0] = 1.0
+    f = lambda b: -np.sum(y * (X @ b) - np.logaddexp(0, X @ b))
+    res = optimize.minimize(f, np.zeros(4), method="BFGS", options={"gtol": 1e-9})
+    assert np.allclose(host.parameters_of(est), res.x, atol=2e-6)
+    h.apop_vtable_drop(b"apop_score", m.contents.log_likelihood)
+
+
 def test_probit_recovery_like_reference_test(host, oracle):
     """test_probit_and_logit (tests/test_apop.c:935-959): recover beta within 0.07 (smaller n here)"""
     h = host.lib()
