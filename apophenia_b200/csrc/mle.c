@@ -274,15 +274,27 @@ static int minimize_newton(mle_info *I, const apop_mle_settings *mp, double *x, 
         if (information(fam, I->data, x, n, H)) { status = -1; break; }
         for (size_t i = 0; i < n; i++) p[i] = -g[i];
         double ridge = 0;
+        int solved = 0;
         for (int tries = 0; tries < 8; tries++) { /* observed information may be indefinite far from the optimum */
             double *A = malloc(sizeof(double) * n * n);
             memcpy(A, H, sizeof(double) * n * n);
             for (size_t i = 0; i < n; i++) { A[i * n + i] += ridge; p[i] = -g[i]; }
             const int bad = chol_solve(A, p, n);
             free(A);
-            if (!bad) break;
+            if (!bad) { solved = 1; break; }
             double tr = 0; for (size_t i = 0; i < n; i++) tr += fabs(H[i * n + i]);
             ridge = ridge ? ridge * 10 : 1e-6 * tr / n;
+            if (!(ridge > 0)) break;              /* a vanishing information matrix: every probability saturated */
+        }
+        if (!solved) { /* no usable curvature: a steepest-descent step of the first-step length the gradient
+                        * methods use (GSL: step_size along the normalised gradient), found by the line search */
+            const double xn = nrm(x, n), len = (mp->step_size > 0 ? mp->step_size : 0.05) * (1 + xn) * 20;
+            for (size_t i = 0; i < n; i++) p[i] = gnorm > 0 ? -g[i] * len / gnorm : 0;
+        }
+        { /* a nearly singular information matrix (saturated probabilities) gives an astronomically long
+           * step: cap its length, the line search does the rest */
+            const double pn = nrm(p, n), cap = 10 * (1 + nrm(x, n));
+            if (!(pn <= cap)) for (size_t i = 0; i < n; i++) p[i] = isfinite(pn) && pn > 0 ? p[i] * cap / pn : -g[i] * cap / (gnorm > 0 ? gnorm : 1);
         }
         if (line_search(I, n, x, &f, g, p, 1.0, 0.9)) break;
         if (I->nan_seen) { status = -1; break; }

@@ -182,6 +182,10 @@ def test_amash_logit_real_data_on_device(b200, oracle, host):
     settings = dict(method="BFGS cg", tolerance=1e-10)
     est, p_dev, rep = host.estimate(abi.LOGIT, host.data_from_numpy(raw.copy()), **settings)
     assert rep["status"] == 0
+    # Newton from the same saturated start: the information matrix vanishes there, the first steps fall back to descent
+    est_n, p_newton, rep_n = host.estimate(abi.LOGIT, host.data_from_numpy(raw.copy()), method="Newton", tolerance=1e-12,
+                                           relative_tolerance=True, max_iterations=200)
+    assert rep_n["status"] == 0 and np.max(np.abs(p_newton - p_dev)) < 1e-6
     keep = []
     m = _install_oracle_model(host, oracle, 1, keep)
     host.mle_settings(m, method="BFGS cg", tolerance=1e-10, keep=keep)
