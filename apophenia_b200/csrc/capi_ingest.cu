@@ -16,6 +16,7 @@
 // (inf, nan, hex floats) with a fast exact path for plain decimals.  Quoted fields, backslash
 // escapes and fixed-width layouts are refused (NULL + message): use the reference's reader there.
 #include "capi_internal.cuh"
+#include "host_pool.h"
 #include <fcntl.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
@@ -157,28 +158,10 @@ struct Plan {
     size_t n_rows = 0;
 };
 
-int n_threads() {
-    static int n = 0;
-    if (!n) {
-        const char* e = getenv("APOP_B200_PIN_THREADS");
-        n = e ? atoi(e) : 16;
-        const int hw = (int)std::thread::hardware_concurrency();
-        if (hw > 0 && n > hw) n = hw;
-        if (n < 1) n = 1;
-    }
-    return n;
-}
+int n_threads() { return HostPool::get().size(); }
 
 template <class F>
-void parallel_for(size_t n, F fn) {
-    const int nt = (int)std::min<size_t>((size_t)n_threads(), n ? n : 1);
-    if (nt <= 1) { for (size_t i = 0; i < n; i++) fn(i); return; }
-    std::atomic<size_t> next(0);
-    std::vector<std::thread> pool;
-    for (int t = 0; t < nt; t++)
-        pool.emplace_back([&] { for (size_t i; (i = next.fetch_add(1)) < n;) fn(i); });
-    for (auto& th : pool) th.join();
-}
+void parallel_for(size_t n, F fn) { HostPool::get().run(n, fn); }
 
 // first pass: rules, header, width, segmentation and the number of data rows of every segment
 bool make_plan(const Mapped& M, int has_row_names, int has_col_names, const char* delimiters, size_t seg_bytes, Plan& P) {

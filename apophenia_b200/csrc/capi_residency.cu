@@ -2,6 +2,7 @@
 // upload + re-tiling (apop_b200_pin), the registry keyed by the apop_data address, synthetic
 // device-generated data sets and their download.
 #include "capi_internal.cuh"
+#include "host_pool.h"
 
 using namespace apb;
 
@@ -65,17 +66,12 @@ bool upload(Resident* r, const apop_data* d) {
             okb = cuda_ok(cudaHostAlloc(&R.pin_host[b2], chunk_doubles * sizeof(double), cudaHostAllocDefault), "cudaHostAlloc(staging)") &&
                   cuda_ok(cudaMalloc(&R.pin_dev[b2], chunk_doubles * sizeof(double)), "cudaMalloc(staging)");
         if (!okb) return false;
-        if (!R.pin_ev[0]) { cudaEventCreateWithFlags(&R.pin_ev[0], cudaEventDisableTiming); cudaEventCreateWithFlags(&R.pin_ev[1], cudaEventDisableTiming); }
+        if (!R.pin_ev[0]) {
+            for (int b2 = 0; b2 < 2; b2++) { cudaEventCreateWithFlags(&R.pin_ev[b2], cudaEventDisableTiming); cudaEventCreateWithFlags(&R.pin_copied[b2], cudaEventDisableTiming); }
+        }
         R.pin_cap = chunk_doubles;
     }
-    static int n_threads = 0;
-    if (!n_threads) {
-        const char* e = getenv("APOP_B200_PIN_THREADS");
-        n_threads = e ? atoi(e) : 16;
-        const int hw = (int)std::thread::hardware_concurrency();
-        if (hw > 0 && n_threads > hw) n_threads = hw;
-        if (n_threads < 1) n_threads = 1;
-    }
+    const int n_threads = HostPool::get().size();
     bool ok = true;
     int ci = 0;
     static const bool trace = getenv("APOP_B200_PIN_TRACE") != nullptr;
@@ -106,18 +102,20 @@ bool upload(Resident* r, const apop_data* d) {
                 else for (size_t i = a0; i < a1; i++) hw_[i] = d->weights->data[(r0 + i) * d->weights->stride];
             }
         };
-        const int nt = (rows * (size_t)scols < ((size_t)1 << 17)) ? 1 : n_threads;   // small chunks: not worth a thread
-        if (nt == 1) gather(0, rows);
+        if (rows * (size_t)scols < ((size_t)1 << 17)) gather(0, rows);   // small chunks: not worth waking the pool
         else {
-            std::vector<std::thread> pool;
-            for (int t = 0; t < nt; t++) pool.emplace_back(gather, rows * t / nt, rows * (t + 1) / nt);
-            for (auto& th : pool) th.join();
+            const size_t pieces = (size_t)n_threads * 4;                 // finer than the thread count: evens out stragglers
+            HostPool::get().run(pieces, [&](size_t p) { gather(rows * p / pieces, rows * (p + 1) / pieces); });
         }
         t_gather += since(tg);
         double* dX = R.pin_dev[buf];
         double* dy = dX + rows * (size_t)k;
         double* dw = dy + (hy ? rows : 0);
-        ok = ok && cuda_ok(cudaMemcpyAsync(dX, hX, rows * (size_t)scols * sizeof(double), cudaMemcpyHostToDevice, R.stream), "H2D chunk");
+        // copies on their own stream, back to back; the tiling kernel of chunk i runs on the main stream while
+        // chunk i+1 is crossing PCIe (pin_ev[buf], waited for above, also covers the device staging buffer)
+        ok = ok && cuda_ok(cudaMemcpyAsync(dX, hX, rows * (size_t)scols * sizeof(double), cudaMemcpyHostToDevice, R.copy_stream), "H2D chunk");
+        ok = ok && cuda_ok(cudaEventRecord(R.pin_copied[buf], R.copy_stream), "event");
+        ok = ok && cuda_ok(cudaStreamWaitEvent(R.stream, R.pin_copied[buf], 0), "stream wait");
         ok = ok && cuda_ok(tile_pack(k ? dX : nullptr, hy ? dy : nullptr, hw ? dw : nullptr, rows, k, cols,
                                      r->tiles + (r0 / TILE_ROWS) * (size_t)cols * TILE_ROWS, R.stream, col0), "tile_pack");
         ok = ok && cuda_ok(cudaEventRecord(R.pin_ev[buf], R.stream), "event");

@@ -86,6 +86,7 @@ extern "C" int apop_b200_init(int device) {
     R.device = device;
     R.num_sms = prop.multiProcessorCount;
     if (!cuda_ok(cudaStreamCreateWithFlags(&R.stream, cudaStreamNonBlocking), "cudaStreamCreate")) return 1;
+    if (!cuda_ok(cudaStreamCreateWithFlags(&R.copy_stream, cudaStreamNonBlocking), "cudaStreamCreate")) return 1;
     cudaEventCreate(&R.ev0);
     cudaEventCreate(&R.ev1);
     if (!cuda_ok(cudaMalloc(&R.d_ticket, 64), "cudaMalloc")) return 1;
@@ -131,6 +132,7 @@ extern "C" void apop_b200_finalize(void) {
     cudaEventDestroy(R.ev0);
     cudaEventDestroy(R.ev1);
     cudaStreamDestroy(R.stream);
+    if (R.copy_stream) { cudaStreamDestroy(R.copy_stream); R.copy_stream = nullptr; }
     R.ready = false;
 }
 

@@ -77,6 +77,8 @@ struct Runtime {
     double* pin_host[2] = {nullptr, nullptr};
     double* pin_dev[2] = {nullptr, nullptr};
     cudaEvent_t pin_ev[2] = {nullptr, nullptr};
+    cudaEvent_t pin_copied[2] = {nullptr, nullptr};
+    cudaStream_t copy_stream = nullptr;   // H2D copies of the upload run here, back to back, while the main stream tiles
     size_t pin_cap = 0;   // doubles per staging buffer
     std::unordered_map<const apop_data*, Resident*> reg;
     // stats
