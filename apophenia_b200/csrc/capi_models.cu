@@ -62,7 +62,7 @@ bool eval_glm(Resident* r, GlmFam fam, const double* beta, size_t P, const doubl
     const int NOUT = MAX_ACC + K;
     GlmLaunch L;
     L.tiles = r->tiles; L.n_rows = r->n_rows; L.n_tiles = r->n_tiles;
-    L.grid = grid_for(bps_ref, r->n_tiles, GLM_THREADS / 32);
+    L.grid = grid_for(bps_ref, r->n_tiles, wide ? glm_wide_tiles_per_block(K) : GLM_THREADS / 32);
     if (!ensure_partials((size_t)L.grid * NOUT)) return false;
     L.partials = R.d_partials; L.ticket = R.d_ticket; L.out = R.d_out; L.stream = R.stream;
     L.fin = make_fin(NOUT);

@@ -396,9 +396,11 @@ def test_empty_and_too_wide_inputs(b200):
 
 
 @pytest.mark.parametrize("fam,n,k", [("probit", 20011, 40), ("probit", 5000, 33), ("logit", 9000, 64), ("poisson_reg", 6000, 100),
-                                     ("ols", 7000, 48), ("probit", 3000, 257)])
+                                     ("ols", 7000, 48), ("probit", 3000, 257), ("probit", 4001, 129), ("logit", 3000, 160),
+                                     ("poisson_reg", 2500, 200), ("ols", 3001, 225), ("probit", 2000, 256), ("logit", 2000, 700)])
 def test_wide_data_beyond_32_columns(b200, oracle, fam, n, k):
-    """k > 32: the two-sweep kernel (glm_wide.cu); same parity bar"""
+    """k > 32: the cooperative kernel (one CTA of ceil(k/32) warps per tile, k <= 256) and the two-sweep
+    kernel beyond (glm_wide.cu); same parity bar"""
     ab = b200
     rng = np.random.default_rng(n + k)
     X = rng.uniform(-1, 1, (n, k)); X[:, 0] = 1
