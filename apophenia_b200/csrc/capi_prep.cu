@@ -3,6 +3,7 @@
 // column, the recoding of the outcomes, and the start point.  One call, after which the host
 // prep only has the small things left to do (pages, parameter shapes, settings).
 #include "capi_internal.cuh"
+#include "host_pool.h"
 #include <algorithm>
 
 using namespace apb;
@@ -60,6 +61,14 @@ extern "C" int apop_b200_prep_outcome(apop_data* d, double* cats_out, size_t max
     return rc;
 }
 static int prep_outcome_locked(apop_data* d, double* cats_out, size_t max_cats, size_t* ncat, double* start, int sync_host) {
+    static const bool trace = getenv("APOP_B200_PIN_TRACE") != nullptr;
+    auto t_prev = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!trace) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[apop_b200 prep] %-28s %.3f s\n", what, std::chrono::duration<double>(now - t_prev).count());
+        t_prev = now;
+    };
     if (!d || !d->matrix) { set_error("apop_b200_prep_outcome: NULL data or no matrix"); return 1; }
     if (!require_ready()) return 1;
     Runtime& R = rt();
@@ -83,6 +92,7 @@ static int prep_outcome_locked(apop_data* d, double* cats_out, size_t max_cats, 
         }
         R.reg[d] = r;
     }
+    lap("upload + tiling");
     const bool shuffled = r->y_col0;
     // ---- category table (get_category_table / apop_data_to_factors) and recoding
     std::vector<double> cats;
@@ -97,8 +107,10 @@ static int prep_outcome_locked(apop_data* d, double* cats_out, size_t max_cats, 
         if (ncat) *ncat = cats.size();
         if (cats_out) for (size_t c = 0; c < cats.size(); c++) cats_out[c] = cats[c];
     }
+    lap("category table + recode");
     // ---- start point of probit_prep (model/apop_probit.c:65-80) from the shuffled columns
     if (start && apop_b200_probit_start(d, start) != 0) return 1;
+    lap("start point");
     // ---- the reference's prep mutates the caller's data: mirror that on request
     if (sync_host) {
         const size_t n = r->n_rows;
@@ -109,9 +121,22 @@ static int prep_outcome_locked(apop_data* d, double* cats_out, size_t max_cats, 
             b->size = n; b->data = (double*)malloc(sizeof(double) * (n ? n : 1));
             v->size = n; v->stride = 1; v->data = b->data; v->block = b; v->owner = 1;
             d->vector = v;
+            if (b->data) {   // first touch by the host pool: the driver's pageable copy below is slow on untouched pages
+                const size_t pieces = (size_t)HostPool::get().size() * 4;
+                double* y = b->data;
+                HostPool::get().run(pieces, [&](size_t p) { memset(y + n * p / pieces, 0, sizeof(double) * (n * (p + 1) / pieces - n * p / pieces)); });
+            }
         }
+        lap("host vector allocation");
         if (apop_b200_download(d, nullptr, d->vector->data, nullptr) != 0) return 1;   // recoded outcomes (stride 1 only)
-        if (shuffled) for (size_t i = 0; i < n; i++) d->matrix->data[i * d->matrix->tda] = 1.0;
+        lap("outcome download");
+        if (shuffled) {   // column 0 := 1 is a strided write over the whole matrix: spread it over the host pool
+            const size_t pieces = (size_t)HostPool::get().size() * 4;
+            double* M = d->matrix->data;
+            const size_t tda = d->matrix->tda;
+            HostPool::get().run(pieces, [&](size_t p) { for (size_t i = n * p / pieces; i < n * (p + 1) / pieces; i++) M[i * tda] = 1.0; });
+        }
+        lap("host column 0 := 1");
         r->y_col0 = false;   // the host copy now has the reference's post-prep shape
     }
     return 0;
