@@ -51,8 +51,6 @@ bool ensure_partials(size_t doubles) {
 }
 }  // namespace apb
 
-#define LOCK std::lock_guard<std::recursive_mutex> lock_(rt_mutex())
-
 bool require_ready() {
     if (rt().ready) return true;
     // lazy init on device 0 so that a bare registered model works out of the box

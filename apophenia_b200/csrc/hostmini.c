@@ -51,7 +51,7 @@ gsl_matrix *gsl_matrix_alloc(size_t n1, size_t n2) {
     gsl_matrix *m = calloc(1, sizeof *m);
     gsl_block *b = calloc(1, sizeof *b);
     b->size = n1 * n2;
-    b->data = malloc(sizeof(double) * (n1 * n2 ? n1 * n2 : 1));
+    b->data = malloc(sizeof(double) * (b->size > 0 ? b->size : 1));
     m->size1 = n1; m->size2 = n2; m->tda = n2; m->data = b->data; m->block = b; m->owner = 1;
     return m;
 }
