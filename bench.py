@@ -167,10 +167,13 @@ def main():
     real_stdout = os.dup(1)
     os.dup2(2, 1)
 
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    # the ranks of one box share its host cores: split them between the ranks' upload pools
+    os.environ.setdefault("APOP_B200_PIN_THREADS", str(max(1, (os.cpu_count() or 16) // max(world, 1))))
+
     import torch
     import apophenia_b200 as ab
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     dist = None
