@@ -9,7 +9,7 @@
 // HBM traffic stays 8(k+1) bytes per row; the second touch of each tile is served by L2.
 //
 // For 32 < k <= 256 a cooperative variant keeps everything in registers instead: the NW = ceil(k/32)
-// warps of a CTA work on the SAME tile, warp w owning columns [32w, 32w+32) exactly like the
+// warps of a CTA work on the SAME tile, warp w owning ceil(k/NW) consecutive columns exactly like the
 // register-resident kernel owns its 32 (lane = row, coalesced 256-byte loads, x kept for the score).
 // The partial dot products meet in shared memory (one barrier per tile, ping-pong buffers), every warp
 // then evaluates the family on the full x.beta -- NW-fold redundant FP64 work that stays far below the
@@ -112,7 +112,8 @@ glm_coop_kernel(const double* __restrict__ tiles, const unsigned long long n_row
     double* part = smem + NW * 32;            // [2][NW][32] partial dot products, ping-pong per tile
     double* red = part + 2 * NW * 32;         // MAX_ACC + NW*32 doubles for the reduction tail
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int c0 = warp * 32;                 // first column of this warp
+    const int kw = (K + NW - 1) / NW;         // columns per warp, balanced (k = 40: 20 + 20, not 32 + 8)
+    const int c0 = warp * kw;                 // first column of this warp
     const double aux[4] = {aux4.x, aux4.y, aux4.z, aux4.w};
     const int NOUT = MAX_ACC + K;
     for (int j = threadIdx.x; j < NW * 32; j += NW * 32) sbeta[j] = (j < K) ? beta[j] : 0.0;
@@ -127,12 +128,12 @@ glm_coop_kernel(const double* __restrict__ tiles, const unsigned long long n_row
         const double* base = tiles + t * (unsigned long long)cols * TILE_ROWS + lane;
         double x[32];
 #pragma unroll
-        for (int j = 0; j < 32; j++) x[j] = (c0 + j < K) ? ld_stream(base + (c0 + j) * TILE_ROWS) : 0.0;   // warp-uniform predicate
+        for (int j = 0; j < 32; j++) x[j] = (j < kw && c0 + j < K) ? ld_stream(base + (c0 + j) * TILE_ROWS) : 0.0;   // warp-uniform predicate
         const double y = ld_stream(base + K * TILE_ROWS);
         const double w = has_w ? ld_stream(base + (K + 1) * TILE_ROWS) : 1.0;
         double xbp = 0.0;
 #pragma unroll
-        for (int j = 0; j < 32; j++) xbp = fma(x[j], sbeta[c0 + j], xbp);
+        for (int j = 0; j < 32; j++) xbp = fma(x[j], (j < kw) ? sbeta[c0 + j] : 0.0, xbp);
         part[(pp * NW + warp) * 32 + lane] = xbp;
         __syncthreads();
         double xb = 0.0;
@@ -153,7 +154,7 @@ glm_coop_kernel(const double* __restrict__ tiles, const unsigned long long n_row
 #pragma unroll
     for (int j = 0; j < 32; j++) {
         const double v = warp_sum(g[j]);
-        if (lane == 0) red[MAX_ACC + c0 + j] = v;
+        if (lane == 0 && j < kw && c0 + j < K) red[MAX_ACC + c0 + j] = v;
     }
     if (warp == 0) {
 #pragma unroll
