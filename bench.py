@@ -283,6 +283,10 @@ def run_e2e(ab, args, fam, beta_true, world, rank, barrier, dist, torch):
     if need * 2.5 > avail / max(world, 1):
         n = int(avail / max(world, 1) / 2.5 / ((k + 1) * 8))
     n = max(32, n // 32 * 32)
+    if dist is not None:   # every rank must hold the same number of rows: take the smallest estimate
+        t = torch.tensor([n], device="cuda", dtype=torch.int64)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        n = int(t[0])
     # host data set: the same synthetic recipe, generated on the device and copied back
     src = ab.synth(fam, n, k, beta_true, ncat=args.ncat, seed=8, row_offset=rank * n)
     X, y = src.download()
