@@ -111,6 +111,35 @@ def _fit_on_synth(fam, s, k, start, method="Newton"):
     return m, host.parameters_of(m), keep
 
 
+def cfg_logit8_fit(rows=20_000_000, k=32, C=8):
+    """BASELINE config 2 as a fit: multinomial logit MLE (P = k (C-1) = 224 parameters) on resident data,
+    apop_maximum_likelihood of the host mirror over the device LL and analytic score"""
+    from apophenia_b200 import abi, host
+    h, lib = host.lib(), abi.load_library()
+    rng = np.random.default_rng(8)
+    B = rng.uniform(-1, 1, k * (C - 1))
+    s = ab.synth(ab.LOGIT, rows, k, B, ncat=C)
+    out = {"config": f"multinomial logit MLE, C={C}, {rows}x{k}, P={k * (C - 1)} parameters, start at 0"}
+    ab.ll_score(ab.LOGIT, s, B)      # first-use initialisation outside the timings
+    for method, tol in (("BFGS cg", 1e-9), ("FR cg", 1e-9)):
+        m = h.apop_model_copy(host.model_object(abi.LOGIT))
+        abi.check(lib.apop_b200_register(m, abi.LOGIT), "register")
+        m.contents.parameters = h.apop_data_alloc(0, k, C - 1)
+        m.contents.data = s.ptr
+        keep = []
+        host.mle_settings(m, method=method, tolerance=tol, relative_tolerance=True, max_iterations=2000, starting_pt=np.zeros(k * (C - 1)), keep=keep)
+        l0 = ab.launch_count()
+        t0 = time.perf_counter()
+        h.apop_maximum_likelihood(s.ptr, m)
+        dt = time.perf_counter() - t0
+        rep = h.apop_mle_last_report()
+        est = host.parameters_of(m)
+        out[method] = {"seconds": dt, "status": rep.status, "iterations": rep.iterations, "passes": int(ab.launch_count() - l0),
+                       "ll": rep.ll, "gradient_norm": rep.gradient_norm, "max_abs_err_vs_B_true": float(np.max(np.abs(est - B)))}
+    s.free()
+    return out
+
+
 def cfg_bootstrap_cov(rows=5_000_000, k=20, m=1000):
     """BASELINE config 4 end to end: apop_bootstrap_cov of a probit fit (counts + lock-step replicate fits)"""
     from apophenia_b200 import host
@@ -245,7 +274,7 @@ def cfg_ingest(rows=2_000_000, k=16):
             "speedup_vs_pandas_plus_pin": (t_pandas + t_pin) / t_dev, "identical": ok}
 
 
-ALL = {"ingest": cfg_ingest, "prep": cfg_prep, "config1": cfg_config1, "bootstrap_cov": cfg_bootstrap_cov, "metropolis": cfg_metropolis, "logit8": cfg_logit8, "bootstrap": cfg_bootstrap, "chains": cfg_chains, "poisson": cfg_poisson, "newton": cfg_newton}
+ALL = {"logit8_fit": cfg_logit8_fit, "ingest": cfg_ingest, "prep": cfg_prep, "config1": cfg_config1, "bootstrap_cov": cfg_bootstrap_cov, "metropolis": cfg_metropolis, "logit8": cfg_logit8, "bootstrap": cfg_bootstrap, "chains": cfg_chains, "poisson": cfg_poisson, "newton": cfg_newton}
 
 if __name__ == "__main__":
     ab.init(0)
