@@ -201,3 +201,34 @@ def test_amash_logit_real_data_on_device(b200, oracle, host):
     H = ab.information(ab.LOGIT, d, p_dev)
     assert np.allclose(H, oracle.information(1, X, y, p_dev).astype(float), rtol=1e-11)
     ab.unpin(d)
+
+
+def test_entries_are_callable_from_any_host_thread(b200, oracle):
+    """SURVEY 8(b) threading: the reference's callers may sit in OpenMP regions; every entry takes the
+    library mutex and sets the device itself, so concurrent calls from several host threads on different
+    data sets must return exactly what serial calls return"""
+    import threading
+    ab = b200
+    sets = []
+    for seed, (n, k) in enumerate(((30011, 7), (20000, 12), (9999, 32))):
+        X, y, beta = gen_probit_logit_sample(n, k, seed=40 + seed)
+        d = ab.pin(ab.Data(matrix=X, vector=y))
+        sets.append((d, beta, ab.ll_score(ab.PROBIT, d, beta)))
+    errors = []
+
+    def worker(tid):
+        try:
+            for i in range(25):
+                d, beta, (ll0, g0) = sets[(tid + i) % len(sets)]
+                ll, g = ab.ll_score(ab.PROBIT, d, beta)
+                if ll != ll0 or not np.array_equal(g, g0):
+                    errors.append((tid, i))
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(6)]
+    for t in threads: t.start()
+    for t in threads: t.join()
+    assert not errors, errors[:3]
+    for d, _, _ in sets:
+        ab.unpin(d)
