@@ -70,6 +70,7 @@ static int prep_outcome_locked(apop_data* d, double* cats_out, size_t max_cats, 
         t_prev = now;
     };
     if (!d || !d->matrix) { set_error("apop_b200_prep_outcome: NULL data or no matrix"); return 1; }
+    if (sync_host && d->vector && d->vector->stride != 1) { set_error("apop_b200_prep_outcome: sync_host needs a contiguous outcome vector (stride 1)"); return 1; }
     if (!require_ready()) return 1;
     Runtime& R = rt();
     cudaSetDevice(R.device);
