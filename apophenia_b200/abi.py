@@ -20,7 +20,9 @@ BERNOULLI, BETA, ZIPF, DIRICHLET, TDIST, YULE = range(9, 15)
 FAMILY_NAMES = {PROBIT: "probit", LOGIT: "logit", POISSON: "poisson", NORMAL: "normal", OLS: "ols",
                 POISSON_REG: "poisson_reg", EXPONENTIAL: "exponential", GAMMA: "gamma", LOGNORMAL: "lognormal",
                 BERNOULLI: "bernoulli", BETA: "beta", ZIPF: "zipf", DIRICHLET: "dirichlet", TDIST: "t", YULE: "yule"}
-MAP_IDENTITY, MAP_DEV, MAP_DEV2, MAP_POISSON, MAP_LOG, MAP_EXP = range(6)
+MAP_IDENTITY, MAP_DEV, MAP_DEV2, MAP_POISSON, MAP_LOG, MAP_EXP, MAP_ABS, MAP_SQRT, MAP_SCALE, MAP_POW = range(10)
+(ROW_SUM, ROW_MEAN, ROW_SUMSQ, ROW_MAX, ROW_MIN, ROW_DOT, ROW_PROBIT_LL, ROW_LOGIT2_LL, ROW_POISSON_REG_LL,
+ ROW_OLS_ERROR) = range(10)
 
 
 class gsl_block(C.Structure):
@@ -104,6 +106,10 @@ SIGNATURES = {
     "apop_b200_invalidate": (C.c_int, [_PD]),
     "apop_b200_is_pinned": (C.c_int, [_PD]),
     "apop_b200_set_auto_pin": (None, [C.c_int]),
+    "apop_b200_set_timing": (None, [C.c_int]),
+    "apop_b200_global_rows": (C.c_double, [_PD]),
+    "apop_b200_map": (C.c_int, [_PD, C.c_int, C.c_double, C.c_char, _dp, _dp]),
+    "apop_b200_map_rows": (C.c_int, [_PD, C.c_int, _dp, C.c_size_t, _dp, _dp]),
     "apop_b200_synth": (_PD, [C.c_int, C.c_size_t, C.c_size_t, C.c_int, _dp, C.c_uint64, C.c_uint64]),
     "apop_b200_synth_free": (None, [_PD]),
     "apop_b200_download": (C.c_int, [_PD, _dp, _dp, _dp]),
@@ -251,6 +257,15 @@ class Data:
     @property
     def ptr(self):
         return C.pointer(self.struct)
+
+    def __del__(self):
+        # the resident copy is keyed by this struct's address: release it with the owner (an apop_data
+        # allocated later at the same address must never meet a stale registry entry)
+        try:
+            if _LIB is not None:
+                _LIB.apop_b200_unpin(C.pointer(self.struct))
+        except Exception:
+            pass
 
     def add_page(self, page):
         """append a page to the ->more list (apop_data_add_page)"""

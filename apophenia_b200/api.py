@@ -12,16 +12,20 @@ import numpy as np
 from . import abi
 from .abi import (B200Error, Data, Model, PROBIT, LOGIT, POISSON, NORMAL, OLS, POISSON_REG,  # noqa: F401
                   EXPONENTIAL, GAMMA, LOGNORMAL, BERNOULLI, BETA, ZIPF, DIRICHLET, TDIST, YULE,
-                  MAP_IDENTITY, MAP_DEV, MAP_DEV2, MAP_POISSON, MAP_LOG, MAP_EXP)
+                  MAP_IDENTITY, MAP_DEV, MAP_DEV2, MAP_POISSON, MAP_LOG, MAP_EXP, MAP_ABS, MAP_SQRT, MAP_SCALE, MAP_POW,
+                  ROW_SUM, ROW_MEAN, ROW_SUMSQ, ROW_MAX, ROW_MIN, ROW_DOT, ROW_PROBIT_LL, ROW_LOGIT2_LL,
+                  ROW_POISSON_REG_LL, ROW_OLS_ERROR)
 
 __all__ = ["init", "finalize", "pin", "unpin", "invalidate", "is_pinned", "log_likelihood", "score",
-           "ll_score", "map_sum", "synth", "SynthData", "launch_count", "last_pass_ms", "pass_timer_reset",
+           "ll_score", "map_sum", "synth", "SynthData", "launch_count", "last_pass_ms", "pass_timer_reset", "set_timing",
            "pass_timer", "probit_model", "logit_model", "vector_model", "Data", "Model", "B200Error",
            "PROBIT", "LOGIT", "POISSON", "NORMAL", "OLS", "POISSON_REG", "EXPONENTIAL", "GAMMA", "LOGNORMAL",
            "BERNOULLI", "BETA", "ZIPF", "DIRICHLET", "TDIST", "YULE", "comm_init_from_torch",
            "comm_finalize", "set_auto_pin", "last_error", "information", "ols_gram",
            "dot", "col_sums", "probit_start", "prep_outcome", "logit_expected", "text_to_host", "text_to_resident", "ll_score_batched", "bootstrap_counts", "counts_download",
-           "MAP_IDENTITY", "MAP_DEV", "MAP_DEV2", "MAP_POISSON", "MAP_LOG", "MAP_EXP"]
+           "MAP_IDENTITY", "MAP_DEV", "MAP_DEV2", "MAP_POISSON", "MAP_LOG", "MAP_EXP", "MAP_ABS", "MAP_SQRT",
+           "MAP_SCALE", "MAP_POW", "ROW_SUM", "ROW_MEAN", "ROW_SUMSQ", "ROW_MAX", "ROW_MIN", "ROW_DOT",
+           "ROW_PROBIT_LL", "ROW_LOGIT2_LL", "ROW_POISSON_REG_LL", "ROW_OLS_ERROR", "map", "map_rows", "global_rows"]
 
 _dp = C.POINTER(C.c_double)
 
@@ -72,7 +76,14 @@ def last_pass_ms():
     return float(_lib().apop_b200_last_pass_ms())
 
 
+def set_timing(on=True):
+    """per-pass CUDA-event timing (off by default: it costs ~25 us per pass)"""
+    _lib().apop_b200_set_timing(int(bool(on)))
+
+
 def pass_timer_reset():
+    """zero the accumulated kernel time; asking for the timer switches per-pass timing on"""
+    _lib().apop_b200_set_timing(1)
     _lib().apop_b200_pass_timer_reset()
 
 
@@ -223,6 +234,34 @@ def map_sum(d, fn, p0=0.0, part="a"):
     return float(_lib().apop_b200_map_sum(_ptr(d), int(fn), float(p0), part.encode()))
 
 
+def map(d, fn, p0=0.0, part="a", n_rows=None, k=None):  # noqa: A001 (the reference's name)
+    """apop_map with a materialised result: (vector or None, matrix or None) of the input's shape"""
+    n = n_rows if n_rows is not None else (d.matrix.shape[0] if getattr(d, "matrix", None) is not None else d.vector.shape[0])
+    kk = k if k is not None else (d.matrix.shape[1] if getattr(d, "matrix", None) is not None else 0)
+    has_v = getattr(d, "vector", None) is not None or getattr(d, "has_y", False)
+    ov = np.zeros(n) if has_v else None
+    om = np.zeros((n, kk)) if kk else None
+    abi.check(_lib().apop_b200_map(_ptr(d), int(fn), float(p0), part.encode(),
+                                   ov.ctypes.data_as(_dp) if ov is not None else None,
+                                   om.ctypes.data_as(_dp) if om is not None else None), "apop_b200_map")
+    return ov, om
+
+
+def map_rows(d, fn, n_rows, param=None, aux=None):
+    """apop_map(.part='r') with one of the built-in row functions: one double per row"""
+    out = np.zeros(n_rows)
+    p = np.ascontiguousarray(param, dtype=np.float64).ravel() if param is not None else None
+    a = np.ascontiguousarray(aux, dtype=np.float64).ravel() if aux is not None else None
+    abi.check(_lib().apop_b200_map_rows(_ptr(d), int(fn), p.ctypes.data_as(_dp) if p is not None else None,
+                                        p.size if p is not None else 0, a.ctypes.data_as(_dp) if a is not None else None,
+                                        out.ctypes.data_as(_dp)), "apop_b200_map_rows")
+    return out
+
+
+def global_rows(d):
+    return float(_lib().apop_b200_global_rows(_ptr(d)))
+
+
 # ---- parameter containers shaped like the reference's --------------------------
 def probit_model(beta, data=None, name="Probit"):
     """parameters = k x 1 matrix, as probit_prep allocates them (model/apop_probit.c:49)"""
@@ -322,7 +361,7 @@ def comm_init_from_torch():
     abi.check(lib.apop_b200_comm_init(world, rank, C.cast(buf2, C.c_void_p)), "apop_b200_comm_init")
     # fused allreduce over NVLink peer memory (default; APOP_B200_ALLREDUCE=nccl keeps NCCL only)
     import os
-    if os.environ.get("APOP_B200_ALLREDUCE", "p2p") != "nccl" and world <= 8:
+    if os.environ.get("APOP_B200_ALLREDUCE", "p2p") != "nccl" and 2 <= world <= 8:
         hbuf = (C.c_char * 64)()
         abi.check(lib.apop_b200_comm_p2p_handle(world, C.cast(hbuf, C.c_void_p)), "apop_b200_comm_p2p_handle")
         mine = torch.tensor(list(bytes(hbuf)), dtype=torch.uint8)

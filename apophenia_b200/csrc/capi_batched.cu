@@ -58,6 +58,58 @@ extern "C" int apop_b200_ols_gram(apop_data* d, double* xtx, double* xty) {
     return ok ? 0 : 1;
 }
 
+// Observed information of the multinomial logit, P x P in pack order (index j*(C-1)+c), from
+// ceil((C-1) C / 8) launches of the pair-block kernel (logit_info.cu).
+static bool eval_logit_info(Resident* r, const double* B, size_t C1, double* H) {
+    Runtime& R = rt();
+    const int K = r->k;
+    if (K < 1 || K > MAX_K_REG) return set_error("k = %d columns: the information kernel covers 1..%d", K, MAX_K_REG);
+    if (C1 < 2 || C1 > (size_t)LOGIT_MAX_C1) return set_error("%zu outcome categories: the multinomial kernels cover 3..%d", C1 + 1, LOGIT_MAX_C1 + 1);
+    static int bps_cache[MAX_K_REG + 1][LOGIT_MAX_C1 + 1];
+    int& bps = bps_cache[K][C1];
+    if (!bps) bps = logit_info_blocks_per_sm(K, (int)C1);
+    if (bps <= 0) return set_error("multinomial information kernel unavailable for k=%d, C=%zu", K, C1 + 1);
+    const int KB = logit_kb(K), NOUT = LOGIT_INFO_NP * KB * KB;
+    const size_t P = (size_t)K * C1;
+    LogitParams prm;
+    memset(&prm, 0, sizeof prm);
+    memcpy(prm.B, B, P * sizeof(double));
+    std::vector<std::pair<int, int>> pairs;
+    for (int a = 0; a < (int)C1; a++)
+        for (int b = a; b < (int)C1; b++) pairs.push_back({a, b});
+    for (size_t p0 = 0; p0 < pairs.size(); p0 += LOGIT_INFO_NP) {
+        LogitInfoPairs pr;
+        for (int i = 0; i < LOGIT_INFO_NP; i++) {
+            const bool live = p0 + i < pairs.size();
+            pr.a[i] = live ? pairs[p0 + i].first : -1;
+            pr.b[i] = live ? pairs[p0 + i].second : -1;
+        }
+        LogitLaunch L;
+        L.tiles = r->tiles; L.n_rows = r->n_rows; L.n_tiles = r->n_tiles; L.k = K; L.cols = r->cols;
+        L.grid = grid_for(bps, r->n_tiles, LOGIT_INFO_THREADS / 32);
+        if (!ensure_partials((size_t)L.grid * NOUT)) return false;
+        L.partials = R.d_partials; L.ticket = R.d_ticket; L.out = R.d_out; L.stream = R.stream;
+        L.fin = make_fin(NOUT);
+        time_begin();
+        if (!cuda_ok(logit_info_launch((int)C1, L, prm, pr), "multinomial information launch")) return false;
+        time_end_record();
+        R.launches++;
+        if (!reduce_and_fetch(NOUT, L.fin)) return false;
+        time_collect();
+        for (int i = 0; i < LOGIT_INFO_NP && p0 + i < pairs.size(); i++) {
+            const int a = pr.a[i], b = pr.b[i];
+            const double* blk = R.h_out + (size_t)i * KB * KB;
+            for (int j = 0; j < K; j++)
+                for (int j2 = 0; j2 < K; j2++) {
+                    const double v = blk[j * KB + j2];
+                    H[((size_t)j * C1 + a) * P + (size_t)j2 * C1 + b] = v;
+                    H[((size_t)j * C1 + b) * P + (size_t)j2 * C1 + a] = v;   // W_ab = W_ba
+                }
+        }
+    }
+    return true;
+}
+
 extern "C" int apop_b200_information(apop_b200_family family, apop_data* d, const double* beta, size_t P, double* H) {
     LOCK;
     if (!d || !beta || !H) { set_error("apop_b200_information: NULL argument"); return 1; }
@@ -66,7 +118,12 @@ extern "C" int apop_b200_information(apop_b200_family family, apop_data* d, cons
     bool ok = false;
     std::vector<double> out;
     double scale = 1.0;
-    if ((size_t)r->k != P) set_error("apop_b200_information: P = %zu but the data has %d columns (binary-outcome families only)", P, r->k);
+    if (family == APOP_B200_LOGIT && r->k > 0 && P > (size_t)r->k && P % (size_t)r->k == 0) {
+        const bool okm = eval_logit_info(r, beta, P / (size_t)r->k, H);   // multinomial: P = k (C-1)
+        release(r);
+        return okm ? 0 : 1;
+    }
+    if ((size_t)r->k != P) set_error("apop_b200_information: P = %zu but the data has %d columns", P, r->k);
     else if (family == APOP_B200_PROBIT) ok = eval_xtwx(r, XTWX_PROBIT, beta, nullptr, out);
     else if (family == APOP_B200_LOGIT) ok = eval_xtwx(r, XTWX_LOGIT2, beta, nullptr, out);
     else if (family == APOP_B200_POISSON_REG) ok = eval_xtwx(r, XTWX_POISSON_REG, beta, nullptr, out);
@@ -104,7 +161,7 @@ extern "C" int apop_b200_ll_score_batched(apop_b200_family family, apop_data* d,
     do {
         const int K = r->k;
         if ((size_t)K != P) { set_error("batched path: P = %zu but the data has %d columns", P, K); break; }
-        if (K < 1 || K > MAX_K_REG || !r->has_y || r->has_w) { set_error("batched path: needs 1..%d columns, an outcome vector and no weights", MAX_K_REG); break; }
+        if (K < 1 || K > MAX_K_REG || !r->has_y) { set_error("batched path: needs 1..%d columns and an outcome vector", MAX_K_REG); break; }   // a weights column is ignored, as these families do
         if (use_counts && (!r->counts || r->counts_m < m)) { set_error("batched path: no resident resample counts for %zu replicates (call apop_b200_bootstrap_counts)", m); break; }
         if (use_counts && fam == GLM_POISSON_REG) { set_error("batched path: resample counts are not supported for the Poisson regression constant"); break; }
         const int KB = batched_kb(K), NOUT = 1 + KB;

@@ -25,6 +25,7 @@ bool allreduce_host(double* v, int n);
 bool allreduce_scalar(double* v);
 // residency (capi_residency.cu)
 bool upload(apb::Resident* r, const apop_data* d);
+apb::HostSig host_sig(const apop_data* d);
 apb::Resident* acquire(apop_data* d);
 void release(apb::Resident* r);
 // evaluators (capi_models.cu, capi_batched.cu)
@@ -41,5 +42,7 @@ bool lgamma_const(apb::Resident* r, double& v);
 bool pack_parameters(const apop_data* p, std::vector<double>& out);
 const apop_data* category_page(const apop_data* d);
 const apop_data* named_page(const apop_data* d, const char* title);
+const apop_data* named_page_or_self(const apop_data* d, const char* title);
+bool is_device_entry(void* log_likelihood_fn);   // capi_register.cu: one of this library's log-likelihood entries
 void fill_nan(gsl_vector* g);
 void store_score(gsl_vector* g, const double* src, size_t n, double scale);

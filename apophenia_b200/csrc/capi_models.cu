@@ -17,10 +17,13 @@ int grid_for(int blocks_per_sm, size_t n_tiles, int warps_per_block) {
     return (int)g;
 }
 
-void time_begin() { cudaEventRecord(rt().ev0, rt().stream); }
-void time_end_record() { cudaEventRecord(rt().ev1, rt().stream); }
+// Per-pass CUDA-event timing is opt-in (apop_b200_set_timing / APOP_B200_TIMING=1): the two event records
+// and the elapsed-time query cost ~25 us per pass, 5 % of a strong-scaling pass of 0.5 ms.
+void time_begin() { if (rt().timing) cudaEventRecord(rt().ev0, rt().stream); }
+void time_end_record() { if (rt().timing) cudaEventRecord(rt().ev1, rt().stream); }
 void time_collect() {
     Runtime& R = rt();
+    if (!R.timing) { R.n_passes++; return; }
     float ms = 0;
     if (cudaEventElapsedTime(&ms, R.ev0, R.ev1) == cudaSuccess) {
         R.last_ms = ms;
@@ -44,19 +47,15 @@ bool eval_glm(Resident* r, GlmFam fam, const double* beta, size_t P, const doubl
         out = r->memo_out;
         return true;
     }
-    const bool has_w = r->has_w && fam == GLM_OLS;
-    // a weights column the family ignores still sits in the tile: the kernels
-    // index columns by COLS, so only OLS may carry weights
-    if (r->has_w && fam != GLM_OLS) return set_error("weights are only used by the OLS family; drop them before pinning");
+    // a weights column sets the tile stride for every family, but only OLS reads it: probit, logit and the
+    // Poisson regression ignore d->weights exactly as the reference's do (model/apop_probit.c never touches them)
+    const bool reads_w = r->has_w && fam == GLM_OLS;
+    const bool has_w = r->has_w;
     const bool wide = K > MAX_K_REG;
-    static int tma_env = -1;
-    if (tma_env < 0) { const char* e = getenv("APOP_B200_GLM_TMA"); tma_env = (e && e[0] == '1') ? 1 : 0; }
-    const bool tma = tma_env && fam == GLM_PROBIT && !has_w && (K == 16 || K == 20 || K == 24 || K == 32);
     static int bps_cache[GLM_FAM_COUNT][MAX_K_REG + 1][2];
     int bps_wide = 0;
     int& bps = wide ? bps_wide : bps_cache[fam][K][has_w ? 1 : 0];
-    if (tma) { static int tb[MAX_K_REG + 1]; if (!tb[K]) tb[K] = glm_tma_blocks_per_sm_probit(K); bps_wide = tb[K]; }
-    int& bps_ref = tma ? bps_wide : bps;
+    int& bps_ref = bps;
     if (!bps_ref) bps_ref = wide ? glm_wide_blocks_per_sm(fam, K) : glm_blocks_per_sm(fam, K, has_w);
     if (bps_ref <= 0) return set_error("kernel for family %d, k=%d is not available on this device", (int)fam, K);
     const int NOUT = MAX_ACC + K;
@@ -75,8 +74,7 @@ bool eval_glm(Resident* r, GlmFam fam, const double* beta, size_t P, const doubl
         if (!cuda_ok(cudaMemcpyAsync(R.d_beta, beta, P * sizeof(double), cudaMemcpyHostToDevice, R.stream), "H2D beta")) return false;
     }
     time_begin();
-    if (!cuda_ok(tma ? glm_tma_launch_probit(K, L, prm)
-                     : wide ? glm_wide_launch(fam, K, r->cols, has_w, L, R.d_beta, prm.aux) : glm_launch(fam, K, has_w, L, prm),
+    if (!cuda_ok(wide ? glm_wide_launch(fam, K, r->cols, reads_w, L, R.d_beta, prm.aux) : glm_launch(fam, K, has_w, L, prm),
                  "glm kernel launch")) return false;
     time_end_record();
     R.launches++;
@@ -146,6 +144,13 @@ const apop_data* named_page(const apop_data* d, const char* title) {
     return nullptr;
 }
 
+// apop_data_get_page (apop_data.m4.c:1298-1304) also matches the data set itself
+const apop_data* named_page_or_self(const apop_data* d, const char* title) {
+    for (const apop_data* pg = d; pg; pg = pg->more)
+        if (pg->names && pg->names->title && !strcasecmp(pg->names->title, title)) return pg;
+    return nullptr;
+}
+
 void fill_nan(gsl_vector* g) {
     if (g && g->data)
         for (size_t i = 0; i < g->size; i++) g->data[i * g->stride] = NAN;
@@ -205,7 +210,7 @@ bool eval_logit(Resident* r, const std::vector<double>& B, size_t C1, const std:
     if (B.size() != (size_t)K * C1) return set_error("parameters are %zu doubles; the data has %d columns x %zu free categories", B.size(), K, C1);
     if (K < 1 || K > MAX_K_REG) return set_error("k = %d columns: the fused kernels cover 1..%d", K, MAX_K_REG);
     if (C1 < 2 || C1 > (size_t)LOGIT_MAX_C1) return set_error("%zu outcome categories: the multinomial kernel covers 3..%d", C1 + 1, LOGIT_MAX_C1 + 1);
-    if (!r->has_y || r->has_w) return set_error("logit needs an outcome vector and no weights column");
+    if (!r->has_y) return set_error("logit needs an outcome vector (run the model's prep first)");
     std::vector<double> key(B);
     key.insert(key.end(), cats.begin(), cats.end());
     if (r->memo_valid && r->memo_fam == 200 + (int)C1 && r->memo_beta.size() == key.size() &&
@@ -220,7 +225,7 @@ bool eval_logit(Resident* r, const std::vector<double>& B, size_t C1, const std:
     const int KB = logit_kb(K);
     const int NOUT = 1 + KB * (int)C1;
     LogitLaunch L;
-    L.tiles = r->tiles; L.n_rows = r->n_rows; L.n_tiles = r->n_tiles; L.k = K;
+    L.tiles = r->tiles; L.n_rows = r->n_rows; L.n_tiles = r->n_tiles; L.k = K; L.cols = r->cols;   // a weights column only widens the tile stride
     L.grid = grid_for(bps, r->n_tiles, LOGIT_THREADS / 32);
     if (!ensure_partials((size_t)L.grid * NOUT)) return false;
     L.partials = R.d_partials; L.ticket = R.d_ticket; L.out = R.d_out; L.stream = R.stream;
@@ -327,47 +332,164 @@ extern "C" void apop_b200_poisson_reg_score(apop_data* d, gsl_vector* g, apop_mo
 }
 
 // ---- OLS -------------------------------------------------------------------
+// ols_log_likelihood (model/apop_ols.c:129-172) has four branches besides the plain one; all are served:
+//   un-prepped data (:149-153)   no outcome vector yet: column 0 of the matrix is the outcome and
+//                                expected += beta_0 (1 - actual), i.e. exactly x.beta with column 0 := 1.  The
+//                                upload shuffles the column out on the device (tile_pack's y_col0).
+//   <Predicted> page (:139-145)  when p->info carries it and d == p->data, the errors are column 2 of that
+//                                page (zero padded to the rows of d), whatever p->parameters say.
+//   <Error variance> page (:157) sigma from the page instead of the sample variance of the errors.
+//   input_distribution (:163-166) every row's density is multiplied by P(x_i): LL += sum_i log P(x_i).
+// ols_score (:175-205) has only the un-prepped branch; there the multiplier of column 0 is the RAW
+// column 0 (the outcome), as coded: g_0 = sum w y e / sigma^2.
 struct OlsEval {
     bool ok = false;
     long double ll = NAN, sigma2 = NAN;
     std::vector<double> g;
 };
-static OlsEval ols_entry(apop_data* d, apop_model* m) {
+static void* settings_group(const apop_model* m, const char* name) {
+    if (!m || !m->settings) return nullptr;
+    for (const apop_settings_type* s = m->settings; s->name[0]; s++)
+        if (!strcmp(s->name, name)) return s->setting_group;
+    return nullptr;
+}
+// the resident copy OLS works on: prepped data as usual; un-prepped data with the outcome shuffled out
+static Resident* acquire_ols(apop_data* d, bool& unprepped) {
+    unprepped = d && !d->vector && d->matrix;
+    if (!unprepped) return acquire(d);
+    if (!require_ready()) return nullptr;
+    Runtime& R = rt();
+    cudaSetDevice(R.device);
+    auto it = R.reg.find(d);
+    if (it != R.reg.end()) {
+        Resident* r = acquire(d);                 // refreshes a dirty or stale entry
+        if (!r) return nullptr;
+        if (r->has_y) { unprepped = !r->synthetic && r->y_col0; return r; }   // pinned through the device prep: already shuffled
+        // pinned raw (k columns, no outcome): leave that copy alone and work on a shuffled one
+    }
+    Resident* r = new Resident();
+    r->y_col0 = true;
+    if (!upload(r, d)) { free_resident(r); return nullptr; }
+    if (R.auto_pin && it == R.reg.end()) R.reg[d] = r;
+    else r->transient = true;
+    return r;
+}
+// sum_i log P(x_i) for the input distribution of apop_lm_settings; 0 for the improper uniform default
+static bool ols_input_term(apop_data* d, Resident* r, apop_model* id, long double& term) {
+    term = 0;
+    if (!id || (!id->log_likelihood && !id->p)) return true;
+    if (!strncasecmp(id->name, "Improper uniform", 16)) return true;       // P(x) = 1
+    if (id->log_likelihood && is_device_entry((void*)id->log_likelihood)) {
+        // the device families are sums over cells: one call over the matrix part of the resident copy
+        // (justarow->vector = NULL, :163), through a header-only view registered for the call
+        Runtime& R = rt();
+        apop_data view;
+        memset(&view, 0, sizeof view);
+        view.matrix = d->matrix;
+        view.more = d->more;
+        Resident tmp = *r;
+        tmp.has_y = false; tmp.transient = false; tmp.synthetic = true;    // shares the tiles: never uploaded, never freed
+        tmp.memo_valid = false; tmp.have_lgamma_y = tmp.have_poisson = tmp.have_gamma = false; tmp.consts.clear();
+        tmp.n_global_epoch = ~0ull; tmp.counts = nullptr; tmp.lgy = nullptr;
+        R.reg[&view] = &tmp;
+        const long double v = id->log_likelihood(&view, id);
+        R.reg.erase(&view);
+        term = v;
+        return !std::isnan((double)v);
+    }
+    // a host model: the reference's own loop, one apop_p per row view (needs the host buffers)
+    if (!d->matrix || !d->matrix->data) return set_error("OLS input_distribution: a host model needs host data");
+    const gsl_matrix* M = d->matrix;
+    for (size_t i = 0; i < M->size1; i++) {
+        gsl_matrix row = {1, M->size2, M->tda, M->data + i * M->tda, nullptr, 0};
+        apop_data just;
+        memset(&just, 0, sizeof just);
+        just.matrix = &row;
+        const long double lp = id->log_likelihood ? id->log_likelihood(&just, id) : logl(id->p(&just, id));
+        term += lp;
+    }
+    return true;
+}
+static OlsEval ols_entry(apop_data* d, apop_model* m, bool for_score) {
     OlsEval o;
-    if (d && !d->vector) {
-        set_error("OLS data is not prepped (no outcome vector): run ols_shuffle / the model's prep first");
-        if (m) m->error = 'd';
+    if (!m || !m->parameters || !d || !d->matrix) { set_error("NULL model, parameters or data"); return o; }
+    std::vector<double> beta, out;
+    if (!pack_parameters(m->parameters, beta)) { set_error("empty parameters"); return o; }
+    bool unprepped = false;
+    Resident* r = acquire_ols(d, unprepped);
+    if (!r) { d->error = 'a'; return o; }
+    double n, mc, vc;
+    // the un-prepped score needs sum w e^2 (for g_0 = sum w y e); it takes the place of sum log w
+    const double aux[4] = {(for_score && unprepped) ? 1.0 : 0.0, 0, 0, 0};
+    if (!eval_glm(r, GLM_OLS, beta.data(), beta.size(), aux, out) || !global_counts(r, n, mc, vc)) {
+        m->error = 'd';
+        release(r);
         return o;
     }
-    GlmEval e = glm_entry(GLM_OLS, d, m, nullptr);
-    if (!e.ok) { release(e.r); return o; }
-    double n, mc, vc;
-    if (!global_counts(e.r, n, mc, vc)) { release(e.r); return o; }
-    const long double S1 = e.out[0], S2 = e.out[1], S3 = e.r->has_w ? e.out[2] : 0.0L;
-    // sample variance of the errors (gsl_stats_variance: n-1 in the denominator)
-    long double var = (S2 - S1 * S1 / n) / (n - 1);
-    o.sigma2 = var;
+    long double S1 = out[0], S2 = out[1];
+    const long double S3 = (r->has_w && !for_score) ? out[2] : 0.0L;
+    // the score always takes the sample variance of the errors at these parameters (:192)
+    const long double var_score = (S2 - S1 * S1 / n) / (n - 1);
+    o.sigma2 = var_score;
+    if (for_score) {
+        o.g.assign(out.begin() + MAX_ACC, out.end());
+        if (unprepped) {
+            // column 0 of the caller's matrix is y itself: sum w y e = beta . (sum w x e) - sum w e^2
+            long double bg = 0;
+            for (size_t j = 0; j < beta.size(); j++) bg += (long double)beta[j] * out[MAX_ACC + j];
+            const long double swe2 = r->has_w ? (long double)out[2] : S2;
+            o.g[0] = (double)(bg - swe2);
+        }
+        for (auto& v : o.g) v = (double)(v / var_score);
+        o.ok = true;
+        release(r);
+        return o;
+    }
+    // ---- LL: errors from the <Predicted> page when the model carries one for this very data set
+    const apop_data* pred = m->info ? named_page_or_self(m->info, "<Predicted>") : nullptr;
+    if (pred && d == m->data && pred->matrix && pred->matrix->size2 >= 3) {
+        // column 2 of the page as a strided vector; rows beyond it count as zero errors (:141-144)
+        gsl_vector ev = {pred->matrix->size1 < r->n_rows ? pred->matrix->size1 : r->n_rows, pred->matrix->tda,
+                         pred->matrix->data + 2, nullptr, 0};
+        apop_data view;
+        memset(&view, 0, sizeof view);
+        view.vector = &ev;
+        Resident* rv = acquire(&view);
+        double c5[CELLS_NOUT];
+        const bool okv = rv && eval_cells(rv, CELLS_NORMAL, 0.0, c5, /*matrix=*/false);
+        release(rv);
+        if (!okv) { release(r); m->error = 'd'; return o; }
+        S1 = c5[2]; S2 = c5[3];
+        if (rt().nranks > 1) {   // the page holds this rank's rows only
+            double v2[2] = {(double)S1, (double)S2};
+            if (!allreduce_host(v2, 2)) { release(r); return o; }
+            S1 = v2[0]; S2 = v2[1];
+        }
+    }
+    long double var_ll = (S2 - S1 * S1 / n) / (n - 1);
     const apop_data* ev = named_page(m->parameters, "<Error variance>");
-    long double var_ll = var;
-    if (ev) var_ll = ev->matrix ? ev->matrix->data[0] : (ev->vector ? ev->vector->data[0] : var);
+    if (ev) var_ll = ev->matrix ? ev->matrix->data[0] : (ev->vector ? ev->vector->data[0] : var_ll);
     const long double sigma = sqrtl(var_ll);
-    // sum_i log( phi(e_i; sigma) w_i ) with phi the Gaussian density
+    // sum_i log( phi(e_i; sigma) w_i P(x_i) ) with phi the Gaussian density
     o.ll = -S2 / (2 * var_ll) - n * logl(sigma * 2.50662827463100050241576528481104525L) + S3;
-    o.g.assign(e.out.begin() + MAX_ACC, e.out.end());
-    for (auto& v : o.g) v = (double)(v / var);
+    long double xterm = 0;
+    struct lm_group { int destroy_data; apop_data* instruments; char want_cov, want_expected_value; apop_model* input_distribution; };
+    const lm_group* lms = (const lm_group*)settings_group(m, "apop_lm");
+    if (lms && lms->input_distribution && !ols_input_term(d, r, lms->input_distribution, xterm)) { release(r); m->error = 'd'; return o; }
+    o.ll += xterm;
     o.ok = true;
-    release(e.r);
+    release(r);
     return o;
 }
 extern "C" long double apop_b200_ols_ll(apop_data* d, apop_model* m) {
     LOCK;
-    OlsEval o = ols_entry(d, m);
+    OlsEval o = ols_entry(d, m, false);
     return o.ok ? o.ll : (long double)NAN;
 }
 extern "C" void apop_b200_ols_score(apop_data* d, gsl_vector* g, apop_model* m) {
     LOCK;
     if (!g) return;
-    OlsEval o = ols_entry(d, m);
+    OlsEval o = ols_entry(d, m, true);
     if (o.ok) store_score(g, o.g.data(), o.g.size(), 1.0);
     else fill_nan(g);
 }
@@ -691,6 +813,30 @@ extern "C" double apop_b200_ll_score(apop_b200_family family, apop_data* d, cons
     case APOP_B200_EXPONENTIAL: ll = apop_b200_exponential_ll(d, &m); if (score) apop_b200_exponential_score(d, &g, &m); break;
     case APOP_B200_GAMMA: ll = apop_b200_gamma_ll(d, &m); if (score) apop_b200_gamma_score(d, &g, &m); break;
     case APOP_B200_LOGNORMAL: ll = apop_b200_lognormal_ll(d, &m); if (score) apop_b200_lognormal_score(d, &g, &m); break;
+    case APOP_B200_BERNOULLI: ll = apop_b200_bernoulli_ll(d, &m); if (score) apop_b200_bernoulli_score(d, &g, &m); break;
+    case APOP_B200_BETA: ll = apop_b200_beta_ll(d, &m); if (score) apop_b200_beta_score(d, &g, &m); break;
+    case APOP_B200_DIRICHLET: ll = apop_b200_dirichlet_ll(d, &m); if (score) apop_b200_dirichlet_score(d, &g, &m); break;
+    case APOP_B200_YULE: ll = apop_b200_yule_ll(d, &m); if (score) apop_b200_yule_score(d, &g, &m); break;
+    case APOP_B200_ZIPF:
+    case APOP_B200_T: {
+        // no analytic score in the reference either: apop_score falls back to apop_numerical_gradient
+        // (apop_mle.m4.c:92-143, gsl_deriv_central's 5-point rule at delta = 1e-3) over the device LL
+        long double (*f)(apop_data*, apop_model*) = family == APOP_B200_ZIPF ? apop_b200_zipf_ll : apop_b200_t_ll;
+        ll = f(d, &m);
+        if (score) {
+            std::vector<double> b(beta, beta + P);
+            v.data = b.data();
+            const double h = 1e-3, at[4] = {-h, -h / 2, h / 2, h};
+            for (size_t j = 0; j < P; j++) {
+                double fv[4];
+                for (int q = 0; q < 4; q++) { b[j] = beta[j] + at[q]; fv[q] = (double)f(d, &m); }
+                b[j] = beta[j];
+                const double r3 = 0.5 * (fv[3] - fv[0]), r5 = (4.0 / 3.0) * (fv[2] - fv[1]) - (1.0 / 3.0) * r3;
+                score[j] = r5 / h;
+            }
+        }
+        break;
+    }
     default: set_error("unknown family %d", (int)family);
     }
     return (double)ll;

@@ -30,7 +30,12 @@ static bool device_categories(Resident* r, size_t max_cats, std::vector<double>&
             !cuda_ok(next_distinct_launch(r->tiles, r->n_rows, r->n_tiles, ycol, r->cols, above, c == 0, d_key, grid, R.stream), "next_distinct launch")) return false;
         R.launches++;
         if (!cuda_ok(cudaMemcpyAsync(&key, d_key, 8, cudaMemcpyDeviceToHost, R.stream), "D2H key") ||
-            !cuda_ok(cudaStreamSynchronize(R.stream), "prep sync")) return false;
+            !cuda_ok(cudaStreamSynchronize(R.stream), "prep sync")) {
+            // leaving a loop of collectives on a local error would desynchronise the ranks: poison the
+            // communicator so that this rank fails loudly from here on (its peers time out and do the same)
+            if (R.nranks > 1) R.comm_failed = true;
+            return false;
+        }
         // the smallest candidate over the ranks: every rank publishes its own in its slot of a sum
         double mine = (key == ~0ull) ? INFINITY : key_to_double(key);
         if (R.nranks > 1) {
@@ -85,6 +90,7 @@ static int prep_outcome_locked(apop_data* d, double* cats_out, size_t max_cats, 
         sync_host = 0;
     } else {
         r->y_col0 = (d->vector == nullptr);
+        r->recoded = false;   // a fresh prep reads the raw outcomes of the host copy
         if (!upload(r, d)) {
             free_resident(r);
             if (it != R.reg.end()) R.reg.erase(it);
@@ -105,6 +111,8 @@ static int prep_outcome_locked(apop_data* d, double* cats_out, size_t max_cats, 
         for (size_t c = 0; c < cats.size(); c++) tab.v[c] = cats[c];
         if (!cuda_ok(recode_launch(r->tiles, r->n_rows, r->n_tiles, r->k, r->cols, tab, R.stream), "recode launch")) return 1;
         R.launches++;
+        r->recoded = true; r->recode_pending = !sync_host; r->cats = tab;
+        r->memo_valid = false;
         if (ncat) *ncat = cats.size();
         if (cats_out) for (size_t c = 0; c < cats.size(); c++) cats_out[c] = cats[c];
     }
@@ -139,6 +147,7 @@ static int prep_outcome_locked(apop_data* d, double* cats_out, size_t max_cats, 
         }
         lap("host column 0 := 1");
         r->y_col0 = false;   // the host copy now has the reference's post-prep shape
+        r->sig = host_sig(d);  // ... and that shape is what the resident copy corresponds to
     }
     return 0;
 }

@@ -29,6 +29,11 @@ static Entry entry_of(apop_b200_family f) {
     default: return {nullptr, nullptr};
     }
 }
+bool is_device_entry(void* fn) {
+    for (int f = 0; f < (int)APOP_B200_MODEL_COUNT; f++)
+        if (fn && (void*)entry_of((apop_b200_family)f).ll == fn) return true;
+    return false;
+}
 static std::unordered_map<apop_model*, ll_fn>& saved_ll() {
     static std::unordered_map<apop_model*, ll_fn> m;
     return m;

@@ -16,6 +16,19 @@ static void data_shape(const apop_data* d, size_t& n, int& k, bool& has_y, bool&
     has_w = d->weights != nullptr;
 }
 
+HostSig host_sig(const apop_data* d) {
+    HostSig g;
+    if (d->matrix) { g.m = d->matrix->data; g.m1 = d->matrix->size1; g.m2 = d->matrix->size2; g.tda = d->matrix->tda; }
+    if (d->vector) { g.v = d->vector->data; g.vn = d->vector->size; g.vs = d->vector->stride; }
+    if (d->weights) { g.w = d->weights->data; g.wn = d->weights->size; }
+    return g;
+}
+// a registry entry whose host header no longer looks like what was uploaded (a new apop_data allocated at
+// the address of a freed one, or the same one reshaped by a prep) must not be served from the stale copy
+static bool sig_stale(const Resident* r, const apop_data* d) {
+    return !r->synthetic && !(r->sig == host_sig(d));
+}
+
 bool upload(Resident* r, const apop_data* d) {
     Runtime& R = rt();
     size_t n;
@@ -43,6 +56,11 @@ bool upload(Resident* r, const apop_data* d) {
     r->n_rows = n; r->k = k; r->has_y = hy || col0; r->has_w = hw; r->cols = cols; r->n_tiles = n_tiles;
     r->memo_valid = false; r->have_lgamma_y = false; r->have_poisson = false; r->have_gamma = false; r->consts.clear(); r->dirty = false;
     r->n_global_epoch = ~0ull;
+    r->sig = host_sig(d);
+    // resample counts and the per-row lgamma column belong to the rows that were resident before
+    if (r->counts) { cudaFree(r->counts); r->counts = nullptr; }
+    r->counts_m = 0;
+    if (r->lgy) { cudaFree(r->lgy); r->lgy = nullptr; }
     if (!need) return true;
 
     // Staged, pipelined upload.  Chunks of rows are gathered from the caller's (pageable,
@@ -120,6 +138,10 @@ bool upload(Resident* r, const apop_data* d) {
                                      r->tiles + (r0 / TILE_ROWS) * (size_t)cols * TILE_ROWS, R.stream, col0), "tile_pack");
         ok = ok && cuda_ok(cudaEventRecord(R.pin_ev[buf], R.stream), "event");
     }
+    // the outcome was recoded on the device while the host copy kept its raw values (prep_outcome with
+    // sync_host = 0): a refresh from that host copy applies the same category table again
+    if (ok && r->recoded && r->recode_pending && r->has_y)
+        ok = cuda_ok(recode_launch(r->tiles, r->n_rows, r->n_tiles, r->k, r->cols, r->cats, R.stream), "recode launch");
     ok = ok && cuda_ok(cudaStreamSynchronize(R.stream), "pin sync");
     if (trace)
         fprintf(stderr, "[apop_b200 pin] %.3f GB in %.3f s (%d chunks of %zu rows, %d threads): gather %.3f s, waiting for the copy engine %.3f s\n",
@@ -136,6 +158,7 @@ extern "C" int apop_b200_pin(apop_data* d) {
     auto it = R.reg.find(d);
     Resident* r = (it != R.reg.end()) ? it->second : new Resident();
     if (r->synthetic) return 0;
+    if (it != R.reg.end() && sig_stale(r, d)) { r->dirty = true; r->recoded = false; r->y_col0 = false; }
     if (it != R.reg.end() && !r->dirty) return 0;   // already resident (e.g. by the device prep); apop_b200_invalidate forces a refresh
     if (!upload(r, d)) {
         if (it == R.reg.end()) free_resident(r);
@@ -178,6 +201,7 @@ Resident* acquire(apop_data* d) {
     auto it = R.reg.find(d);
     if (it != R.reg.end()) {
         Resident* r = it->second;
+        if (sig_stale(r, d)) { r->dirty = true; r->recoded = false; r->y_col0 = false; }
         if (r->dirty && !upload(r, d)) return nullptr;
         if (r->consts_epoch != R.comm_epoch) {   // cached sums are sums over the ranks of one communicator
             r->memo_valid = false; r->have_lgamma_y = false; r->have_poisson = false; r->have_gamma = false; r->consts.clear();

@@ -96,6 +96,7 @@ extern "C" int apop_b200_init(int device) {
     *R.h_err = 0;
     if (!cuda_ok(cudaHostGetDevicePointer(&R.h_err_dev, R.h_err, 0), "cudaHostGetDevicePointer")) return 1;
     if (!cuda_ok(cudaMalloc(&R.d_vals, 64 * sizeof(double)), "cudaMalloc")) return 1;
+    { const char* e = getenv("APOP_B200_TIMING"); R.timing = e && e[0] == '1'; }
     R.ready = true;
     R.err.clear();
     return 0;
@@ -105,6 +106,7 @@ void free_resident(Resident* r) {
     if (!r) return;
     if (r->tiles) cudaFree(r->tiles);
     if (r->counts) cudaFree(r->counts);
+    if (r->lgy) cudaFree(r->lgy);
     delete r;
 }
 
@@ -123,7 +125,14 @@ extern "C" void apop_b200_finalize(void) {
     cudaFree(R.d_out);
     cudaFreeHost(R.h_out);
     cudaFreeHost(R.h_err);
-    for (int b2 = 0; b2 < 2; b2++) { if (R.pin_host[b2]) cudaFreeHost(R.pin_host[b2]); if (R.pin_dev[b2]) cudaFree(R.pin_dev[b2]); R.pin_host[b2] = nullptr; R.pin_dev[b2] = nullptr; }
+    for (int b2 = 0; b2 < 2; b2++) {
+        if (R.pin_host[b2]) cudaFreeHost(R.pin_host[b2]);
+        if (R.pin_dev[b2]) cudaFree(R.pin_dev[b2]);
+        R.pin_host[b2] = nullptr; R.pin_dev[b2] = nullptr;
+        // events belong to the device they were created on: a later init on another device makes its own
+        if (R.pin_ev[b2]) { cudaEventDestroy(R.pin_ev[b2]); R.pin_ev[b2] = nullptr; }
+        if (R.pin_copied[b2]) { cudaEventDestroy(R.pin_copied[b2]); R.pin_copied[b2] = nullptr; }
+    }
     R.pin_cap = 0;
     cudaFree(R.d_vals);
     if (R.d_beta) { cudaFree(R.d_beta); R.d_beta = nullptr; }
@@ -146,6 +155,7 @@ extern "C" double apop_b200_pass_timer_total_ms(unsigned long long* n) {
     return rt().total_ms;
 }
 extern "C" void apop_b200_set_auto_pin(int on) { rt().auto_pin = on != 0; }
+extern "C" void apop_b200_set_timing(int on) { rt().timing = on != 0; }
 
 // --------------------------------------------------------------------------
 //  NCCL, bound at run time (torch's bundled libnccl if it is already loaded in
@@ -183,6 +193,7 @@ extern "C" int apop_b200_comm_init(int nranks, int rank, const void* id128) {
     if (!require_ready() || !nccl_load()) return 1;
     Runtime& R = rt();
     cudaSetDevice(R.device);
+    if (R.comm || R.p2p_active || R.p2p_local) apop_b200_comm_finalize();   // never leak an earlier communicator
     NcclId id;
     memcpy(&id, id128, sizeof id);
     if (!nccl_ok(R.nccl.CommInitRank(&R.comm, nranks, id, rank), "ncclCommInitRank")) return 1;
@@ -207,6 +218,7 @@ extern "C" int apop_b200_comm_finalize(void) {
     if (R.p2p_local) { cudaFree(R.p2p_local); R.p2p_local = nullptr; }
     R.nranks = 1;
     R.rank = 0;
+    R.comm_failed = false;
     R.comm_epoch++;
     return 0;
 }
@@ -265,7 +277,9 @@ FinalizeCtx make_fin(int nout) {
     FinalizeCtx f;
     memset(&f, 0, sizeof f);
     f.nranks = 1;
-    f.spin_limit = 40000000ull;   // ~10 s of 64 ns sleeps + loads, then the error flag
+    static unsigned long long spin_env = 0;   // ~10 s of 64 ns sleeps + loads, then the error flag (tests shorten it)
+    if (!spin_env) { const char* e = getenv("APOP_B200_P2P_SPIN_LIMIT"); spin_env = e ? strtoull(e, nullptr, 10) : 0; if (!spin_env) spin_env = 40000000ull; }
+    f.spin_limit = spin_env;
     f.err = R.h_err_dev;
     if (R.nranks > 1 && R.p2p_active && nout <= R.p2p_slot) {
         f.nranks = R.nranks; f.rank = R.rank; f.seq = ++R.p2p_seq; f.slot = R.p2p_slot;
@@ -278,9 +292,19 @@ FinalizeCtx make_fin(int nout) {
 // complete a reduction launched with `fin`: `n` doubles, summed over all ranks, end up in h_out
 bool reduce_and_fetch(size_t n, const FinalizeCtx& fin) {
     Runtime& R = rt();
+    if (R.comm_failed && R.nranks > 1) {
+        // sticky: after a timeout the ranks' sequence counters are out of step, and a later pass could add a
+        // slot its peer has already overwritten -- fail every reduction until the communicator is rebuilt
+        cudaStreamSynchronize(R.stream);
+        return set_error("the communicator failed earlier (a peer never arrived); call apop_b200_comm_finalize and re-initialise it");
+    }
     if (fin.host_out) {   // the kernel published (and, with peers, exchanged) the result itself
         if (!cuda_ok(cudaStreamSynchronize(R.stream), "stream sync")) return false;
-        if (*R.h_err) { *R.h_err = 0; return set_error("fused allreduce: a peer rank never arrived (sequence %llu)", fin.seq); }
+        if (*R.h_err) {
+            *R.h_err = 0;
+            R.comm_failed = true;
+            return set_error("fused allreduce: a peer rank never arrived (sequence %llu)", fin.seq);
+        }
         return true;
     }
     if (R.comm && R.nranks > 1)

@@ -154,7 +154,15 @@ __device__ __forceinline__ void grid_finalize(const double* __restrict__ partial
     } else {
         for (int v = threadIdx.x; v < nout; v += blockDim.x) {
             double s = 0.0, c = 0.0;
-            for (unsigned b = 0; b < gridDim.x; b++) {
+            unsigned b = 0;
+            for (; b + 4 <= gridDim.x; b += 4) {   // four loads in flight per dependent add chain (same order of additions)
+                double x[4], e;
+#pragma unroll
+                for (int u = 0; u < 4; u++) x[u] = __ldcg(partials + (size_t)(b + u) * nout + v);
+#pragma unroll
+                for (int u = 0; u < 4; u++) { two_sum(s, x[u], s, e); c += e; }
+            }
+            for (; b < gridDim.x; b++) {
                 double e;
                 two_sum(s, __ldcg(partials + (size_t)b * nout + v), s, e);
                 c += e;

@@ -42,9 +42,10 @@ static void *dev(const char *name) {
 int apop_b200_family_of(apop_model *m) {
     static const char *names[] = {"apop_b200_probit_ll", "apop_b200_logit_ll", "apop_b200_poisson_ll", "apop_b200_normal_ll",
                                   "apop_b200_ols_ll", "apop_b200_poisson_reg_ll", "apop_b200_exponential_ll",
-                                  "apop_b200_gamma_ll", "apop_b200_lognormal_ll"};
+                                  "apop_b200_gamma_ll", "apop_b200_lognormal_ll", "apop_b200_bernoulli_ll", "apop_b200_beta_ll",
+                                  "apop_b200_zipf_ll", "apop_b200_dirichlet_ll", "apop_b200_t_ll", "apop_b200_yule_ll"};
     if (!m || !m->log_likelihood) return -1;
-    for (int f = 0; f < 9; f++) { void *p = dlsym(RTLD_DEFAULT, names[f]); if (p && p == (void *)m->log_likelihood) return f; }
+    for (int f = 0; f < 15; f++) { void *p = dlsym(RTLD_DEFAULT, names[f]); if (p && p == (void *)m->log_likelihood) return f; }
     return -1;
 }
 
@@ -119,21 +120,109 @@ apop_data *apop_data_covariance(const apop_data *in) {
     return out;
 }
 
-/* ---- covariance of an estimate: inverse observed information ----------------------- */
-apop_data *apop_model_numerical_covariance(apop_data *data, apop_model *m) {
+/* general inverse (Gauss-Jordan with partial pivoting), for Hessians that are not positive definite */
+static int general_inverse(const double *A, double *inv, size_t n) {
+    long double *W = malloc(sizeof(long double) * n * 2 * n);
+    for (size_t i = 0; i < n; i++) for (size_t j = 0; j < 2 * n; j++) W[i * 2 * n + j] = j < n ? A[i * n + j] : (j - n == i ? 1 : 0);
+    for (size_t c = 0; c < n; c++) {
+        size_t piv = c;
+        for (size_t i = c + 1; i < n; i++) if (fabsl(W[i * 2 * n + c]) > fabsl(W[piv * 2 * n + c])) piv = i;
+        if (!(fabsl(W[piv * 2 * n + c]) > 0)) { free(W); return 1; }
+        if (piv != c) for (size_t j = 0; j < 2 * n; j++) { long double t = W[c * 2 * n + j]; W[c * 2 * n + j] = W[piv * 2 * n + j]; W[piv * 2 * n + j] = t; }
+        const long double d = W[c * 2 * n + c];
+        for (size_t j = 0; j < 2 * n; j++) W[c * 2 * n + j] /= d;
+        for (size_t i = 0; i < n; i++) {
+            if (i == c) continue;
+            const long double f = W[i * 2 * n + c];
+            if (f != 0) for (size_t j = 0; j < 2 * n; j++) W[i * 2 * n + j] -= f * W[c * 2 * n + j];
+        }
+    }
+    for (size_t i = 0; i < n; i++) for (size_t j = 0; j < n; j++) inv[i * n + j] = (double)W[i * 2 * n + n + j];
+    free(W);
+    return 0;
+}
+
+/* ---- second derivatives ----------------------------------------------------------------
+ * apop_model_hessian (apop_mle.m4.c:187-223): the numeric gradient (gsl_deriv_central's 5-point rule
+ * at delta, :92-108) of every score component, the two estimates of each off-diagonal element averaged.
+ * The reference differentiates one component at a time (4 P score passes each); one score pass returns
+ * all P components, so perturbing parameter j serves column j of every component: 4 P passes in all.
+ * The score comes from the vtable (device entry) or, without one, from apop_numerical_gradient. */
+apop_data *apop_model_hessian(apop_data *data, apop_model *model, double delta) {
+    if (!model || !model->parameters) return NULL;
+    if (!delta) { apop_mle_settings *mp = apop_settings_get_grp(model, "apop_mle"); delta = mp ? mp->delta : 1e-3; }
+    gsl_vector *beta = apop_data_pack(model->parameters, NULL);
+    if (!beta) return NULL;
+    const size_t P = beta->size;
+    apop_data *out = apop_data_calloc(P, P, 0);
+    gsl_vector *work = gsl_vector_alloc(P), *sc[4];
+    for (int q = 0; q < 4; q++) sc[q] = gsl_vector_alloc(P);
+    const double at[4] = {-delta, -delta / 2, delta / 2, delta};
+    for (size_t j = 0; j < P; j++) {
+        for (int q = 0; q < 4; q++) {
+            memcpy(work->data, beta->data, sizeof(double) * P);
+            work->data[j] += at[q];
+            apop_data_unpack(work, model->parameters);
+            apop_score(data, sc[q], model);
+        }
+        for (size_t k = 0; k < P; k++) {   /* d score_k / d beta_j */
+            const double r3 = 0.5 * (sc[3]->data[k] - sc[0]->data[k]);
+            const double r5 = (4.0 / 3.0) * (sc[2]->data[k] - sc[1]->data[k]) - (1.0 / 3.0) * r3;
+            const double dv = r5 / delta;
+            out->matrix->data[k * P + j] += dv / 2;
+            out->matrix->data[j * P + k] += dv / 2;
+        }
+    }
+    apop_data_unpack(beta, model->parameters);
+    for (int q = 0; q < 4; q++) gsl_vector_free(sc[q]);
+    gsl_vector_free(work); gsl_vector_free(beta);
+    return out;
+}
+
+/* Observed information -d2LL/db db' at the model's parameters, P x P row-major: one device pass where the
+ * family has an analytic form (probit, binary and multinomial logit, Poisson regression, OLS), else the
+ * negated numeric Hessian above.  Returns 0 on success; *analytic tells which one it was. */
+int apop_b200_observed_information(apop_data *data, apop_model *m, double *H, int *analytic) {
+    if (!m || !m->parameters || !H) return 1;
     info_fn information = (info_fn)dev("apop_b200_information");
     const int fam = apop_b200_family_of(m);
-    if (!information || fam < 0 || !m->parameters) return NULL;
     gsl_vector *b = apop_data_pack(m->parameters, NULL);
+    if (!b) return 1;
     const size_t P = b->size;
+    int rc = 1;
+    if (analytic) *analytic = 0;
+    if (information && (fam == 0 || fam == 1 || fam == 4 || fam == 5)) {
+        rc = information(fam, data, b->data, P, H);
+        if (rc == 0 && analytic) *analytic = 1;
+    }
+    if (rc != 0) {
+        apop_data *hess = apop_model_hessian(data, m, 0);
+        if (hess) {
+            for (size_t i = 0; i < P * P; i++) H[i] = -hess->matrix->data[i];
+            apop_data_free(hess);
+            rc = 0;
+        }
+    }
+    gsl_vector_free(b);
+    return rc;
+}
+
+/* ---- covariance of an estimate: inverse observed information (apop_mle.m4.c:239-265) ------------ */
+apop_data *apop_model_numerical_covariance(apop_data *data, apop_model *m) {
+    if (!m || !m->parameters) return NULL;
+    gsl_vector *b = apop_data_pack(m->parameters, NULL);
+    if (!b) return NULL;
+    const size_t P = b->size;
+    gsl_vector_free(b);
     double *H = malloc(sizeof(double) * P * P);
     apop_data *cov = NULL;
-    if (information(fam, data, b->data, P, H) == 0) {
+    if (apop_b200_observed_information(data, m, H, NULL) == 0) {
         cov = apop_data_calloc(P, P, 0);
-        if (spd_inverse(H, cov->matrix->data, P)) { cov->error = 'm'; }
-        apop_data_add_page(m->parameters, cov, "<Covariance>");
+        /* -(hessian)^-1 = (information)^-1; Cholesky when it is positive definite, else a general inverse */
+        if (spd_inverse(H, cov->matrix->data, P) && general_inverse(H, cov->matrix->data, P)) cov->error = 'm';
+        if (!apop_data_get_page(m->parameters, "<Covariance>")) apop_data_add_page(m->parameters, cov, "<Covariance>");
     }
-    free(H); gsl_vector_free(b);
+    free(H);
     return cov;
 }
 

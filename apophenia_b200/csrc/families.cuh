@@ -138,7 +138,7 @@ struct FamOls {
         const double e = xb - y;
         o.s[0] = e;
         o.s[1] = e * e;
-        o.s[2] = log(w);
+        o.s[2] = (aux[0] != 0.0) ? w * e * e : log(w);   // aux[0]: the un-prepped score's sum w e^2 (capi_models.cu)
         o.d = w * e;
         return o;
     }

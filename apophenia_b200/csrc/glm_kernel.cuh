@@ -137,10 +137,6 @@ cudaError_t glm_wide_launch(GlmFam fam, int k, int cols, bool has_w, const GlmLa
 int glm_wide_blocks_per_sm(GlmFam fam, int k);
 int glm_wide_tiles_per_block(int k);   // 1 for the cooperative variant (k <= 256), else warps per block
 
-// TMA-streamed variant (glm_tma.cu), probit, k in {16, 20, 24, 32}; 0 blocks = not available
-cudaError_t glm_tma_launch_probit(int k, const GlmLaunch& L, const GlmParams& prm);
-int glm_tma_blocks_per_sm_probit(int k);
-
 // defined in glm_<family>.cu
 cudaError_t glm_launch(GlmFam fam, int k, bool has_w, const GlmLaunch& L, const GlmParams& prm);
 int glm_blocks_per_sm(GlmFam fam, int k, bool has_w);

@@ -87,6 +87,13 @@ apop_data *apop_data_calloc(size_t size1, size_t size2, int size3) {
 }
 void apop_data_free(apop_data *d) {
     if (!d) return;
+    { /* a resident copy keyed by this address must die with it: the next apop_data malloc'ed at the same
+       * address would otherwise be evaluated against stale HBM contents (and the copy would leak) */
+        static int (*unpin)(apop_data *) = NULL;
+        static int looked = 0;
+        if (!looked) { unpin = (int (*)(apop_data *))dlsym(RTLD_DEFAULT, "apop_b200_unpin"); looked = unpin != NULL; }
+        if (unpin) unpin(d);
+    }
     apop_data_free(d->more);
     gsl_vector_free(d->vector);
     gsl_matrix_free(d->matrix);

@@ -74,7 +74,9 @@ apop_mle_report apop_mle_last_report(void);
 int apop_b200_family_of(apop_model *m);      /* which device family is installed in m (-1: none) */
 void apop_b200_install_estimates(void);      /* closed-form estimate methods of poisson / normal / ols */
 apop_data *apop_data_covariance(const apop_data *in);
-apop_data *apop_model_numerical_covariance(apop_data *data, apop_model *m);   /* -H^-1 from one information pass */
+apop_data *apop_model_hessian(apop_data *data, apop_model *model, double delta);   /* numeric: apop_mle.m4.c:187-223 */
+int apop_b200_observed_information(apop_data *data, apop_model *m, double *H, int *analytic);   /* device pass, else numeric */
+apop_data *apop_model_numerical_covariance(apop_data *data, apop_model *m);   /* (observed information)^-1 */
 /* apop_bootstrap_cov (apop_bootstrap.m4.c:122): gsl_rng* replaced by a seed; iterations <= 0 means 1000 */
 apop_data *apop_bootstrap_cov(apop_data *data, apop_model *model, uint64_t seed, int iterations, apop_data **boot_store);
 /* apop_mcmc_settings (apop.m4.h, defaults apop_mcmc.m4.c:35-43) + initial proposal scale, seed, chain count */

@@ -37,7 +37,7 @@ __device__ __forceinline__ void dmma_884(double& d0, double& d1, double a, doubl
 template <int KB, int C1, int HYB_STAGES>
 __global__ void __launch_bounds__(LOGIT_THREADS, HYB_STAGES == 2 ? 3 : 4)
 logit_hybrid_kernel(const double* __restrict__ tiles, const unsigned long long n_rows,
-                    const unsigned long long n_tiles, const int K, const __grid_constant__ LogitParams prm,
+                    const unsigned long long n_tiles, const int K, const int cols, const __grid_constant__ LogitParams prm,
                     double* __restrict__ partials, unsigned int* __restrict__ ticket,
                     double* __restrict__ out, const __grid_constant__ FinalizeCtx fin) {
     constexpr int WARPS = LOGIT_THREADS / 32;
@@ -52,7 +52,6 @@ logit_hybrid_kernel(const double* __restrict__ tiles, const unsigned long long n
     double* slab = ring + HYB_STAGES * TILE_D;            // R^T[c][row], 8 rows of 32, same swizzle
     const unsigned long long gwarp = (unsigned long long)blockIdx.x * WARPS + warp;
     const unsigned long long nwarps = (unsigned long long)gridDim.x * WARPS;
-    const int cols = K + 1;
 
     // columns K..KB-1 of both stages and the slab rows of the padding categories are zero for the
     // whole kernel (the prefetch never writes them): no predicate in the loops below
@@ -236,7 +235,7 @@ static cudaError_t hyb_launch_st(const LogitLaunch& L, const LogitParams& prm) {
     static_assert((size_t)(LOGIT_THREADS / 32) * (1 + KB * C1) + (1 + KB * C1) <= hyb_smem<KB, ST>() / sizeof(double), "reduction scratch must fit the rings");
     static bool done = false;
     if (!done) { cudaFuncSetAttribute(logit_hybrid_kernel<KB, C1, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hyb_smem<KB, ST>()); done = true; }
-    logit_hybrid_kernel<KB, C1, ST><<<L.grid, LOGIT_THREADS, hyb_smem<KB, ST>(), L.stream>>>(L.tiles, L.n_rows, L.n_tiles, L.k, prm, L.partials, L.ticket, L.out, L.fin);
+    logit_hybrid_kernel<KB, C1, ST><<<L.grid, LOGIT_THREADS, hyb_smem<KB, ST>(), L.stream>>>(L.tiles, L.n_rows, L.n_tiles, L.k, L.cols, prm, L.partials, L.ticket, L.out, L.fin);
     return cudaGetLastError();
 }
 template <int KB, int C1, int ST>

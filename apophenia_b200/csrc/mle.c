@@ -77,12 +77,12 @@ static int line_search(mle_info *I, size_t n, double *x, double *f, double *g, c
     if (!(d0 < 0)) return 1;
     double *xt = malloc(sizeof(double) * n), *gt = malloc(sizeof(double) * n);
     ls_pt lo = {0, f0, d0}, hi = {0, 0, 0}, cur;
-    int have_hi = 0, rc = 1;
+    int have_hi = 0, rc = 1, any_finite = 0;
     double a = a0;
     for (int it = 0; it < 40; it++) {
         const int bad = ls_eval(I, n, x, p, a, xt, gt, &cur);
-        if (bad) { /* NaN or inf: treat as too long a step */
-            I->nan_seen = 0;
+        if (!bad) any_finite = 1;
+        if (bad) { /* NaN or inf: treat as too long a step (a search whose trials are ALL NaN ends with -1 below) */
             hi = (ls_pt){a, INFINITY, 0}; have_hi = 1;
             a = lo.a + 0.25 * (a - lo.a);
             if (a - lo.a < 1e-16 * fmax(1.0, lo.a)) break;
@@ -129,6 +129,10 @@ static int line_search(mle_info *I, size_t n, double *x, double *f, double *g, c
     }
     if (rc == 0) { memcpy(x, xt, sizeof(double) * n); memcpy(g, gt, sizeof(double) * n); *f = cur.f; }
     free(xt); free(gt);
+    /* NaN trials next to finite ones are over-long steps; NaN everywhere is the reference's
+     * negshell longjmp: the fit ends with status -1 (apop_mle.m4.c:310,451-453) */
+    if (any_finite) I->nan_seen = 0;
+    else if (I->nan_seen) return -1;
     return rc;
 }
 
@@ -244,7 +248,6 @@ static int minimize_simplex(mle_info *I, const apop_mle_settings *mp, double *x,
 /* "Newton": damped Newton on the score with the observed information computed by one
  * device pass (apop_b200_information), in place of the reference's finite-difference
  * Jacobian root finder (apop_mle.m4.c:885-916). */
-typedef int (*info_fn)(int, apop_data *, const double *, size_t, double *);
 static int chol_solve(double *A, double *b, size_t n) { /* A = L L', solves in place; 1 if not PD */
     for (size_t j = 0; j < n; j++) {
         long double s = A[j * n + j];
@@ -263,15 +266,19 @@ static int chol_solve(double *A, double *b, size_t n) { /* A = L L', solves in p
 }
 static int minimize_newton(mle_info *I, const apop_mle_settings *mp, double *x, int *iters, double *gnorm_out) {
     const size_t n = I->n;
-    info_fn information = (info_fn)dlsym(RTLD_DEFAULT, "apop_b200_information");
     const int fam = apop_b200_family_of(I->model);
-    if (!information || fam < 0) { fprintf(stderr, "Newton needs apop_b200_information and a registered device model\n"); return -1; }
+    if (fam < 0) { fprintf(stderr, "Newton needs a registered device model\n"); return -1; }
     double *g = malloc(sizeof(double) * n), *p = malloc(sizeof(double) * n), *H = malloc(sizeof(double) * n * n);
     double f = fdf(x, I, g), gnorm = nrm(g, n);
     int it = 0, status = isnan(f) ? -1 : 0;
     while (status == 0 && it < mp->max_iterations && !converged(mp, gnorm, f)) {
         it++;
-        if (information(fam, I->data, x, n, H)) { status = -1; break; }
+        /* the information at x: one device pass (probit, logit incl. multinomial, Poisson regression, OLS),
+         * else the reference's numeric Hessian of the score (apop_mle.m4.c:885-916 takes a finite-difference
+         * Jacobian for every model) */
+        memcpy(I->bv->data, x, sizeof(double) * n);
+        apop_data_unpack(I->bv, I->model->parameters);
+        if (apop_b200_observed_information(I->data, I->model, H, NULL)) { status = -1; break; }
         for (size_t i = 0; i < n; i++) p[i] = -g[i];
         double ridge = 0;
         int solved = 0;
@@ -296,8 +303,9 @@ static int minimize_newton(mle_info *I, const apop_mle_settings *mp, double *x, 
             const double pn = nrm(p, n), cap = 10 * (1 + nrm(x, n));
             if (!(pn <= cap)) for (size_t i = 0; i < n; i++) p[i] = isfinite(pn) && pn > 0 ? p[i] * cap / pn : -g[i] * cap / (gnorm > 0 ? gnorm : 1);
         }
-        if (line_search(I, n, x, &f, g, p, 1.0, 0.9)) break;
+        const int lrc = line_search(I, n, x, &f, g, p, 1.0, 0.9);
         if (I->nan_seen) { status = -1; break; }
+        if (lrc) break;
         gnorm = nrm(g, n);
         if (mp->verbose) printf("%5i f()=%.10g |gradient|=%.3g\n", it, f, gnorm);
     }
@@ -342,7 +350,12 @@ void apop_maximum_likelihood(apop_data *data, apop_model *dist) { /* apop_mle.m4
     apop_data_free(dist->info);
     dist->info = apop_data_alloc(4, 0, 0);
     apop_data_add_page(NULL, dist->info, "<Info>");
-    const double nobs = data ? (data->matrix ? data->matrix->size1 : (data->vector ? data->vector->size : 0)) : 0;
+    double nobs = data ? (data->matrix ? data->matrix->size1 : (data->vector ? data->vector->size : 0)) : 0;
+    { /* row-sharded data: the information criteria count the rows of ALL ranks */
+        double (*global_rows)(apop_data *) = (double (*)(apop_data *))dlsym(RTLD_DEFAULT, "apop_b200_global_rows");
+        const double g = (global_rows && data) ? global_rows(data) : 0;
+        if (g > 0) nobs = g;
+    }
     dist->info->vector->data[0] = status;
     dist->info->vector->data[1] = ll;
     dist->info->vector->data[2] = 2 * (double)I.n - 2 * ll;

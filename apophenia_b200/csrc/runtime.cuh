@@ -12,6 +12,14 @@
 
 namespace apb {
 
+// what a host apop_data looked like when it was uploaded
+struct HostSig {
+    const void *m = nullptr, *v = nullptr, *w = nullptr;
+    size_t m1 = 0, m2 = 0, tda = 0, vn = 0, vs = 0, wn = 0;
+    bool operator==(const HostSig& o) const {
+        return m == o.m && v == o.v && w == o.w && m1 == o.m1 && m2 == o.m2 && tda == o.tda && vn == o.vn && vs == o.vs && wn == o.wn;
+    }
+};
 // A data set kept in HBM between optimizer iterations.
 struct Resident {
     size_t n_rows = 0;
@@ -44,6 +52,15 @@ struct Resident {
     // resample multiplicities for the batched path
     unsigned char* counts = nullptr;
     size_t counts_m = 0;
+    // per-row lgamma(y+1) in tile order (Poisson regression with resample counts), built on first use
+    double* lgy = nullptr;
+    // identity of the host buffers this copy was made from: a different apop_data allocated at the same
+    // address (or the same one reshaped) is re-uploaded instead of being served from the stale copy
+    HostSig sig;
+    // the outcome column was recoded on the device (apop_b200_prep_outcome): a dirty re-upload of a host
+    // copy that still holds the raw outcomes re-applies the table
+    bool recoded = false, recode_pending = false;
+    CatTable cats;
 };
 
 struct NcclApi {
@@ -62,6 +79,7 @@ struct Runtime {
     int num_sms = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timing = false;      // CUDA-event timing of every pass: opt-in (APOP_B200_TIMING=1 / apop_b200_set_timing(1))
     double* d_partials = nullptr;
     size_t partials_cap = 0;  // doubles
     unsigned int* d_ticket = nullptr;
@@ -91,6 +109,7 @@ struct Runtime {
     unsigned long long comm_epoch = 0;   // bumped whenever the set of ranks changes
     // fused allreduce over NVLink peer memory (CUDA IPC), see common.cuh grid_finalize
     bool p2p_active = false;
+    bool comm_failed = false;     // a collective timed out: every later reduction fails until the communicator is rebuilt
     int p2p_slot = 0;
     unsigned long long p2p_seq = 0;
     double* p2p_local = nullptr;                 // this rank's inbox + flags allocation

@@ -87,6 +87,16 @@ struct apop_model {
     char error;
 };
 
+/* ---- apop_lm_settings (apop.m4.h:1243-1249): the "apop_lm" settings group of apop_ols; the OLS entry
+ * reads input_distribution from it (model/apop_ols.c:135-136,163-166) */
+typedef struct {
+    int destroy_data;
+    apop_data *instruments;
+    char want_cov;
+    char want_expected_value;
+    apop_model *input_distribution;
+} apop_lm_settings;
+
 /* vtable signature for the score (apop.m4.h:531-533) */
 typedef void (*apop_score_type)(apop_data *d, gsl_vector *gradient, apop_model *params);
 #define apop_score_hash(m1) ((size_t)((m1)->log_likelihood ? (m1)->log_likelihood : (m1)->p))
@@ -130,6 +140,10 @@ unsigned long long apop_b200_launch_count(void);
 double apop_b200_last_pass_ms(void);
 void apop_b200_pass_timer_reset(void);
 double apop_b200_pass_timer_total_ms(unsigned long long *n_passes);
+/* Per-pass CUDA-event timing feeds the three calls above.  It is off by default (two event records and a
+ * query cost ~25 us per pass); switch it on here or with APOP_B200_TIMING=1.  With timing off the pass
+ * counter still runs and the millisecond figures stay 0. */
+void apop_b200_set_timing(int on);
 
 /* Multi-GPU: rows are sharded, one rank per process.  The 128-byte NCCL unique
  * id is produced on rank 0 and carried to the other ranks by the host program
@@ -166,6 +180,9 @@ int apop_b200_is_pinned(const apop_data *d);
 /* unpinned data policy: 0 = upload per call and drop (always correct, default),
  * 1 = pin on first sight and trust the caller to invalidate. */
 void apop_b200_set_auto_pin(int on);
+/* Rows of the whole data set behind d over all ranks (= its own rows on one GPU); 0 if d is not
+ * resident.  The information criteria of a sharded fit count these (apop_mle.m4.c:378-409). */
+double apop_b200_global_rows(apop_data *d);
 
 /* Synthetic, device-generated data sets in the resident layout (SURVEY 8(d),
  * recipe of tests/test_apop.c:889-907).  The returned apop_data is a host
@@ -186,6 +203,10 @@ int apop_b200_download(const apop_data *d, double *X_rowmajor, double *y, double
  *  (1..32 on the register-resident kernels, wider data on a two-sweep kernel);
  *  multinomial logit, the information matrix and the batched path take 1..32 and up to
  *  8 outcome categories.  Anything else is refused with NaN and model->error = 'd'.
+ *  A weights column is read by OLS only; probit, logit and the Poisson regression ignore it,
+ *  as the reference's do.  OLS serves every branch of ols_log_likelihood (model/apop_ols.c:129-172):
+ *  un-prepped data (outcome still in column 0), the <Predicted> and <Error variance> pages, and
+ *  the input_distribution of apop_lm_settings.
  * ------------------------------------------------------------------ */
 long double apop_b200_probit_ll(apop_data *d, apop_model *m);       /* replaces multiprobit_log_likelihood, model/apop_probit.c:104 */
 void apop_b200_probit_score(apop_data *d, gsl_vector *g, apop_model *m); /* replaces probit_dlog_likelihood, :130 */
@@ -259,10 +280,38 @@ typedef enum {
     APOP_B200_MAP_DEV2 = 2,        /* (x - p0)^2                (normal apply_me2)       */
     APOP_B200_MAP_POISSON = 3,     /* x==0?0: p0*x - lgamma(x+1), -inf if invalid (poisson apply_me) */
     APOP_B200_MAP_LOG = 4,         /* log(x)                                              */
-    APOP_B200_MAP_EXP = 5          /* exp(x)                                              */
+    APOP_B200_MAP_EXP = 5,         /* exp(x)                                              */
+    APOP_B200_MAP_ABS = 6,         /* |x|                       (apop_map only)           */
+    APOP_B200_MAP_SQRT = 7,        /* sqrt(x)                   (apop_map only)           */
+    APOP_B200_MAP_SCALE = 8,       /* p0 * x                    (apop_map only)           */
+    APOP_B200_MAP_POW = 9          /* x^p0                      (apop_map only)           */
 } apop_b200_map_fn;
 /* part: 'a' all (vector and matrix), 'v' vector only, 'm' matrix only */
 double apop_b200_map_sum(apop_data *d, apop_b200_map_fn fn, double p0, char part);
+
+/* apop_map with a materialised result (apop_mapply.m4.c:119-217, output shapes :300-313).  The reference
+ * applies a HOST function pointer per cell / row; a device library cannot, so the functions the models on
+ * this path map with -- and the elementary ones -- are offered as enums.
+ *   apop_b200_map       fn_d / fn_dp shapes, part 'a' | 'v' | 'm': the result has the shape of the input;
+ *                       out_vector (n_rows) and out_matrix (n_rows x k row-major) are caller buffers, either
+ *                       may be NULL; a part that is not mapped is copied through.
+ *   apop_b200_map_rows  fn_v / fn_vp / fn_r / fn_rp shapes, part 'r': one double per row into out (n_rows).
+ *                       param = k doubles for ROW_DOT and the per-row log-likelihood terms (the model's beta);
+ *                       aux = NULL or the two category values of the binary logit. */
+typedef enum {
+    APOP_B200_ROW_SUM = 0,             /* sum_j x_ij                                              */
+    APOP_B200_ROW_MEAN = 1,            /* mean_j x_ij                                             */
+    APOP_B200_ROW_SUMSQ = 2,           /* sum_j x_ij^2                                            */
+    APOP_B200_ROW_MAX = 3,
+    APOP_B200_ROW_MIN = 4,
+    APOP_B200_ROW_DOT = 5,             /* x_i . param              (apop_dot, one column)         */
+    APOP_B200_ROW_PROBIT_LL = 6,       /* biprobit_ll_row          model/apop_probit.c:83-88      */
+    APOP_B200_ROW_LOGIT2_LL = 7,       /* one_logit_row, C = 2     model/apop_probit.c:212-229    */
+    APOP_B200_ROW_POISSON_REG_LL = 8,  /* y x.b - exp(x.b) - lgamma(y+1)              */
+    APOP_B200_ROW_OLS_ERROR = 9        /* x_i . param - y_i        model/apop_ols.c:146-155       */
+} apop_b200_row_fn;
+int apop_b200_map(apop_data *d, apop_b200_map_fn fn, double p0, char part, double *out_vector, double *out_matrix);
+int apop_b200_map_rows(apop_data *d, apop_b200_row_fn fn, const double *param, size_t nparam, const double *aux, double *out);
 
 /* apop_dot(d, parameters) (apop_linear_algebra.m4.c:424-448): the N x c index X.B, row-major
  * into a caller buffer; B is k x c row-major (parameters->matrix).  On a dimension mismatch
@@ -286,9 +335,11 @@ int apop_b200_ols_gram(apop_data *d, double *xtx, double *xty);
 double apop_b200_ll_score(apop_b200_family family, apop_data *d, const double *beta, size_t P,
                           double *score);
 
-/* Observed information  -d2LL/dbeta dbeta' (P*P row-major) by one device pass
- * (replaces the numeric Hessian, apop_mle.m4.c:187-223).  PROBIT, LOGIT(binary),
- * POISSON_REG, OLS.  Returns 0 on success. */
+/* Observed information  -d2LL/dbeta dbeta' (P*P row-major, pack order) on the FP64 tensor path
+ * (replaces the numeric Hessian, apop_mle.m4.c:187-223).  PROBIT, LOGIT, POISSON_REG, OLS: one pass with
+ * P = k; multinomial LOGIT with P = k (C-1): sum_i x_i x_i' (x) (diag p_i - p_i p_i') from ceil((C-1) C / 8)
+ * passes.  Families without an analytic form get the reference's own numeric Hessian over the device
+ * score from the host side (apop_model_hessian in the host mirror).  Returns 0 on success. */
 int apop_b200_information(apop_b200_family family, apop_data *d, const double *beta, size_t P,
                           double *H);
 

@@ -948,3 +948,84 @@ double oracle_time_logit_ll(const double *X, size_t tda, const double *y, size_t
     free(cats);
     return t1 - t0;
 }
+
+/* ---- round 2 additions --------------------------------------------------------------------- */
+
+/* Observed information of the multinomial logit, -d2LL/dB dB' = sum_i (x_i x_i') (x) (diag p_i - p_i p_i'),
+ * P x P in pack order (index j*(C-1)+c), all in long double.  The reference has no analytic form (its
+ * Hessian is numeric, apop_mle.m4.c:187-223); this is the derivative of the commented-out score
+ * (model/apop_probit.c:244-289) and is what the device kernel is checked against. */
+void oracle_logit_information(const double *X, size_t tda, size_t N, size_t k, const double *B, size_t C,
+                              long double *H) {
+    const size_t C1 = C - 1, P = k * C1;
+    for (size_t q = 0; q < P * P; q++) H[q] = 0;
+    ld *row = malloc(sizeof(ld) * C1), *p = malloc(sizeof(ld) * C1), *W = malloc(sizeof(ld) * C1 * C1);
+    for (size_t i = 0; i < N; i++) {
+        const double *x = X + i * tda;
+        for (size_t c = 0; c < C1; c++) row[c] = dot_l(x, B + c, C1, k);
+        ld max = 0;
+        for (size_t c = 0; c < C1; c++) if (row[c] > max) max = row[c];
+        ld den = expl(-max);
+        for (size_t c = 0; c < C1; c++) den += expl(row[c] - max);
+        for (size_t c = 0; c < C1; c++) p[c] = expl(row[c] - max) / den;
+        for (size_t a = 0; a < C1; a++)
+            for (size_t b = 0; b < C1; b++) W[a * C1 + b] = (a == b ? p[a] : 0) - p[a] * p[b];
+        for (size_t j = 0; j < k; j++)
+            for (size_t j2 = 0; j2 < k; j2++) {
+                const ld xx = (ld)x[j] * x[j2];
+                for (size_t a = 0; a < C1; a++)
+                    for (size_t b = 0; b < C1; b++) H[(j * C1 + a) * P + j2 * C1 + b] += xx * W[a * C1 + b];
+            }
+    }
+    free(row); free(p); free(W);
+}
+
+/* Probit LL and score in EXACT mode over row blocks in parallel: every thread keeps long double
+ * partials of its contiguous block, the blocks are added in block order.  Same arithmetic per row as
+ * oracle_probit_ll / oracle_probit_score(ORACLE_EXACT); only the grouping of the additions differs
+ * (long double: 64-bit mantissa, so the grouping is far below the 1e-12 tolerance).  Used to check the
+ * 1e-8 fitted-parameter target at the full 100M x 32 size. */
+void oracle_probit_ll_score_exact_omp(const double *X, size_t tda, const double *y, size_t N, size_t k,
+                                      const double *beta, int threads, long double *ll_out, long double *g_out,
+                                      long double *abs_out) {
+    const int T = threads > 0 ? threads : omp_get_num_procs();
+    ld *pl = calloc((size_t)T, sizeof(ld)), *pg = calloc((size_t)T * k, sizeof(ld)), *pa = calloc((size_t)T * k, sizeof(ld));
+#pragma omp parallel num_threads(T)
+    {
+        const int t = omp_get_thread_num(), nt = omp_get_num_threads();
+        const size_t lo = N * (size_t)t / nt, hi = N * (size_t)(t + 1) / nt;
+        ld l = 0;
+        ld *g = pg + (size_t)t * k, *a = pa + (size_t)t * k;
+        oracle_probit_ll(X + lo * tda, tda, y + lo, hi - lo, k, beta, ORACLE_EXACT, &l);
+        oracle_probit_score(X + lo * tda, tda, y + lo, hi - lo, k, beta, ORACLE_EXACT, g, a);
+        pl[t] = l;
+    }
+    *ll_out = 0;
+    for (size_t j = 0; j < k; j++) { g_out[j] = 0; if (abs_out) abs_out[j] = 0; }
+    for (int t = 0; t < T; t++) {
+        *ll_out += pl[t];
+        for (size_t j = 0; j < k; j++) { g_out[j] += pg[(size_t)t * k + j]; if (abs_out) abs_out[j] += pa[(size_t)t * k + j]; }
+    }
+    free(pl); free(pg); free(pa);
+}
+
+/* The reference's bootstrap resample (apop_bootstrap.m4.c:143-149): for each of the N rows of the scratch
+ * set one gsl_rng_uniform_int draw and an apop_data_memcpy of a one-row view (matrix row + vector element),
+ * serial.  taus2 is replaced by xorshift (streams are "parity unpinned"); the memory traffic
+ * and the per-row call structure are what is timed.  Returns seconds. */
+static void copy_row(double *Xo, double *yo, const double *X, size_t tda, const double *y, size_t k, size_t dst, size_t src) {
+    memcpy(Xo + dst * k, X + src * tda, sizeof(double) * k);
+    yo[dst] = y[src];
+}
+double oracle_time_bootstrap_resample(const double *X, size_t tda, const double *y, size_t N, size_t k,
+                                      unsigned long long seed, double *Xo, double *yo) {
+    void (*volatile cp)(double *, double *, const double *, size_t, const double *, size_t, size_t, size_t) = copy_row;
+    unsigned long long s = seed * 0x9E3779B97F4A7C15ull + 1;
+    const double t0 = now_s();
+    for (size_t j = 0; j < N; j++) {
+        s ^= s << 13; s ^= s >> 7; s ^= s << 17;
+        const size_t r = (size_t)(((unsigned __int128)s * N) >> 64);
+        cp(Xo, yo, X, tda, y, k, j, r);
+    }
+    return now_s() - t0;
+}

@@ -138,6 +138,16 @@ double oracle_time_logit_ll(const double *X, size_t tda, const double *y, size_t
                             const double *B, size_t C, int threads, double *ll_out);
 int oracle_max_threads(void);
 
+/* round 2: multinomial-logit observed information (exact), the OpenMP EXACT probit pass used at the full
+ * 100M x 32 size, and the bootstrap row-copy loop of apop_bootstrap.m4.c:143-149 for the CPU baseline */
+void oracle_logit_information(const double *X, size_t tda, size_t N, size_t k, const double *B, size_t C,
+                              long double *H);
+void oracle_probit_ll_score_exact_omp(const double *X, size_t tda, const double *y, size_t N, size_t k,
+                                      const double *beta, int threads, long double *ll_out, long double *g_out,
+                                      long double *abs_out);
+double oracle_time_bootstrap_resample(const double *X, size_t tda, const double *y, size_t N, size_t k,
+                                      unsigned long long seed, double *Xo, double *yo);
+
 #ifdef __cplusplus
 }
 #endif

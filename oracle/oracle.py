@@ -297,5 +297,34 @@ def time_logit_ll(X, y, B, threads=0):
     return {"seconds": tot, "ll": ll.value}
 
 
+def logit_information(X, B, ncat):
+    """multinomial-logit observed information, P x P in pack order (long double)"""
+    X, Xp, tda = _mat(X); b, bp = _d(np.asarray(B).ravel())
+    k = X.shape[1]
+    P = k * (ncat - 1)
+    H, Hp = _ld(P * P)
+    lib().oracle_logit_information(Xp, _sz(tda), _sz(X.shape[0]), _sz(k), bp, _sz(ncat), Hp)
+    return H.reshape(P, P)
+
+
+def probit_ll_score_exact_omp(X, y, beta, threads=0):
+    """EXACT-mode probit LL, score and score scale over row blocks in parallel (long double)"""
+    X, Xp, tda = _mat(X); y, yp = _d(y); b, bp = _d(beta)
+    k = X.shape[1]
+    ll, llp = _ld(1); g, gp = _ld(k); a, ap = _ld(k)
+    lib().oracle_probit_ll_score_exact_omp(Xp, _sz(tda), yp, _sz(X.shape[0]), _sz(k), bp, C.c_int(threads), llp, gp, ap)
+    return ll[0], g, a
+
+
+def time_bootstrap_resample(X, y, seed=8):
+    """seconds of the reference's serial row-copy resample of all N rows (apop_bootstrap.m4.c:143-149)"""
+    X, Xp, tda = _mat(X); y, yp = _d(y)
+    Xo = np.empty_like(X); yo = np.empty_like(y)
+    f = lib().oracle_time_bootstrap_resample
+    f.restype = C.c_double
+    return float(f(Xp, _sz(tda), yp, _sz(X.shape[0]), _sz(X.shape[1]), C.c_ulonglong(seed),
+                   Xo.ctypes.data_as(C.POINTER(C.c_double)), yo.ctypes.data_as(C.POINTER(C.c_double))))
+
+
 def max_threads():
     return lib().oracle_max_threads()
