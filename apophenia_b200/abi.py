@@ -107,6 +107,7 @@ SIGNATURES = {
     "apop_b200_is_pinned": (C.c_int, [_PD]),
     "apop_b200_set_auto_pin": (None, [C.c_int]),
     "apop_b200_set_timing": (None, [C.c_int]),
+    "apop_b200_set_local_only": (None, [C.c_int]),
     "apop_b200_global_rows": (C.c_double, [_PD]),
     "apop_b200_map": (C.c_int, [_PD, C.c_int, C.c_double, C.c_char, _dp, _dp]),
     "apop_b200_map_rows": (C.c_int, [_PD, C.c_int, _dp, C.c_size_t, _dp, _dp]),

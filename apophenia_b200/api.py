@@ -17,7 +17,7 @@ from .abi import (B200Error, Data, Model, PROBIT, LOGIT, POISSON, NORMAL, OLS, P
                   ROW_POISSON_REG_LL, ROW_OLS_ERROR)
 
 __all__ = ["init", "finalize", "pin", "unpin", "invalidate", "is_pinned", "log_likelihood", "score",
-           "ll_score", "map_sum", "synth", "SynthData", "launch_count", "last_pass_ms", "pass_timer_reset", "set_timing",
+           "ll_score", "map_sum", "synth", "SynthData", "launch_count", "last_pass_ms", "pass_timer_reset", "set_timing", "set_local_only",
            "pass_timer", "probit_model", "logit_model", "vector_model", "Data", "Model", "B200Error",
            "PROBIT", "LOGIT", "POISSON", "NORMAL", "OLS", "POISSON_REG", "EXPONENTIAL", "GAMMA", "LOGNORMAL",
            "BERNOULLI", "BETA", "ZIPF", "DIRICHLET", "TDIST", "YULE", "comm_init_from_torch",
@@ -79,6 +79,11 @@ def last_pass_ms():
 def set_timing(on=True):
     """per-pass CUDA-event timing (off by default: it costs ~25 us per pass)"""
     _lib().apop_b200_set_timing(int(bool(on)))
+
+
+def set_local_only(on=True):
+    """evaluate this rank's rows only (no cross-GPU exchange) while on"""
+    _lib().apop_b200_set_local_only(int(bool(on)))
 
 
 def pass_timer_reset():

@@ -192,7 +192,7 @@ extern "C" int apop_b200_ll_score_batched(apop_b200_family family, apop_data* d,
         if (!cuda_ok(batched_launch((int)fam, L), "batched kernel launch")) break;
         time_end_record();
         R.launches += 2;
-        if (R.comm && R.nranks > 1 &&
+        if (R.comm && R.nranks > 1 && !R.local_only &&
             !nccl_ok(R.nccl.AllReduce(dOut, dOut, m * NOUT, 8, 0, R.comm, R.stream), "ncclAllReduce")) break;
         std::vector<double> h(m * NOUT);
         if (!cuda_ok(cudaMemcpyAsync(h.data(), dOut, m * NOUT * sizeof(double), cudaMemcpyDeviceToHost, R.stream), "D2H")) break;
@@ -249,7 +249,7 @@ extern "C" int apop_b200_bootstrap_counts(apop_data* d, size_t m, uint64_t seed)
     cudaMemsetAsync(r->counts, 0, bytes, R.stream);
     // the resample is of the global data set: ranks share seed, each keeps its own rows
     double n_global = (double)r->n_rows, offset = 0.0;
-    if (R.nranks > 1) {
+    if (R.nranks > 1 && !R.local_only) {
         // exclusive prefix of the shard sizes = this rank's first global row
         std::vector<double> sizes(R.nranks, 0.0);
         sizes[R.rank] = (double)r->n_rows;

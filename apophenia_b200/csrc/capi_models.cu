@@ -106,7 +106,7 @@ bool global_counts(Resident* r, double& n_rows, double& m_cells, double& v_cells
     Runtime& R = rt();
     if (r->n_global_epoch != R.comm_epoch) {   // one exchange per (data set, communicator), then cached
         double n = (double)r->n_rows;
-        if (R.nranks > 1 && !allreduce_scalar(&n)) return false;
+        if (R.nranks > 1 && !R.local_only && !allreduce_scalar(&n)) return false;
         r->n_global = n;
         r->n_global_epoch = R.comm_epoch;
     }

@@ -156,6 +156,14 @@ extern "C" double apop_b200_pass_timer_total_ms(unsigned long long* n) {
 }
 extern "C" void apop_b200_set_auto_pin(int on) { rt().auto_pin = on != 0; }
 extern "C" void apop_b200_set_timing(int on) { rt().timing = on != 0; }
+extern "C" void apop_b200_set_local_only(int on) {
+    LOCK;
+    Runtime& R = rt();
+    if (R.local_only == (on != 0)) return;
+    R.local_only = on != 0;
+    // memoised evaluations and cached constants are sums over a set of ranks: drop them with the set
+    R.comm_epoch++;
+}
 
 // --------------------------------------------------------------------------
 //  NCCL, bound at run time (torch's bundled libnccl if it is already loaded in
@@ -281,6 +289,8 @@ FinalizeCtx make_fin(int nout) {
     if (!spin_env) { const char* e = getenv("APOP_B200_P2P_SPIN_LIMIT"); spin_env = e ? strtoull(e, nullptr, 10) : 0; if (!spin_env) spin_env = 40000000ull; }
     f.spin_limit = spin_env;
     f.err = R.h_err_dev;
+    // local-only mode, or a communicator that already failed (reduce_and_fetch then reports it): no exchange
+    if (R.local_only || R.comm_failed) { f.host_out = R.h_out_dev; return f; }
     if (R.nranks > 1 && R.p2p_active && nout <= R.p2p_slot) {
         f.nranks = R.nranks; f.rank = R.rank; f.seq = ++R.p2p_seq; f.slot = R.p2p_slot;
         for (int p = 0; p < R.nranks; p++) { f.inbox[p] = R.p2p_inbox[p]; f.flags[p] = R.p2p_flags[p]; }
@@ -292,7 +302,7 @@ FinalizeCtx make_fin(int nout) {
 // complete a reduction launched with `fin`: `n` doubles, summed over all ranks, end up in h_out
 bool reduce_and_fetch(size_t n, const FinalizeCtx& fin) {
     Runtime& R = rt();
-    if (R.comm_failed && R.nranks > 1) {
+    if (R.comm_failed && R.nranks > 1 && !R.local_only) {
         // sticky: after a timeout the ranks' sequence counters are out of step, and a later pass could add a
         // slot its peer has already overwritten -- fail every reduction until the communicator is rebuilt
         cudaStreamSynchronize(R.stream);
@@ -317,7 +327,7 @@ bool reduce_and_fetch(size_t n, const FinalizeCtx& fin) {
 // sum host doubles across ranks (n <= 64); result back in v
 bool allreduce_host(double* v, int n) {
     Runtime& R = rt();
-    if (R.nranks <= 1) return true;
+    if (R.nranks <= 1 || R.local_only) return true;
     if (!cuda_ok(cudaMemcpyAsync(R.d_vals, v, n * sizeof(double), cudaMemcpyHostToDevice, R.stream), "H2D")) return false;
     const FinalizeCtx fin = make_fin(n);
     if (!cuda_ok(exchange_launch(R.d_vals, n, R.d_ticket, R.d_out, R.stream, fin), "exchange launch")) return false;

@@ -109,6 +109,7 @@ struct Runtime {
     unsigned long long comm_epoch = 0;   // bumped whenever the set of ranks changes
     // fused allreduce over NVLink peer memory (CUDA IPC), see common.cuh grid_finalize
     bool p2p_active = false;
+    bool local_only = false;      // evaluate this rank's rows only (checks and single-rank baselines inside a multi-rank job)
     bool comm_failed = false;     // a collective timed out: every later reduction fails until the communicator is rebuilt
     int p2p_slot = 0;
     unsigned long long p2p_seq = 0;

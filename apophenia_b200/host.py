@@ -83,6 +83,11 @@ def lib():
         h.apop_data_covariance.argtypes = [_PD]
         h.apop_model_numerical_covariance.restype = _PD
         h.apop_model_numerical_covariance.argtypes = [_PD, _PM]
+        h.apop_model_hessian.restype = _PD
+        h.apop_model_hessian.argtypes = [_PD, _PM, C.c_double]
+        h.apop_b200_observed_information.argtypes = [_PD, _PM, C.POINTER(C.c_double), C.POINTER(C.c_int)]
+        h.apop_settings_group_alloc.restype = C.c_void_p
+        h.apop_settings_group_alloc.argtypes = [_PM, C.c_char_p, C.c_void_p, C.c_size_t]
         h.apop_bootstrap_cov.restype = _PD
         h.apop_bootstrap_cov.argtypes = [_PD, _PM, C.c_uint64, C.c_int, C.POINTER(_PD)]
         h.apop_mcmc_settings_defaults.restype = apop_mcmc_settings

@@ -162,6 +162,10 @@ int apop_b200_comm_size(void);
 int apop_b200_comm_p2p_handle(int nranks, void *handle64);
 int apop_b200_comm_p2p_init(int nranks, int rank, const void *handles);
 int apop_b200_comm_p2p_active(void);
+/* Inside a multi-rank job, evaluate this rank's rows only (no exchange) while on: the parity probe of
+ * bench.py compares the fused cross-GPU sum with an independent torch.distributed all-reduce of these
+ * local results, and rank 0 times the single-GPU pass of the fixed-size problem with it. */
+void apop_b200_set_local_only(int on);
 
 /* ------------------------------------------------------------------ *
  *  Residency: X, y (and weights) live in HBM between optimizer iterations

@@ -1,11 +1,15 @@
 #!/usr/bin/env python
-"""Multi-GPU parity check, run under torchrun on a box with >= 2 B200s (not collected by
-pytest):  torchrun --nproc-per-node 2 tests/multi_gpu_check.py
+"""Multi-GPU parity check, run under torchrun on a box with >= 2 B200s (tests/test_gpu_multi.py
+launches it from pytest -m gpu when the box has them):  torchrun --nproc-per-node 2 tests/multi_gpu_check.py
 Rows are sharded contiguously; every rank must return the oracle's full-data LL/score, and
 bitwise the same numbers as every other rank, with the fused NVLink allreduce (default) and
 with APOP_B200_ALLREDUCE=nccl."""
 import os
 import sys
+
+# the fused allreduce gives up on a missing peer after this many polls (~2 s here instead of ~10 s):
+# the timeout leg at the end of this script waits for it
+os.environ.setdefault("APOP_B200_P2P_SPIN_LIMIT", "4000000")
 
 import numpy as np
 import torch
@@ -101,6 +105,38 @@ def main():
     tot = torch.tensor(c.sum(0).astype(np.float64)).cuda()
     dist.all_reduce(tot)
     checks.append(bool(torch.all(tot == n)))     # the resample is of the GLOBAL data set
+    # multinomial observed information over the shards (P = 32 x 7: wider than the fused exchange slot,
+    # so it takes the NCCL path) and identical on every rank
+    Hm = ab.information(ab.LOGIT, dh, Bh.ravel())
+    Hmw = o.logit_information(Xh, Bh, 8).astype(float)
+    checks.append(bool(np.max(np.abs(Hm - Hmw)) <= 1e-11 * np.abs(Hmw).max()))
+    checks.append(same_everywhere(Hm, world))
+    # local-only mode: this rank's rows alone, and the sum over ranks of those is the fused result
+    ab.set_local_only(True)
+    lll, lg = ab.ll_score(ab.PROBIT, d, beta)
+    ab.set_local_only(False)
+    tl = torch.tensor(np.concatenate([[lll], lg])).cuda()
+    dist.all_reduce(tl)
+    ll_f, g_f = ab.ll_score(ab.PROBIT, d, beta)
+    checks.append(bool(np.allclose(tl.cpu().numpy(), np.concatenate([[ll_f], g_f]), rtol=1e-13, atol=1e-9)))
+    checks.append(abs(lll - float(o.probit_ll(X[lo:hi], y[lo:hi], beta, o.EXACT))) <= 1e-12 * abs(lll))
+    # ---- the peer-timeout path of the fused exchange (common.cuh grid_finalize): rank 0 enters a reduction
+    # alone; it must come back with an error (never hang, never a silent sum), stay failed until the
+    # communicator is rebuilt, and work again afterwards
+    if mode == "p2p-fused":
+        dist.barrier()
+        if rank == 0:
+            ll_t, _ = ab.ll_score(ab.PROBIT, d, beta * 1.01)
+            checks.append(bool(np.isnan(ll_t)) and "peer" in ab.last_error())
+            ll_t2, _ = ab.ll_score(ab.PROBIT, d, beta * 1.02)        # sticky
+            checks.append(bool(np.isnan(ll_t2)) and "communicator failed" in ab.last_error())
+        dist.barrier()
+        ab.comm_finalize()
+        ab.comm_init_from_torch()
+        ll_r, g_r = ab.ll_score(ab.PROBIT, d, beta)
+        want = float(o.probit_ll(X, y, beta, o.EXACT))
+        checks.append(abs(ll_r - want) <= 1e-12 * abs(want))
+        checks.append(same_everywhere(np.concatenate([[ll_r], g_r]), world))
     ok = all(checks)
     flag = torch.tensor([1.0 if ok else 0.0]).cuda()
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)

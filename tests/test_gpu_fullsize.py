@@ -77,6 +77,68 @@ def test_probit_100Mx32(b200, oracle):
     assert np.all(np.linalg.eigvalsh(H) > 0) and np.all(np.abs(est - beta) < 6 * se)
 
 
+def test_probit_100Mx32_fitted_parameters_within_1e8_of_the_oracle_optimum(b200, oracle):
+    """The 1e-8 fitted-parameter target AT the target size.  beta_hat is the device-driven MLE on the full
+    100M x 32 data.  One full-data oracle pass (EXACT mode, long double, OpenMP over row blocks, the data
+    regenerated window by window from the same Philox counters) gives the oracle's score at beta_hat; the
+    oracle-driven optimum beta* solves g_oracle(beta*) = 0, so beta* - beta_hat = H^-1 g_oracle(beta_hat)
+    up to a quadratically small remainder (H = observed information at beta_hat).  The test bounds
+    |H^-1 g_oracle|_j <= 1e-8 |beta_hat_j| for every j, and checks the device's own full-size LL and score
+    against that oracle pass at 1e-12 on the way."""
+    import json
+    import os
+    import time
+    if os.environ.get("APOP_B200_SKIP_SLOW"):
+        pytest.skip("APOP_B200_SKIP_SLOW set")
+    from apophenia_b200 import abi, host
+    ab = b200
+    n, k = 100_000_000, 32
+    rng = np.random.default_rng(8)
+    beta = rng.uniform(-1, 1, k)
+    full = ab.synth(ab.PROBIT, n, k, beta, seed=8)
+    h, lib = host.lib(), abi.load_library()
+    m = h.apop_model_copy(host.model_object(abi.PROBIT))
+    abi.check(lib.apop_b200_register(m, abi.PROBIT), "register")
+    m.contents.parameters = h.apop_data_alloc(k, 1, 0)
+    m.contents.data = full.ptr
+    keep = []
+    host.mle_settings(m, method="Newton", tolerance=1e-12, relative_tolerance=True, max_iterations=50,
+                      starting_pt=ab.probit_start(full, k), keep=keep)
+    h.apop_maximum_likelihood(full.ptr, m)
+    est = host.parameters_of(m)
+    ll_dev, g_dev = ab.ll_score(ab.PROBIT, full, est)
+    H = ab.information(ab.PROBIT, full, est)
+    full.free()
+    # ---- the oracle over all 100M rows, 10M at a time
+    t0 = time.perf_counter()
+    L = np.longdouble
+    ll_o, g_o, a_o = L(0), np.zeros(k, dtype=L), np.zeros(k, dtype=L)
+    chunk = 10_000_000
+    threads = max(oracle.max_threads(), os.cpu_count() or 1)
+    for lo in range(0, n, chunk):
+        w = ab.synth(ab.PROBIT, chunk, k, beta, seed=8, row_offset=lo)
+        X, y = w.download()
+        w.free()
+        l, g, a = oracle.probit_ll_score_exact_omp(X, y, est, threads)
+        ll_o += l; g_o += g; a_o += a
+    secs = time.perf_counter() - t0
+    # full-size parity of the device pass itself
+    assert abs(L(ll_dev) - ll_o) <= 1e-12 * abs(ll_o)
+    assert np.all(np.abs(g_dev.astype(L) - g_o) <= 1e-12 * a_o)
+    # the parameter bound
+    step = np.linalg.solve(H, g_o.astype(float))
+    rel = np.abs(step) / np.abs(est)
+    rec = {"rows": n, "k": k, "max_rel_param_gap_to_oracle_optimum": float(rel.max()), "bound": 1e-8,
+           "ll_rel_err_fullsize": float(abs(L(ll_dev) - ll_o) / abs(ll_o)),
+           "score_rel_err_fullsize_max": float(np.max(np.abs(g_dev.astype(L) - g_o) / a_o)),
+           "oracle_score_inf_norm": float(np.max(np.abs(g_o))), "oracle_pass_seconds": secs, "oracle_threads": threads,
+           "min_abs_beta_hat": float(np.min(np.abs(est)))}
+    out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out_dir):
+        json.dump(rec, open(os.path.join(out_dir, "param_pin_100Mx32.json"), "w"), indent=1)
+    assert rel.max() <= 1e-8, rec
+
+
 def test_logit8_20Mx32(b200, oracle):
     """BASELINE config 2: multinomial logit, C = 8"""
     ab = b200
