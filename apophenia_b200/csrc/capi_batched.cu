@@ -101,7 +101,9 @@ static bool eval_logit_info(Resident* r, const double* B, size_t C1, double* H) 
             const double* blk = R.h_out + (size_t)i * KB * KB;
             for (int j = 0; j < K; j++)
                 for (int j2 = 0; j2 < K; j2++) {
-                    const double v = blk[j * KB + j2];
+                    // X' diag(w) X is symmetric; the two triangles of a diagonal 8 x 8 block come from different
+                    // products (fl(w x_j) x_j2 vs fl(w x_j2) x_j): take the upper one for both, H == H' bitwise
+                    const double v = (j <= j2) ? blk[j * KB + j2] : blk[j2 * KB + j];
                     H[((size_t)j * C1 + a) * P + (size_t)j2 * C1 + b] = v;
                     H[((size_t)j * C1 + b) * P + (size_t)j2 * C1 + a] = v;   // W_ab = W_ba
                 }

@@ -3,6 +3,7 @@
 // device-generated data sets and their download.
 #include "capi_internal.cuh"
 #include "host_pool.h"
+#include <condition_variable>
 
 using namespace apb;
 
@@ -27,6 +28,214 @@ HostSig host_sig(const apop_data* d) {
 // the address of a freed one, or the same one reshaped by a prep) must not be served from the stale copy
 static bool sig_stale(const Resident* r, const apop_data* d) {
     return !r->synthetic && !(r->sig == host_sig(d));
+}
+
+// --------------------------------------------------------------------------
+//  Zero-copy upload: registered windows of the caller's own matrix
+// --------------------------------------------------------------------------
+// The staged upload below copies every byte twice on the host (pageable -> pinned staging, then DMA reads
+// the staging buffer): 3-4x host-memory traffic per byte, which is what limits 8 ranks pinning through one
+// host (7.6 GB/s per GPU in round 1).  When the matrix is contiguous (tda == size2) the DMA engine can read
+// the caller's buffer itself: a helper thread page-locks it window by window (cudaHostRegister, 128 MB
+// windows on 2 MB boundaries, a few windows ahead of the copy), every window crosses PCIe with ONE
+// cudaMemcpyAsync straight from the caller's memory into a device landing buffer, and the tiling kernel
+// re-lays it (rows that straddle a window boundary are carried over device-side).  The outcome and weight
+// vectors (3 % of the bytes) still go through a small pinned staging buffer.  Registration speed depends on
+// the pages behind the buffer (measured on the pool box, tools/pin_probe2.py: 9-12 GB/s on 4 KB pages,
+// 53 GB/s on transparent huge pages, e.g. GLIBC_TUNABLES=glibc.malloc.hugetlb=1 for a malloc'ing caller):
+// APOP_B200_PIN_MODE=auto (default) measures the first window and falls back to the staged upload when a
+// single rank would be slower this way; =register / =staged force either.
+struct RegWindow { uintptr_t lo, hi; int state; bool ours; };   // state: 0 pending, 1 registered, 2 failed
+struct Registrar {
+    std::mutex m;
+    std::condition_variable cv;
+    std::vector<RegWindow> w;
+    size_t consumed = 0;          // windows the main thread is done copying from (may be unregistered)
+    size_t unregistered = 0;
+    bool stop = false;
+    int device = 0;
+    int ahead = 3;
+    double first_rate = 0.0;
+    void run() {
+        cudaSetDevice(device);
+        size_t next = 0;
+        for (;;) {
+            size_t todo_unreg = 0;
+            {
+                std::unique_lock<std::mutex> lk(m);
+                cv.wait(lk, [&] { return stop || unregistered < consumed || (next < w.size() && next < consumed + ahead); });
+                if (unregistered < consumed) todo_unreg = consumed - unregistered;
+                else if (stop || next >= w.size()) { if (stop || unregistered >= w.size()) break; continue; }
+            }
+            if (todo_unreg) {
+                for (size_t i = 0; i < todo_unreg; i++) {
+                    RegWindow& x = w[unregistered + i];
+                    if (x.state == 1 && x.ours) cudaHostUnregister((void*)x.lo);
+                }
+                std::lock_guard<std::mutex> lk(m);
+                unregistered += todo_unreg;
+                cv.notify_all();
+                continue;
+            }
+            RegWindow& x = w[next];
+            const auto t0 = std::chrono::steady_clock::now();
+            cudaError_t e = cudaHostRegister((void*)x.lo, x.hi - x.lo, cudaHostRegisterDefault);
+            const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            int st = 1;
+            bool ours = true;
+            if (e == cudaErrorHostMemoryAlreadyRegistered) { ours = false; cudaGetLastError(); }   // the caller pinned it: even better
+            else if (e != cudaSuccess) { st = 2; cudaGetLastError(); }
+            {
+                std::lock_guard<std::mutex> lk(m);
+                x.state = st; x.ours = ours;
+                if (next == 0) first_rate = (st == 1 && ours && dt > 0) ? (x.hi - x.lo) * 1e-9 / dt : (st == 1 ? 1e9 : 0.0);
+                cv.notify_all();
+            }
+            if (st == 2) {   // nothing beyond this window will be registered
+                std::lock_guard<std::mutex> lk(m);
+                for (size_t j = next + 1; j < w.size(); j++) w[j].state = 2;
+                next = w.size();
+                cv.notify_all();
+                continue;
+            }
+            next++;
+        }
+        // leave nothing page-locked behind
+        for (size_t i = unregistered; i < w.size(); i++)
+            if (w[i].state == 1 && w[i].ours) cudaHostUnregister((void*)w[i].lo);
+    }
+};
+
+static int pin_mode_env() {   // 0 auto, 1 staged, 2 register (read per upload: tests switch it)
+    const char* e = getenv("APOP_B200_PIN_MODE");
+    return (e && !strcmp(e, "staged")) ? 1 : (e && !strcmp(e, "register")) ? 2 : 0;
+}
+
+// Uploads rows [0, done) through registered windows and returns `done`: all n rows, or a multiple of
+// TILE_ROWS (possibly 0) from which the staged path carries on.  ok = false on a CUDA error.
+static size_t upload_registered(Resident* r, const apop_data* d, bool col0, int cols, bool& ok) {
+    Runtime& R = rt();
+    ok = true;
+    const int mode = pin_mode_env();
+    const size_t n = r->n_rows;
+    const int k = r->k;
+    const bool hy = d->vector != nullptr, hw = d->weights != nullptr;
+    if (mode == 1 || !d->matrix || k < 1 || d->matrix->tda != (size_t)k) return 0;
+    if ((hy && d->vector->stride != 1) || (hw && d->weights->stride != 1)) return 0;
+    const size_t rb = (size_t)k * sizeof(double), total = n * rb;
+    if (total < ((size_t)256 << 20) && mode != 2) return 0;          // small data: the staged path is simpler and as fast
+    const size_t PAGE = 4096, ALIGN = (size_t)2 << 20;
+    size_t WB = (size_t)128 << 20;                                    // window: a multiple of the 2 MB huge-page size
+    if (const char* e = getenv("APOP_B200_PIN_WINDOW_MB")) { const long mb = atol(e); if (mb >= 2) WB = (size_t)(mb / 2 * 2) << 20; }
+    const uintptr_t base = (uintptr_t)d->matrix->data;
+    const uintptr_t lo = base & ~(uintptr_t)(PAGE - 1), hi = (base + total + PAGE - 1) & ~(uintptr_t)(PAGE - 1);
+    Registrar G;
+    G.device = R.device;
+    for (uintptr_t a = lo; a < hi;) {
+        uintptr_t b = (a == lo) ? ((lo & ~(uintptr_t)(ALIGN - 1)) + WB) : a + WB;
+        if (b > hi) b = hi;
+        G.w.push_back(RegWindow{a, b, 0, true});
+        a = b;
+    }
+    const size_t nw = G.w.size();
+    // landing buffers: [carry: up to 32 rows + a partial one][window][y][w]
+    const size_t carry_cap = ((33 * rb) + 255) / 256 * 256;
+    const size_t max_rows = WB / rb + 66;
+    const size_t yw_bytes = max_rows * sizeof(double) * ((hy ? 1 : 0) + (hw ? 1 : 0));
+    const size_t dev_need = carry_cap + WB + PAGE + yw_bytes + 512;
+    if (R.reg_dev_cap < dev_need) {
+        for (int b2 = 0; b2 < 2; b2++) { if (R.reg_dev[b2]) cudaFree(R.reg_dev[b2]); R.reg_dev[b2] = nullptr; }
+        R.reg_dev_cap = 0;
+        for (int b2 = 0; b2 < 2; b2++)
+            if (!cuda_ok(cudaMalloc(&R.reg_dev[b2], dev_need), "cudaMalloc(landing buffer)")) { ok = false; return 0; }
+        R.reg_dev_cap = dev_need;
+    }
+    if (yw_bytes && R.reg_hy_cap < yw_bytes) {
+        for (int b2 = 0; b2 < 2; b2++) { if (R.reg_hy[b2]) cudaFreeHost(R.reg_hy[b2]); R.reg_hy[b2] = nullptr; }
+        R.reg_hy_cap = 0;
+        for (int b2 = 0; b2 < 2; b2++)
+            if (!cuda_ok(cudaHostAlloc(&R.reg_hy[b2], yw_bytes, cudaHostAllocDefault), "cudaHostAlloc(outcome staging)")) { ok = false; return 0; }
+        R.reg_hy_cap = yw_bytes;
+    }
+    if (!R.reg_copied[0])
+        for (int b2 = 0; b2 < 2; b2++) { cudaEventCreateWithFlags(&R.reg_copied[b2], cudaEventDisableTiming); cudaEventCreateWithFlags(&R.reg_packed[b2], cudaEventDisableTiming); }
+
+    static const bool trace = getenv("APOP_B200_PIN_TRACE") != nullptr;
+    const auto t_begin = std::chrono::steady_clock::now();
+    std::thread worker([&G] { G.run(); });
+    auto finish = [&](size_t consumed_all) {
+        { std::lock_guard<std::mutex> lk(G.m); G.consumed = consumed_all; G.stop = true; G.cv.notify_all(); }
+        worker.join();
+    };
+    // ---- the first window decides (auto mode): is page-locking this memory fast enough to pay off?
+    {
+        std::unique_lock<std::mutex> lk(G.m);
+        G.cv.wait(lk, [&] { return G.w[0].state != 0; });
+    }
+    R.last_register_GBps = G.first_rate;
+    const double need_rate = (R.nranks > 1) ? 4.0 : 25.0;   // several ranks on one host: the staged path is host-memory bound
+    if (G.w[0].state != 1 || (mode == 0 && G.first_rate < need_rate)) {
+        if (trace) fprintf(stderr, "[apop_b200 pin] registered windows not used: first window %s at %.1f GB/s (need %.0f)\n",
+                           G.w[0].state == 1 ? "page-locked" : "could not be page-locked", G.first_rate, need_rate);
+        finish(0);
+        return 0;
+    }
+    size_t row_cursor = 0, carry_len = 0, prev_rows = 0, prev_carry = 0;
+    size_t wi = 0;
+    for (; ok && wi < nw; wi++) {
+        {
+            std::unique_lock<std::mutex> lk(G.m);
+            G.cv.wait(lk, [&] { return G.w[wi].state != 0; });
+            if (G.w[wi].state != 1) break;                   // registration failed from here on: the staged path takes over
+        }
+        const int slot = (int)(wi & 1);
+        if (wi >= 2) {
+            ok = cuda_ok(cudaEventSynchronize(R.reg_packed[slot]), "landing buffer wait");   // window wi-2 is tiled: its buffers are free,
+            std::lock_guard<std::mutex> lk(G.m);                                           // and its host pages may be released
+            G.consumed = wi - 1;
+            G.cv.notify_all();
+        }
+        const uintptr_t hs = G.w[wi].lo < base ? base : G.w[wi].lo;
+        const uintptr_t he = G.w[wi].hi > base + total ? base + total : G.w[wi].hi;
+        const size_t len = he - hs;
+        char* win = R.reg_dev[slot] + carry_cap;
+        const size_t avail = carry_len + len;
+        const bool last = (wi + 1 == nw);
+        size_t rows = avail / rb;
+        if (!last) rows = rows / TILE_ROWS * TILE_ROWS;
+        // outcome / weights of these rows through the pinned staging slot
+        double* hyv = R.reg_hy[slot];
+        double* hwv = hyv ? hyv + (hy ? rows : 0) : nullptr;
+        if (hy && rows) memcpy(hyv, d->vector->data + row_cursor, rows * sizeof(double));
+        if (hw && rows) memcpy(hwv, d->weights->data + row_cursor, rows * sizeof(double));
+        if (wi >= 2) ok = ok && cuda_ok(cudaStreamWaitEvent(R.copy_stream, R.reg_packed[slot], 0), "stream wait");
+        ok = ok && cuda_ok(cudaMemcpyAsync(win, (const void*)hs, len, cudaMemcpyHostToDevice, R.copy_stream), "H2D window");
+        if (carry_len) {   // the rows the previous window left incomplete, placed right before this window's bytes
+            const char* prev_win = R.reg_dev[slot ^ 1] + carry_cap;
+            const char* left = prev_win - prev_carry + prev_rows * rb;
+            ok = ok && cuda_ok(cudaMemcpyAsync(win - carry_len, left, carry_len, cudaMemcpyDeviceToDevice, R.copy_stream), "carry");
+        }
+        ok = ok && cuda_ok(cudaEventRecord(R.reg_copied[slot], R.copy_stream), "event");
+        ok = ok && cuda_ok(cudaStreamWaitEvent(R.stream, R.reg_copied[slot], 0), "stream wait");
+        double* dy = (double*)(win + ((WB + PAGE + 255) / 256 * 256));
+        double* dw = dy + (hy ? rows : 0);
+        if (yw_bytes && rows)
+            ok = ok && cuda_ok(cudaMemcpyAsync(dy, hyv, rows * sizeof(double) * ((hy ? 1 : 0) + (hw ? 1 : 0)), cudaMemcpyHostToDevice, R.stream), "H2D outcome");
+        if (rows)
+            ok = ok && cuda_ok(tile_pack((const double*)(win - carry_len), hy ? dy : nullptr, hw ? dw : nullptr, rows, k, cols,
+                                         r->tiles + (row_cursor / TILE_ROWS) * (size_t)cols * TILE_ROWS, R.stream, col0), "tile_pack");
+        ok = ok && cuda_ok(cudaEventRecord(R.reg_packed[slot], R.stream), "event");
+        prev_rows = rows; prev_carry = carry_len;
+        carry_len = avail - rows * rb;
+        row_cursor += rows;
+    }
+    ok = ok && cuda_ok(cudaStreamSynchronize(R.stream), "pin sync") && cuda_ok(cudaStreamSynchronize(R.copy_stream), "pin sync");
+    finish(nw);
+    R.last_pin_mode = 1;
+    if (trace)
+        fprintf(stderr, "[apop_b200 pin] registered windows: %zu of %zu rows from %zu of %zu windows in %.3f s (first window page-locked at %.1f GB/s)\n",
+                row_cursor, n, wi, nw, std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count(), G.first_rate);
+    return row_cursor;
 }
 
 bool upload(Resident* r, const apop_data* d) {
@@ -63,6 +272,13 @@ bool upload(Resident* r, const apop_data* d) {
     if (r->lgy) { cudaFree(r->lgy); r->lgy = nullptr; }
     if (!need) return true;
 
+    R.last_pin_mode = 0;
+    size_t first_row = 0;
+    {
+        bool okr = true;
+        first_row = upload_registered(r, d, col0, cols, okr);
+        if (!okr) return false;
+    }
     // Staged, pipelined upload.  Chunks of rows are gathered from the caller's (pageable,
     // possibly strided) buffers into one of two pinned staging buffers by a few host threads,
     // sent with one asynchronous copy each, and re-tiled on the device; the gather of chunk
@@ -96,7 +312,7 @@ bool upload(Resident* r, const apop_data* d) {
     double t_wait = 0.0, t_gather = 0.0;
     const auto t_begin = std::chrono::steady_clock::now();
     auto since = [](std::chrono::steady_clock::time_point t0) { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); };
-    for (size_t r0 = 0; ok && r0 < n; r0 += chunk, ci++) {
+    for (size_t r0 = first_row; ok && r0 < n; r0 += chunk, ci++) {
         const size_t rows = (n - r0 < chunk) ? n - r0 : chunk;
         const int buf = ci & 1;
         auto tw = std::chrono::steady_clock::now();

@@ -134,6 +134,13 @@ extern "C" void apop_b200_finalize(void) {
         if (R.pin_copied[b2]) { cudaEventDestroy(R.pin_copied[b2]); R.pin_copied[b2] = nullptr; }
     }
     R.pin_cap = 0;
+    for (int b2 = 0; b2 < 2; b2++) {
+        if (R.reg_dev[b2]) { cudaFree(R.reg_dev[b2]); R.reg_dev[b2] = nullptr; }
+        if (R.reg_hy[b2]) { cudaFreeHost(R.reg_hy[b2]); R.reg_hy[b2] = nullptr; }
+        if (R.reg_copied[b2]) { cudaEventDestroy(R.reg_copied[b2]); R.reg_copied[b2] = nullptr; }
+        if (R.reg_packed[b2]) { cudaEventDestroy(R.reg_packed[b2]); R.reg_packed[b2] = nullptr; }
+    }
+    R.reg_dev_cap = R.reg_hy_cap = 0;
     cudaFree(R.d_vals);
     if (R.d_beta) { cudaFree(R.d_beta); R.d_beta = nullptr; }
     cudaEventDestroy(R.ev0);
@@ -156,6 +163,10 @@ extern "C" double apop_b200_pass_timer_total_ms(unsigned long long* n) {
 }
 extern "C" void apop_b200_set_auto_pin(int on) { rt().auto_pin = on != 0; }
 extern "C" void apop_b200_set_timing(int on) { rt().timing = on != 0; }
+extern "C" int apop_b200_last_pin_mode(double* register_GBps) {
+    if (register_GBps) *register_GBps = rt().last_register_GBps;
+    return rt().last_pin_mode;
+}
 extern "C" void apop_b200_set_local_only(int on) {
     LOCK;
     Runtime& R = rt();

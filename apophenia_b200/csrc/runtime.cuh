@@ -98,6 +98,14 @@ struct Runtime {
     cudaEvent_t pin_copied[2] = {nullptr, nullptr};
     cudaStream_t copy_stream = nullptr;   // H2D copies of the upload run here, back to back, while the main stream tiles
     size_t pin_cap = 0;   // doubles per staging buffer
+    // zero-copy upload (registered windows of the caller's matrix): two device landing buffers, two pinned
+    // staging buffers for the outcome / weights of a window, and their events
+    char* reg_dev[2] = {nullptr, nullptr};
+    double* reg_hy[2] = {nullptr, nullptr};
+    size_t reg_dev_cap = 0, reg_hy_cap = 0;   // bytes
+    cudaEvent_t reg_copied[2] = {nullptr, nullptr}, reg_packed[2] = {nullptr, nullptr};
+    int last_pin_mode = 0;                    // 0 staged, 1 registered windows (apop_b200_last_pin_mode)
+    double last_register_GBps = 0.0;
     std::unordered_map<const apop_data*, Resident*> reg;
     // stats
     unsigned long long launches = 0, n_passes = 0;

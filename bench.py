@@ -60,6 +60,7 @@ def parse():
     ap.add_argument("--no-configs", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--configs", default="cfg2,cfg3,cfg4,cfg5", help="which BASELINE configurations to run")
+    ap.add_argument("--host-pages", default="thp", choices=["thp", "4k"], help="pages behind the e2e host matrix")
     ap.add_argument("--sustain-seconds", type=float, default=2.0, help="length of the back-to-back (sustained) run")
     return ap.parse_args()
 
@@ -416,13 +417,17 @@ def run_e2e(cx, fam, beta_true):
         n = int(t[0])
     # host data set: the same synthetic recipe, generated on the device and copied back
     src = ab.synth(fam, n, k, beta_true, ncat=args.ncat, seed=8, row_offset=rank * n)
-    X, y = src.download()
+    # the host matrix sits on transparent huge pages (anonymous mmap + MADV_HUGEPAGE: what
+    # GLIBC_TUNABLES=glibc.malloc.hugetlb=1 gives a C caller's gsl_matrix_alloc), which lets the upload page-lock
+    # it in place and DMA straight out of it; --host-pages 4k keeps ordinary pages
+    X, y = src.download(hugepages=args.host_pages == "thp")
     src.free()
     d = ab.Data(matrix=X, vector=y)
     cx.barrier()
     t0 = time.perf_counter()
     ab.pin(d)                      # one-off: host->device copy of X, y + tiling
     pin_s = time.perf_counter() - t0
+    pin_mode, reg_rate = ab.last_pin_mode()
     mk = {0: ab.probit_model, 1: ab.logit_model}.get(fam, ab.vector_model)
     shape = (lambda b: b.reshape(k, -1)) if fam == 1 else (lambda b: b)
     for i in range(2):
@@ -450,7 +455,8 @@ def run_e2e(cx, fam, beta_true):
                 "note": "X and y already resident (BASELINE.json north_star keeps them in HBM between optimizer "
                         "iterations): per step only beta goes down and [LL|score] comes back"}
     cold = {"pin_seconds": pin_s, "h2d_bytes": n * (k + 1) * 8, "pin_GBps": n * (k + 1) * 8e-9 / pin_s,
-            "pin_GBps_all_gpus": world * n * (k + 1) * 8e-9 / pin_s, "pin_mode": os.environ.get("APOP_B200_PIN_MODE", "default"),
+            "pin_GBps_all_gpus": world * n * (k + 1) * 8e-9 / pin_s, "pin_mode": pin_mode, "page_lock_GBps_first_window": reg_rate, "host_pages": args.host_pages,
+            "pin_mode_env": os.environ.get("APOP_B200_PIN_MODE", "auto"),
             "first_pass_rows_per_s": n * world / (pin_s + dt / steps)}
     api = "apop_b200_pin + apop_maximum_likelihood (host mirror of the reference driver) over the registered " \
           "apop_b200_<family>_ll / _score entries, on a HOST apop_data"

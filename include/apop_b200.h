@@ -181,6 +181,11 @@ int apop_b200_unpin(apop_data *d);
  * re-upload on next use. */
 int apop_b200_invalidate(apop_data *d);
 int apop_b200_is_pinned(const apop_data *d);
+/* How the most recent upload crossed PCIe: 0 = staged (host threads gather into pinned staging), 1 = zero
+ * copy (the caller's matrix page-locked window by window and read by the DMA engine directly; chosen when
+ * the matrix is contiguous and page-locking it is fast enough -- APOP_B200_PIN_MODE=auto|staged|register).
+ * register_GBps (may be NULL) receives the page-locking rate measured on the first window. */
+int apop_b200_last_pin_mode(double *register_GBps);
 /* unpinned data policy: 0 = upload per call and drop (always correct, default),
  * 1 = pin on first sight and trust the caller to invalidate. */
 void apop_b200_set_auto_pin(int on);

@@ -414,3 +414,48 @@ def test_device_recode_survives_reupload(b200, oracle):
     ab.invalidate(d)
     assert _rel(ab.log_likelihood(ab.LOGIT, d, m), want) <= 1e-12
     ab.unpin(d)
+
+
+# ------------------------------------------------------------------------------------------------
+def test_registered_window_upload_roundtrip(b200, monkeypatch):
+    """the zero-copy upload (cudaHostRegister'ed windows of the caller's matrix, DMA straight out of it):
+    2 MB windows over a 30 MB matrix whose 296-byte rows straddle every window boundary and whose first byte is
+    not page aligned; outcome and weights through the small pinned staging; bit-exact round trip, and the same
+    through the device prep with the outcome in column 0"""
+    ab = b200
+    rng = np.random.default_rng(41)
+    n, k = 100_003, 37
+    big = rng.standard_normal((n + 3, k))
+    X = big[3:]                                   # contiguous rows, base pointer 888 bytes past the allocation
+    y = rng.standard_normal(n)
+    w = rng.uniform(0.5, 2.0, n)
+    monkeypatch.setenv("APOP_B200_PIN_MODE", "register")
+    monkeypatch.setenv("APOP_B200_PIN_WINDOW_MB", "2")
+    d = ab.pin(ab.Data(matrix=X, vector=y, weights=w))
+    assert ab.last_pin_mode()[0] == "registered"
+    Xd = np.zeros((n, k)); yd = np.zeros(n); wd = np.zeros(n)
+    from apophenia_b200 import abi
+    dp = C.POINTER(C.c_double)
+    abi.check(abi.load_library().apop_b200_download(d.ptr, Xd.ctypes.data_as(dp), yd.ctypes.data_as(dp), wd.ctypes.data_as(dp)), "download")
+    assert np.array_equal(Xd, X) and np.array_equal(yd, y) and np.array_equal(wd, w)
+    ab.unpin(d)
+    # staged and registered uploads give bitwise the same resident data, hence the same results
+    Xp, yp, beta = gen_probit_logit_sample(90_001, 33, seed=4)
+    res = {}
+    for mode in ("staged", "register"):
+        monkeypatch.setenv("APOP_B200_PIN_MODE", mode)
+        dd = ab.pin(ab.Data(matrix=Xp, vector=yp))
+        res[mode] = ab.ll_score(ab.PROBIT, dd, beta)
+        ab.unpin(dd)
+    assert res["staged"][0] == res["register"][0] and np.array_equal(res["staged"][1], res["register"][1])
+    # outcome in column 0: the tiling kernel shuffles it out on the registered path as well
+    raw = Xp[:, :20].copy(); raw[:, 0] = yp
+    monkeypatch.setenv("APOP_B200_PIN_MODE", "register")
+    dr = ab.Data(matrix=raw)
+    cats, start = ab.prep_outcome(dr)
+    assert ab.last_pin_mode()[0] == "registered" and np.array_equal(cats, [0.0, 1.0])
+    ll_r = ab.log_likelihood(ab.PROBIT, dr, ab.probit_model(beta[:20], dr))
+    X20 = Xp[:, :20].copy(); X20[:, 0] = 1.0
+    ds = ab.pin(ab.Data(matrix=X20, vector=yp))
+    assert ll_r == ab.log_likelihood(ab.PROBIT, ds, ab.probit_model(beta[:20], ds))
+    ab.unpin(dr); ab.unpin(ds)
