@@ -18,6 +18,7 @@
 // runtime / communication (capi_runtime.cu)
 bool require_ready();
 void free_resident(apb::Resident* r);
+void release_host_registration(apb::Resident* r);
 bool nccl_ok(int rc, const char* what);
 apb::FinalizeCtx make_fin(int nout);
 bool reduce_and_fetch(size_t n, const apb::FinalizeCtx& fin);

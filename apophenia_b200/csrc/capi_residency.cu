@@ -4,6 +4,7 @@
 #include "capi_internal.cuh"
 #include "host_pool.h"
 #include <condition_variable>
+#include <algorithm>
 
 using namespace apb;
 
@@ -40,69 +41,52 @@ static bool sig_stale(const Resident* r, const apop_data* d) {
 // windows on 2 MB boundaries, a few windows ahead of the copy), every window crosses PCIe with ONE
 // cudaMemcpyAsync straight from the caller's memory into a device landing buffer, and the tiling kernel
 // re-lays it (rows that straddle a window boundary are carried over device-side).  The outcome and weight
-// vectors (3 % of the bytes) still go through a small pinned staging buffer.  Registration speed depends on
-// the pages behind the buffer (measured on the pool box, tools/pin_probe2.py: 9-12 GB/s on 4 KB pages,
-// 53 GB/s on transparent huge pages, e.g. GLIBC_TUNABLES=glibc.malloc.hugetlb=1 for a malloc'ing caller):
-// APOP_B200_PIN_MODE=auto (default) measures the first window and falls back to the staged upload when a
-// single rank would be slower this way; =register / =staged force either.
+// vectors (3 % of the bytes) still go through a small pinned staging buffer.
+// Measured on the pool box (tools/pin_probe2.py, tools/pin_modes.py): page-locking runs at 9-12 GB/s on 4 KB
+// pages and 42-53 GB/s on transparent huge pages (GLIBC_TUNABLES=glibc.malloc.hugetlb=1 gives them to a
+// malloc'ing caller), releasing the pages at 36 GB/s, and both calls serialise with the copy submissions on the
+// driver's lock.  So the windows stay page-locked while the data set is resident (a registration cache, as
+// MPI / UCX keep one; released by unpin / invalidate / re-upload / finalize), and the mode is chosen per upload:
+// APOP_B200_PIN_MODE=auto (default) page-locks the first window, compares its rate with what this rank's share
+// of the host threads can gather (one rank with 16 threads stages at 41-48 GB/s and keeps doing so; eight ranks
+// with two threads each do not), and goes on zero-copy or falls back; =register / =staged force either.
 struct RegWindow { uintptr_t lo, hi; int state; bool ours; };   // state: 0 pending, 1 registered, 2 failed
 struct Registrar {
     std::mutex m;
     std::condition_variable cv;
     std::vector<RegWindow> w;
-    size_t consumed = 0;          // windows the main thread is done copying from (may be unregistered)
-    size_t unregistered = 0;
+    size_t consumed = 0;          // windows the main thread has issued copies for
     bool stop = false;
     int device = 0;
     int ahead = 3;
     double first_rate = 0.0;
+    double t_register = 0.0;      // seconds inside cudaHostRegister (trace)
     void run() {
         cudaSetDevice(device);
-        size_t next = 0;
-        for (;;) {
-            size_t todo_unreg = 0;
+        for (size_t next = 0; next < w.size(); next++) {
             {
                 std::unique_lock<std::mutex> lk(m);
-                cv.wait(lk, [&] { return stop || unregistered < consumed || (next < w.size() && next < consumed + ahead); });
-                if (unregistered < consumed) todo_unreg = consumed - unregistered;
-                else if (stop || next >= w.size()) { if (stop || unregistered >= w.size()) break; continue; }
-            }
-            if (todo_unreg) {
-                for (size_t i = 0; i < todo_unreg; i++) {
-                    RegWindow& x = w[unregistered + i];
-                    if (x.state == 1 && x.ours) cudaHostUnregister((void*)x.lo);
-                }
-                std::lock_guard<std::mutex> lk(m);
-                unregistered += todo_unreg;
-                cv.notify_all();
-                continue;
+                cv.wait(lk, [&] { return stop || next < consumed + ahead; });
+                if (stop) break;
             }
             RegWindow& x = w[next];
             const auto t0 = std::chrono::steady_clock::now();
             cudaError_t e = cudaHostRegister((void*)x.lo, x.hi - x.lo, cudaHostRegisterDefault);
             const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            t_register += dt;
             int st = 1;
             bool ours = true;
             if (e == cudaErrorHostMemoryAlreadyRegistered) { ours = false; cudaGetLastError(); }   // the caller pinned it: even better
             else if (e != cudaSuccess) { st = 2; cudaGetLastError(); }
-            {
-                std::lock_guard<std::mutex> lk(m);
-                x.state = st; x.ours = ours;
-                if (next == 0) first_rate = (st == 1 && ours && dt > 0) ? (x.hi - x.lo) * 1e-9 / dt : (st == 1 ? 1e9 : 0.0);
-                cv.notify_all();
-            }
-            if (st == 2) {   // nothing beyond this window will be registered
-                std::lock_guard<std::mutex> lk(m);
-                for (size_t j = next + 1; j < w.size(); j++) w[j].state = 2;
-                next = w.size();
-                cv.notify_all();
-                continue;
-            }
-            next++;
+            std::lock_guard<std::mutex> lk(m);
+            x.state = st; x.ours = ours;
+            // the rate the decision is taken on: the best of the first two windows (the very first call also pays
+            // the driver's one-off set-up)
+            if (next < 2) { const double rate = (st == 1 && ours && dt > 0) ? (x.hi - x.lo) * 1e-9 / dt : (st == 1 ? 1e9 : 0.0); if (rate > first_rate) first_rate = rate; }
+            if (st == 2) for (size_t j = next + 1; j < w.size(); j++) w[j].state = 2;   // nothing beyond this window
+            cv.notify_all();
+            if (st == 2) break;
         }
-        // leave nothing page-locked behind
-        for (size_t i = unregistered; i < w.size(); i++)
-            if (w[i].state == 1 && w[i].ours) cudaHostUnregister((void*)w[i].lo);
     }
 };
 
@@ -131,6 +115,9 @@ static size_t upload_registered(Resident* r, const apop_data* d, bool col0, int 
     const uintptr_t lo = base & ~(uintptr_t)(PAGE - 1), hi = (base + total + PAGE - 1) & ~(uintptr_t)(PAGE - 1);
     Registrar G;
     G.device = R.device;
+    if (const char* e = getenv("APOP_B200_PIN_AHEAD")) { const int a = atoi(e); if (a >= 2) G.ahead = a; }
+    double t_wait_reg = 0.0, t_wait_dev = 0.0, t_issue = 0.0;
+    auto since = [](std::chrono::steady_clock::time_point t0) { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); };
     for (uintptr_t a = lo; a < hi;) {
         uintptr_t b = (a == lo) ? ((lo & ~(uintptr_t)(ALIGN - 1)) + WB) : a + WB;
         if (b > hi) b = hi;
@@ -163,38 +150,50 @@ static size_t upload_registered(Resident* r, const apop_data* d, bool col0, int 
     static const bool trace = getenv("APOP_B200_PIN_TRACE") != nullptr;
     const auto t_begin = std::chrono::steady_clock::now();
     std::thread worker([&G] { G.run(); });
-    auto finish = [&](size_t consumed_all) {
-        { std::lock_guard<std::mutex> lk(G.m); G.consumed = consumed_all; G.stop = true; G.cv.notify_all(); }
+    // stops the helper; keep = the page-locked windows stay with the resident copy, else they are released now
+    auto finish = [&](bool keep) {
+        { std::lock_guard<std::mutex> lk(G.m); G.stop = true; G.cv.notify_all(); }
         worker.join();
+        for (auto& x : G.w)
+            if (x.state == 1 && x.ours) {
+                if (keep) r->host_registered.push_back({(void*)x.lo, (size_t)(x.hi - x.lo)});
+                else cudaHostUnregister((void*)x.lo);
+            }
     };
-    // ---- the first window decides (auto mode): is page-locking this memory fast enough to pay off?
+    // ---- the first two windows decide (auto mode): is page-locking this memory fast enough to pay off?
     {
         std::unique_lock<std::mutex> lk(G.m);
-        G.cv.wait(lk, [&] { return G.w[0].state != 0; });
+        const size_t probe = nw > 1 ? 1 : 0;
+        G.cv.wait(lk, [&] { return G.w[probe].state != 0; });
     }
     R.last_register_GBps = G.first_rate;
-    const double need_rate = (R.nranks > 1) ? 4.0 : 25.0;   // several ranks on one host: the staged path is host-memory bound
+    // what the staged path can be expected to deliver: ~3.2 GB/s per gathering host thread of this rank (measured:
+    // 16 threads 41-48 GB/s, 2 threads 7.6 GB/s), capped by the PCIe link
+    const double need_rate = std::min(50.0, 3.2 * HostPool::get().size());
     if (G.w[0].state != 1 || (mode == 0 && G.first_rate < need_rate)) {
         if (trace) fprintf(stderr, "[apop_b200 pin] registered windows not used: first window %s at %.1f GB/s (need %.0f)\n",
                            G.w[0].state == 1 ? "page-locked" : "could not be page-locked", G.first_rate, need_rate);
-        finish(0);
+        finish(false);
         return 0;
     }
     size_t row_cursor = 0, carry_len = 0, prev_rows = 0, prev_carry = 0;
     size_t wi = 0;
     for (; ok && wi < nw; wi++) {
         {
+            const auto tw = std::chrono::steady_clock::now();
             std::unique_lock<std::mutex> lk(G.m);
             G.cv.wait(lk, [&] { return G.w[wi].state != 0; });
+            t_wait_reg += since(tw);
             if (G.w[wi].state != 1) break;                   // registration failed from here on: the staged path takes over
         }
         const int slot = (int)(wi & 1);
         if (wi >= 2) {
+            const auto tw = std::chrono::steady_clock::now();
             ok = cuda_ok(cudaEventSynchronize(R.reg_packed[slot]), "landing buffer wait");   // window wi-2 is tiled: its buffers are free,
-            std::lock_guard<std::mutex> lk(G.m);                                           // and its host pages may be released
-            G.consumed = wi - 1;
-            G.cv.notify_all();
+            t_wait_dev += since(tw);
         }
+        { std::lock_guard<std::mutex> lk(G.m); G.consumed = wi; G.cv.notify_all(); }   // the helper stays `ahead` windows in front
+        const auto ti = std::chrono::steady_clock::now();
         const uintptr_t hs = G.w[wi].lo < base ? base : G.w[wi].lo;
         const uintptr_t he = G.w[wi].hi > base + total ? base + total : G.w[wi].hi;
         const size_t len = he - hs;
@@ -228,13 +227,15 @@ static size_t upload_registered(Resident* r, const apop_data* d, bool col0, int 
         prev_rows = rows; prev_carry = carry_len;
         carry_len = avail - rows * rb;
         row_cursor += rows;
+        t_issue += since(ti);
     }
     ok = ok && cuda_ok(cudaStreamSynchronize(R.stream), "pin sync") && cuda_ok(cudaStreamSynchronize(R.copy_stream), "pin sync");
-    finish(nw);
+    finish(true);
     R.last_pin_mode = 1;
     if (trace)
-        fprintf(stderr, "[apop_b200 pin] registered windows: %zu of %zu rows from %zu of %zu windows in %.3f s (first window page-locked at %.1f GB/s)\n",
-                row_cursor, n, wi, nw, std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count(), G.first_rate);
+        fprintf(stderr, "[apop_b200 pin] registered windows: %zu of %zu rows from %zu of %zu windows in %.3f s (first window page-locked at %.1f GB/s); "
+                        "main thread: waiting for page-lock %.3f s, for the device %.3f s, issuing %.3f s; helper: page-locking %.3f s (kept while resident)\n",
+                row_cursor, n, wi, nw, since(t_begin), G.first_rate, t_wait_reg, t_wait_dev, t_issue, G.t_register);
     return row_cursor;
 }
 
@@ -273,6 +274,7 @@ bool upload(Resident* r, const apop_data* d) {
     if (!need) return true;
 
     R.last_pin_mode = 0;
+    release_host_registration(r);   // a refresh means the memory behind the pointer may be other pages now
     size_t first_row = 0;
     {
         bool okr = true;
@@ -402,6 +404,8 @@ extern "C" int apop_b200_invalidate(apop_data* d) {
     if (it->second->synthetic) return 1;
     it->second->dirty = true;
     it->second->memo_valid = false;
+    cudaSetDevice(rt().device);
+    release_host_registration(it->second);   // the caller is about to change (or has changed) that memory
     return 0;
 }
 extern "C" int apop_b200_is_pinned(const apop_data* d) {

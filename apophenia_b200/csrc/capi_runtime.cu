@@ -102,8 +102,14 @@ extern "C" int apop_b200_init(int device) {
     return 0;
 }
 
+void release_host_registration(Resident* r) {
+    for (auto& w : r->host_registered) cudaHostUnregister(w.first);
+    if (!r->host_registered.empty()) cudaGetLastError();   // a range the caller already unmapped is not an error worth keeping
+    r->host_registered.clear();
+}
 void free_resident(Resident* r) {
     if (!r) return;
+    release_host_registration(r);
     if (r->tiles) cudaFree(r->tiles);
     if (r->counts) cudaFree(r->counts);
     if (r->lgy) cudaFree(r->lgy);

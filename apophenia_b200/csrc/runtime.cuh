@@ -61,6 +61,9 @@ struct Resident {
     // copy that still holds the raw outcomes re-applies the table
     bool recoded = false, recode_pending = false;
     CatTable cats;
+    // windows of the caller's matrix this library page-locked for a zero-copy upload and keeps page-locked
+    // while the copy is resident (a registration cache: released by unpin / invalidate / re-upload / finalize)
+    std::vector<std::pair<void*, size_t>> host_registered;
 };
 
 struct NcclApi {

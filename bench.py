@@ -416,12 +416,7 @@ def run_e2e(cx, fam, beta_true):
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
         n = int(t[0])
     # host data set: the same synthetic recipe, generated on the device and copied back
-    src = ab.synth(fam, n, k, beta_true, ncat=args.ncat, seed=8, row_offset=rank * n)
-    # the host matrix sits on transparent huge pages (anonymous mmap + MADV_HUGEPAGE: what
-    # GLIBC_TUNABLES=glibc.malloc.hugetlb=1 gives a C caller's gsl_matrix_alloc), which lets the upload page-lock
-    # it in place and DMA straight out of it; --host-pages 4k keeps ordinary pages
-    X, y = src.download(hugepages=args.host_pages == "thp")
-    src.free()
+    X, y = host_dataset(ab, fam, n, k, beta_true, args.ncat, rank * n, args.host_pages)
     d = ab.Data(matrix=X, vector=y)
     cx.barrier()
     t0 = time.perf_counter()
@@ -470,6 +465,26 @@ def run_e2e(cx, fam, beta_true):
                 "what": "host apop_data -> pin (H2D of X, y + tiling) -> probit MLE (BFGS) -> estimates; rows x optimizer "
                         "evaluations / total seconds", "fit_from_host": fit, "resident_step": resident, "cold": cold}
     return dict(resident, rows_per_gpu=n, api=api, cold=cold, fit_from_host=fit)
+
+
+def host_dataset(ab, fam, n, k, beta_true, ncat, row_offset, pages):
+    """The e2e host data set: the synthetic recipe generated on the device window by window, copied back, and
+    written into the host matrix by the CPU -- as a caller that parsed or computed its data would have.  With
+    pages == "thp" the matrix sits on transparent huge pages (anonymous mmap + MADV_HUGEPAGE: what
+    GLIBC_TUNABLES=glibc.malloc.hugetlb=1 gives a C caller's gsl_matrix_alloc), which the upload can page-lock in
+    place at ~50 GB/s and DMA straight out of; "4k" keeps ordinary pages (page-locking at ~10 GB/s: the library
+    then stages through pinned buffers instead)."""
+    X = ab.host_empty((n, k), hugepages=(pages == "thp"))
+    y = np.empty(n)
+    chunk = 4_000_000
+    for lo in range(0, n, chunk):
+        rows = min(chunk, n - lo)
+        src = ab.synth(fam, rows, k, beta_true, ncat=ncat, seed=8, row_offset=row_offset + lo)
+        Xc, yc = src.download()
+        src.free()
+        X[lo:lo + rows] = Xc
+        y[lo:lo + rows] = yc
+    return X, y
 
 
 def run_fit_from_host(cx, d, k):
