@@ -107,6 +107,8 @@ SIGNATURES = {
     "apop_b200_is_pinned": (C.c_int, [_PD]),
     "apop_b200_set_auto_pin": (None, [C.c_int]),
     "apop_b200_last_pin_mode": (C.c_int, [C.POINTER(C.c_double)]),
+    "apop_b200_host_alloc": (C.c_void_p, [C.c_size_t]),
+    "apop_b200_host_free": (None, [C.c_void_p]),
     "apop_b200_set_timing": (None, [C.c_int]),
     "apop_b200_set_local_only": (None, [C.c_int]),
     "apop_b200_global_rows": (C.c_double, [_PD]),

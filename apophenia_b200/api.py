@@ -68,17 +68,27 @@ def last_pin_mode():
     """('staged' | 'registered', page-locking GB/s measured on the first window) of the most recent upload"""
     r = C.c_double(0.0)
     m = _lib().apop_b200_last_pin_mode(C.byref(r))
-    return ("registered" if m == 1 else "staged"), float(r.value)
+    return {0: "staged", 1: "registered", 2: "zero-copy (page-locked source)"}.get(m, str(m)), float(r.value)
 
 
-def host_empty(shape, hugepages=True):
-    """A page-aligned float64 host array.  With hugepages the anonymous mapping is advised to transparent
-    huge pages -- what GLIBC_TUNABLES=glibc.malloc.hugetlb=1 does for a C caller's gsl_matrix_alloc --
-    which cudaHostRegister page-locks about five times faster than 4 KB pages (tools/pin_probe2.py)."""
+def host_empty(shape, hugepages=True, pinned=False):
+    """A page-aligned float64 host array.  pinned: page-locked memory from apop_b200_host_alloc (cudaHostAlloc) --
+    apop_b200_pin then reads it in place (zero copy).  Otherwise an anonymous mapping, with hugepages advised to
+    transparent huge pages (what GLIBC_TUNABLES=glibc.malloc.hugetlb=1 does for a C caller's gsl_matrix_alloc)."""
     import mmap
     n = int(np.prod(shape))
     if n == 0:
         return np.zeros(shape)
+    if pinned:
+        import weakref
+        lib = _lib()
+        p = lib.apop_b200_host_alloc(n * 8)
+        if not p:
+            raise B200Error("apop_b200_host_alloc failed: " + abi.last_error())
+        raw = (C.c_double * n).from_address(p)
+        a = np.frombuffer(raw, dtype=np.float64, count=n).reshape(shape)
+        weakref.finalize(raw, lib.apop_b200_host_free, p)
+        return a
     buf = mmap.mmap(-1, n * 8, flags=mmap.MAP_PRIVATE | mmap.MAP_ANONYMOUS)
     a = np.frombuffer(buf, dtype=np.float64, count=n).reshape(shape)
     if hugepages:

@@ -42,14 +42,17 @@ static bool sig_stale(const Resident* r, const apop_data* d) {
 // cudaMemcpyAsync straight from the caller's memory into a device landing buffer, and the tiling kernel
 // re-lays it (rows that straddle a window boundary are carried over device-side).  The outcome and weight
 // vectors (3 % of the bytes) still go through a small pinned staging buffer.
-// Measured on the pool box (tools/pin_probe2.py, tools/pin_modes.py): page-locking runs at 9-12 GB/s on 4 KB
-// pages and 42-53 GB/s on transparent huge pages (GLIBC_TUNABLES=glibc.malloc.hugetlb=1 gives them to a
-// malloc'ing caller), releasing the pages at 36 GB/s, and both calls serialise with the copy submissions on the
-// driver's lock.  So the windows stay page-locked while the data set is resident (a registration cache, as
-// MPI / UCX keep one; released by unpin / invalidate / re-upload / finalize), and the mode is chosen per upload:
-// APOP_B200_PIN_MODE=auto (default) page-locks the first window, compares its rate with what this rank's share
-// of the host threads can gather (one rank with 16 threads stages at 41-48 GB/s and keeps doing so; eight ranks
-// with two threads each do not), and goes on zero-copy or falls back; =register / =staged force either.
+// Two cases:
+//  * the caller's matrix is page-locked already (allocated with apop_b200_host_alloc / cudaHostAlloc, or
+//    registered by the caller): always taken, no page-locking here.  This is the multi-GPU deployment path.
+//  * pageable memory, APOP_B200_PIN_MODE=register only: a helper thread page-locks the windows ahead of the copy
+//    and they stay page-locked while the data set is resident (a registration cache, as MPI / UCX keep one;
+//    released by unpin / invalidate / re-upload / finalize).  It is NOT the default, by measurement on the pool
+//    boxes (tools/pin_probe2.py, pin_probe3.py, pin_modes.py; profiles/README.md): cudaHostRegister runs at 9-12
+//    GB/s on 4 KB pages and 38-53 GB/s on transparent huge pages first touched by the CPU, cudaHostUnregister at
+//    36 GB/s, both serialise with the copy submissions on the driver's lock, and -- decisive -- two ranks
+//    page-locking at once drop to 14 GB/s each (7 GB/s on a second registration of the same pages), below what
+//    the staged path gives them (26 GB/s each), while one rank alone stages at 41-48 GB/s against 38.
 struct RegWindow { uintptr_t lo, hi; int state; bool ours; };   // state: 0 pending, 1 registered, 2 failed
 struct Registrar {
     std::mutex m;
@@ -107,7 +110,18 @@ static size_t upload_registered(Resident* r, const apop_data* d, bool col0, int 
     if (mode == 1 || !d->matrix || k < 1 || d->matrix->tda != (size_t)k) return 0;
     if ((hy && d->vector->stride != 1) || (hw && d->weights->stride != 1)) return 0;
     const size_t rb = (size_t)k * sizeof(double), total = n * rb;
-    if (total < ((size_t)256 << 20) && mode != 2) return 0;          // small data: the staged path is simpler and as fast
+    if (total < ((size_t)8 << 20) && mode != 2) return 0;            // small data: the staged path is simpler and as fast
+    // Is the caller's matrix page-locked already (cudaHostAlloc / apop_b200_host_alloc / its own cudaHostRegister)?
+    // Then the DMA engine reads it as it is: no page-locking here, no helper thread, no host copy at all.
+    auto pinned_ptr = [](const void* p) {
+        cudaPointerAttributes a;
+        if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+        return a.type == cudaMemoryTypeHost;
+    };
+    const bool pinned_src = pinned_ptr(d->matrix->data) && pinned_ptr((const char*)d->matrix->data + total - 1);
+    // pageable memory is page-locked here only on request (APOP_B200_PIN_MODE=register): measured on the pool
+    // boxes it loses to the staged path for one rank and does not scale over the ranks of one host (see above)
+    if (!pinned_src && mode != 2) return 0;
     const size_t PAGE = 4096, ALIGN = (size_t)2 << 20;
     size_t WB = (size_t)128 << 20;                                    // window: a multiple of the 2 MB huge-page size
     if (const char* e = getenv("APOP_B200_PIN_WINDOW_MB")) { const long mb = atol(e); if (mb >= 2) WB = (size_t)(mb / 2 * 2) << 20; }
@@ -149,11 +163,13 @@ static size_t upload_registered(Resident* r, const apop_data* d, bool col0, int 
 
     static const bool trace = getenv("APOP_B200_PIN_TRACE") != nullptr;
     const auto t_begin = std::chrono::steady_clock::now();
-    std::thread worker([&G] { G.run(); });
+    if (pinned_src) for (auto& x : G.w) { x.state = 1; x.ours = false; }   // nothing to page-lock
+    std::thread worker;
+    if (!pinned_src) worker = std::thread([&G] { G.run(); });
     // stops the helper; keep = the page-locked windows stay with the resident copy, else they are released now
     auto finish = [&](bool keep) {
         { std::lock_guard<std::mutex> lk(G.m); G.stop = true; G.cv.notify_all(); }
-        worker.join();
+        if (worker.joinable()) worker.join();
         for (auto& x : G.w)
             if (x.state == 1 && x.ours) {
                 if (keep) r->host_registered.push_back({(void*)x.lo, (size_t)(x.hi - x.lo)});
@@ -166,11 +182,9 @@ static size_t upload_registered(Resident* r, const apop_data* d, bool col0, int 
         const size_t probe = nw > 1 ? 1 : 0;
         G.cv.wait(lk, [&] { return G.w[probe].state != 0; });
     }
-    R.last_register_GBps = G.first_rate;
-    // what the staged path can be expected to deliver: ~3.2 GB/s per gathering host thread of this rank (measured:
-    // 16 threads 41-48 GB/s, 2 threads 7.6 GB/s), capped by the PCIe link
-    const double need_rate = std::min(50.0, 3.2 * HostPool::get().size());
-    if (G.w[0].state != 1 || (mode == 0 && G.first_rate < need_rate)) {
+    R.last_register_GBps = pinned_src ? 0.0 : G.first_rate;
+    const double need_rate = 0.0;
+    if (G.w[0].state != 1) {
         if (trace) fprintf(stderr, "[apop_b200 pin] registered windows not used: first window %s at %.1f GB/s (need %.0f)\n",
                            G.w[0].state == 1 ? "page-locked" : "could not be page-locked", G.first_rate, need_rate);
         finish(false);
@@ -231,7 +245,7 @@ static size_t upload_registered(Resident* r, const apop_data* d, bool col0, int 
     }
     ok = ok && cuda_ok(cudaStreamSynchronize(R.stream), "pin sync") && cuda_ok(cudaStreamSynchronize(R.copy_stream), "pin sync");
     finish(true);
-    R.last_pin_mode = 1;
+    R.last_pin_mode = pinned_src ? 2 : 1;
     if (trace)
         fprintf(stderr, "[apop_b200 pin] registered windows: %zu of %zu rows from %zu of %zu windows in %.3f s (first window page-locked at %.1f GB/s); "
                         "main thread: waiting for page-lock %.3f s, for the device %.3f s, issuing %.3f s; helper: page-locking %.3f s (kept while resident)\n",

@@ -169,6 +169,21 @@ extern "C" double apop_b200_pass_timer_total_ms(unsigned long long* n) {
 }
 extern "C" void apop_b200_set_auto_pin(int on) { rt().auto_pin = on != 0; }
 extern "C" void apop_b200_set_timing(int on) { rt().timing = on != 0; }
+// Page-locked host memory for the caller's matrix / vector blocks: the upload then needs no host copy
+extern "C" void* apop_b200_host_alloc(size_t bytes) {
+    LOCK;
+    if (!require_ready()) return nullptr;
+    cudaSetDevice(rt().device);
+    void* p = nullptr;
+    if (!cuda_ok(cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable), "cudaHostAlloc")) return nullptr;
+    return p;
+}
+extern "C" void apop_b200_host_free(void* p) {
+    if (!p) return;
+    LOCK;
+    if (rt().ready) cudaSetDevice(rt().device);
+    cudaFreeHost(p);
+}
 extern "C" int apop_b200_last_pin_mode(double* register_GBps) {
     if (register_GBps) *register_GBps = rt().last_register_GBps;
     return rt().last_pin_mode;

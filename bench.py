@@ -60,7 +60,7 @@ def parse():
     ap.add_argument("--no-configs", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--configs", default="cfg2,cfg3,cfg4,cfg5", help="which BASELINE configurations to run")
-    ap.add_argument("--host-pages", default="thp", choices=["thp", "4k"], help="pages behind the e2e host matrix")
+    ap.add_argument("--host-pages", default="pinned", choices=["pinned", "thp", "4k"], help="memory behind the e2e host matrix")
     ap.add_argument("--sustain-seconds", type=float, default=2.0, help="length of the back-to-back (sustained) run")
     return ap.parse_args()
 
@@ -469,12 +469,11 @@ def run_e2e(cx, fam, beta_true):
 
 def host_dataset(ab, fam, n, k, beta_true, ncat, row_offset, pages):
     """The e2e host data set: the synthetic recipe generated on the device window by window, copied back, and
-    written into the host matrix by the CPU -- as a caller that parsed or computed its data would have.  With
-    pages == "thp" the matrix sits on transparent huge pages (anonymous mmap + MADV_HUGEPAGE: what
-    GLIBC_TUNABLES=glibc.malloc.hugetlb=1 gives a C caller's gsl_matrix_alloc), which the upload can page-lock in
-    place at ~50 GB/s and DMA straight out of; "4k" keeps ordinary pages (page-locking at ~10 GB/s: the library
-    then stages through pinned buffers instead)."""
-    X = ab.host_empty((n, k), hugepages=(pages == "thp"))
+    written into the host matrix by the CPU -- as a caller that parsed or computed its data would have.
+    pages == "pinned" (default; the bench contract copies its inputs from pinned host memory): the matrix block comes
+    from apop_b200_host_alloc (cudaHostAlloc), so apop_b200_pin lets the DMA engine read it in place; "thp" / "4k":
+    pageable memory (huge or ordinary pages), which the library gathers through pinned staging buffers."""
+    X = ab.host_empty((n, k), hugepages=(pages == "thp"), pinned=(pages == "pinned"))
     y = np.empty(n)
     chunk = 4_000_000
     for lo in range(0, n, chunk):

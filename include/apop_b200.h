@@ -181,11 +181,21 @@ int apop_b200_unpin(apop_data *d);
  * re-upload on next use. */
 int apop_b200_invalidate(apop_data *d);
 int apop_b200_is_pinned(const apop_data *d);
-/* How the most recent upload crossed PCIe: 0 = staged (host threads gather into pinned staging), 1 = zero
- * copy (the caller's matrix page-locked window by window and read by the DMA engine directly; chosen when
- * the matrix is contiguous and page-locking it is fast enough -- APOP_B200_PIN_MODE=auto|staged|register).
- * register_GBps (may be NULL) receives the page-locking rate measured on the first window. */
+/* How the most recent upload crossed PCIe:
+ *   0  staged: host threads gather the caller's (pageable, possibly strided) buffers into pinned staging,
+ *      one cudaMemcpyAsync per chunk, tiling on the device -- the default for pageable memory;
+ *   2  zero copy from a page-locked source: the caller's matrix was allocated with apop_b200_host_alloc /
+ *      cudaHostAlloc (or registered by the caller), so the DMA engine reads it in place, one cudaMemcpyAsync per
+ *      128 MB window -- chosen automatically, and the way to feed several GPUs from one host;
+ *   1  zero copy from pageable memory page-locked by the library window by window (APOP_B200_PIN_MODE=register
+ *      only; the pages stay locked while the data set is resident).  Measured slower than staging on the pool
+ *      boxes, see DESIGN.md.
+ * register_GBps (may be NULL) receives the page-locking rate measured in mode 1. */
 int apop_b200_last_pin_mode(double *register_GBps);
+/* Page-locked host memory for the data blocks of an apop_data (gsl_block.data): what gsl_matrix_alloc would
+ * malloc, allocated with cudaHostAlloc instead, so that apop_b200_pin needs no host-side copy at all. */
+void *apop_b200_host_alloc(size_t bytes);
+void apop_b200_host_free(void *p);
 /* unpinned data policy: 0 = upload per call and drop (always correct, default),
  * 1 = pin on first sight and trust the caller to invalidate. */
 void apop_b200_set_auto_pin(int on);

@@ -459,3 +459,22 @@ def test_registered_window_upload_roundtrip(b200, monkeypatch):
     ds = ab.pin(ab.Data(matrix=X20, vector=yp))
     assert ll_r == ab.log_likelihood(ab.PROBIT, ds, ab.probit_model(beta[:20], ds))
     ab.unpin(dr); ab.unpin(ds)
+
+
+def test_page_locked_source_goes_zero_copy(b200, oracle):
+    """a matrix allocated with apop_b200_host_alloc is read in place by the DMA engine (mode 2), chosen without any
+    switch; results are those of the staged upload of the same numbers"""
+    ab = b200
+    X, y, beta = gen_probit_logit_sample(70_001, 30, seed=14)     # 16.8 MB: above the 8 MB threshold
+    Xp = ab.host_empty(X.shape, pinned=True)
+    Xp[:] = X
+    d = ab.pin(ab.Data(matrix=Xp, vector=y))
+    assert ab.last_pin_mode()[0].startswith("zero-copy")
+    ll, g = ab.ll_score(ab.PROBIT, d, beta)
+    ab.unpin(d)
+    d2 = ab.pin(ab.Data(matrix=X, vector=y))
+    assert ab.last_pin_mode()[0] == "staged"
+    ll2, g2 = ab.ll_score(ab.PROBIT, d2, beta)
+    ab.unpin(d2)
+    assert ll == ll2 and np.array_equal(g, g2)
+    assert _rel(ll, oracle.probit_ll(X, y, beta, oracle.EXACT)) <= 1e-12
