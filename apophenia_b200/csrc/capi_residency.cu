@@ -250,9 +250,7 @@ static size_t upload_registered(Resident* r, const apop_data* d, bool col0, int 
         fprintf(stderr, "[apop_b200 pin] zero copy (%s): %zu of %zu rows from %zu of %zu windows in %.3f s = %.1f GB/s; main thread: waiting for "
                         "page-lock %.3f s, for the device %.3f s, issuing %.3f s; helper: page-locking %.3f s (best of the first two windows %.1f GB/s)\n",
                 pinned_src ? "source already page-locked" : "windows page-locked here, kept while resident", row_cursor, n, wi, nw, since(t_begin),
-                row_cursor * rb * 1e-9 / since(t_begin), t_wait_reg, t_wait_dev, t_issue, G.t_register, G.first_rate); "
-                        "main thread: waiting for page-lock %.3f s, for the device %.3f s, issuing %.3f s; helper: page-locking %.3f s (kept while resident)\n",
-                row_cursor, n, wi, nw, since(t_begin), G.first_rate, t_wait_reg, t_wait_dev, t_issue, G.t_register);
+                row_cursor * rb * 1e-9 / since(t_begin), t_wait_reg, t_wait_dev, t_issue, G.t_register, G.first_rate);
     return row_cursor;
 }
 
