@@ -34,6 +34,14 @@ __device__ __forceinline__ void dmma_8x8x4(double& d0, double& d1, double a, dou
 // lane q = (r%8)/2 owns bytes q*8 .. q*8+7, ordered (nb = r/8, e = r%2)
 __host__ __device__ __forceinline__ int count_pos(int r) { return ((r & 7) >> 1) * 8 + (r >> 3) * 2 + (r & 1); }
 
+// the per-row constant a family leaves out of s[0] (Poisson regression: -lgamma(y+1)); with resample counts it
+// is weighted by the replicate's multiplicity, so it has to be part of the row term
+template <class Fam, bool ON>
+__device__ __forceinline__ double row_const_of(double y) {
+    if constexpr (ON && Fam::ROW_CONST) return Fam::row_const(y);
+    else return 0.0;
+}
+
 template <int KB, class Fam, bool WANT_SCORE, bool USE_COUNTS, int MB>
 __global__ void __launch_bounds__(BATCH_THREADS, (MB == 1) ? 2 : 1)
 batched_kernel(const double* __restrict__ tiles, const unsigned long long n_rows, const unsigned long long n_tiles,
@@ -115,8 +123,9 @@ batched_kernel(const double* __restrict__ tiles, const unsigned long long n_rows
                     const unsigned long long row = t * TILE_ROWS + nb * 8 + 2 * q + e;
                     const double c = (row < n_rows) ? (double)((cbits >> (8 * (nb * 2 + e))) & 0xffull) : 0.0;
                     const RowOut o = Fam::eval(S[mb][nb][e], yv[nb][e], 1.0, aux);
-                    if (WANT_SCORE) ll[mb].add(c != 0.0 ? c * o.s[0] : 0.0);
-                    else lsum += c != 0.0 ? c * o.s[0] : 0.0;
+                    const double term = o.s[0] + row_const_of<Fam, USE_COUNTS>(yv[nb][e]);
+                    if (WANT_SCORE) ll[mb].add(c != 0.0 ? c * term : 0.0);
+                    else lsum += c != 0.0 ? c * term : 0.0;
                     S[mb][nb][e] = c != 0.0 ? c * o.d : 0.0;   // S now holds D^T
                 }
             if (!WANT_SCORE) ll[mb].add(lsum);
@@ -160,6 +169,180 @@ batched_kernel(const double* __restrict__ tiles, const unsigned long long n_rows
             }
         }
     }
+}
+
+
+// ---------------------------------------------------------------------------------------
+// Shared-centre variant (the default when the caller's m parameter vectors lie close together, as the
+// replicates of a bootstrap and the chains of a sampler do): stage 2 evaluates the family's row term by its
+// degree-6 Taylor polynomial around x0_i = x_i . centre (families.cuh: Taylor<Fam>), whose coefficients are
+// computed once per row and shared by every replicate -- ~15 FP64 operations per (row, replicate) pair instead of
+// the ~85 of a probit link evaluation.  A pair with |x_i.beta_r - x0_i| > delta_max, or a row whose x0 lies in
+// the clamp region of the reference formula, takes the exact evaluation (a divergent branch, rare by
+// construction), so the result never depends on the closeness assumption.
+//   phase A  the 8 warps of the CTA take the next 8 tiles of the CTA's row group, one each, lane = row:
+//            x0, the exact Fam::eval at x0, the coefficients -> a shared slab [8 tiles][NC][32 rows];
+//   phase B  all 8 warps walk those 8 tiles as before (stage 1 DMMA, stage 2 Horner, stage 3 DMMA), reading
+//            the coefficients of their rows back as 16-byte pairs (rows 2q, 2q+1).
+// ---------------------------------------------------------------------------------------
+template <int KB, class Fam, bool WANT_SCORE, bool USE_COUNTS>
+__global__ void __launch_bounds__(BATCH_THREADS, 2)
+batched_taylor_kernel(const double* __restrict__ tiles, const unsigned long long n_rows, const unsigned long long n_tiles,
+                      const int K, const int cols, const double* __restrict__ Bmat, const int P, const int m,
+                      const unsigned char* __restrict__ counts, const int m_pad, const double4 aux4,
+                      const int n_rowgroups, double* __restrict__ partials, const double* __restrict__ centre,
+                      const double delta_max, unsigned long long* __restrict__ exact_slots) {
+    constexpr int WARPS = BATCH_THREADS / 32;
+    constexpr int KS = KB / 4, JB = KB / 8;
+    constexpr int NC = WANT_SCORE ? 13 : 8;     // x0, a0..a6 [, 2 a2, 3 a3, 4 a4, 5 a5, 6 a6]
+    __shared__ __align__(16) double slab[WARPS][NC][TILE_ROWS];
+    __shared__ double s_centre[MAX_K_REG];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, q = lane & 3;
+    const int n_repgroups = (m + WARPS * 8 - 1) / (WARPS * 8);
+    const int repgroup = blockIdx.x % n_repgroups;
+    const int rowgroup = blockIdx.x / n_repgroups;
+    if (rowgroup >= n_rowgroups) return;
+    const int rep0 = (repgroup * WARPS + warp) * 8;
+    const int rep = rep0 + g;
+    const double aux[4] = {aux4.x, aux4.y, aux4.z, aux4.w};
+    if (threadIdx.x < MAX_K_REG) s_centre[threadIdx.x] = ((int)threadIdx.x < K) ? centre[threadIdx.x] : 0.0;
+
+    double bfrag[KS];
+#pragma unroll
+    for (int ks = 0; ks < KS; ks++) {
+        const int j = ks * 4 + q;
+        bfrag[ks] = (rep < m && j < K) ? Bmat[(size_t)rep * P + j] : 0.0;
+    }
+    double G[JB][2];
+#pragma unroll
+    for (int jb = 0; jb < JB; jb++) G[jb][0] = G[jb][1] = 0.0;
+    KSum ll;
+    unsigned int n_exact = 0;     // (tile, row-slot) steps on which this warp ran the exact evaluation
+    __syncthreads();
+
+    for (unsigned long long t0 = rowgroup; t0 < n_tiles; t0 += (unsigned long long)n_rowgroups * WARPS) {
+        // ---- phase A: this warp prepares tile t0 + warp * n_rowgroups
+        {
+            const unsigned long long t = t0 + (unsigned long long)warp * n_rowgroups;
+            if (t < n_tiles) {
+                const double* tile = tiles + t * (unsigned long long)(cols * TILE_ROWS);
+                double x0 = 0.0;
+                for (int j = 0; j < K; j++) x0 = fma(__ldg(tile + j * TILE_ROWS + lane), s_centre[j], x0);
+                const double y = __ldg(tile + K * TILE_ROWS + lane);
+                const RowOut o = Fam::eval(x0, y, 1.0, aux);
+                double a[TAYLOR_D + 1];
+                const bool ok = Taylor<Fam>::coefs(x0, y, o, aux, a) && (t * TILE_ROWS + lane < n_rows);
+                a[0] += row_const_of<Fam, USE_COUNTS>(y);
+                slab[warp][0][lane] = ok ? x0 : __longlong_as_double(0x7ff8000000000000ll);   // NaN: every pair of the row goes exact
+#pragma unroll
+                for (int n = 0; n <= TAYLOR_D; n++) slab[warp][1 + n][lane] = a[n];
+                if (WANT_SCORE) {
+#pragma unroll
+                    for (int n = 2; n <= TAYLOR_D; n++) slab[warp][6 + n][lane] = (double)n * a[n];
+                }
+            }
+        }
+        __syncthreads();
+        // ---- phase B: every warp walks the 8 prepared tiles
+        for (int i = 0; i < WARPS; i++) {
+            const unsigned long long t = t0 + (unsigned long long)i * n_rowgroups;
+            if (t >= n_tiles || rep0 >= m) break;          // (a warp beyond the last replicate only helps with phase A)
+            const double* tile = tiles + t * (unsigned long long)(cols * TILE_ROWS);
+            double S[4][2];
+#pragma unroll
+            for (int nb = 0; nb < 4; nb++) S[nb][0] = S[nb][1] = 0.0;
+#pragma unroll
+            for (int ks = 0; ks < KS; ks++) {
+                const int j = ks * 4 + q;
+                double xf[4];
+#pragma unroll
+                for (int nb = 0; nb < 4; nb++) xf[nb] = (j < K) ? __ldg(tile + j * TILE_ROWS + nb * 8 + g) : 0.0;
+#pragma unroll
+                for (int nb = 0; nb < 4; nb++) dmma_8x8x4(S[nb][0], S[nb][1], bfrag[ks], xf[nb]);
+            }
+            unsigned long long cbits = (rep < m) ? 0x0101010101010101ull : 0ull;   // a lane without a replicate contributes nothing
+            if (USE_COUNTS)
+                cbits = (rep < m) ? __ldg(reinterpret_cast<const unsigned long long*>(
+                                        counts + (t * (unsigned long long)m_pad + rep) * TILE_ROWS + q * 8))
+                                  : 0ull;
+            double lsum = 0.0;
+#pragma unroll
+            for (int nb = 0; nb < 4; nb++) {
+                double2 c[NC];
+#pragma unroll
+                for (int n = 0; n < NC; n++) c[n] = *reinterpret_cast<const double2*>(&slab[i][n][nb * 8 + 2 * q]);
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const unsigned long long row = t * TILE_ROWS + nb * 8 + 2 * q + e;
+                    const double cnt = (row < n_rows) ? (double)((cbits >> (8 * (nb * 2 + e))) & 0xffull) : 0.0;
+#define APB_C(n) (e ? c[n].y : c[n].x)
+                    const double xb = S[nb][e];
+                    const double dl = xb - APB_C(0);
+                    double llv = fma(dl, APB_C(7), APB_C(6));
+                    llv = fma(dl, llv, APB_C(5));
+                    llv = fma(dl, llv, APB_C(4));
+                    llv = fma(dl, llv, APB_C(3));
+                    llv = fma(dl, llv, APB_C(2));
+                    llv = fma(dl, llv, APB_C(1));
+                    double dv = 0.0;
+                    if (WANT_SCORE) {
+                        dv = fma(dl, APB_C(12), APB_C(11));
+                        dv = fma(dl, dv, APB_C(10));
+                        dv = fma(dl, dv, APB_C(9));
+                        dv = fma(dl, dv, APB_C(8));
+                        dv = fma(dl, dv, APB_C(2));
+                    }
+#undef APB_C
+                    // outside the radius (also: the NaN of a row outside the Taylor range): the exact evaluation.  The
+                    // branch is taken by the whole warp (Fam::eval votes warp-wide for its fast exponential), each
+                    // lane keeps what it needs
+                    const bool exact = !(fabs(dl) <= delta_max) && cnt != 0.0;
+                    if (__any_sync(0xffffffffu, exact)) {
+                        n_exact++;
+                        const double2 y2 = __ldg(reinterpret_cast<const double2*>(tile + K * TILE_ROWS + nb * 8 + 2 * q));
+                        const RowOut o = Fam::eval(xb, e ? y2.y : y2.x, 1.0, aux);
+                        llv = exact ? o.s[0] + row_const_of<Fam, USE_COUNTS>(e ? y2.y : y2.x) : llv;
+                        dv = exact ? o.d : dv;
+                    }
+                    lsum += cnt != 0.0 ? cnt * llv : 0.0;
+                    S[nb][e] = cnt != 0.0 ? cnt * dv : 0.0;            // S now holds D^T
+                }
+            }
+            ll.add(lsum);
+            if (WANT_SCORE) {
+#pragma unroll
+                for (int jb = 0; jb < JB; jb++) {
+                    const int j = jb * 8 + g;
+#pragma unroll
+                    for (int nb = 0; nb < 4; nb++) {
+                        double2 x2 = make_double2(0.0, 0.0);
+                        if (j < K) x2 = __ldg(reinterpret_cast<const double2*>(tile + j * TILE_ROWS + nb * 8 + 2 * q));
+                        dmma_8x8x4(G[jb][0], G[jb][1], S[nb][0], x2.x);
+                        dmma_8x8x4(G[jb][0], G[jb][1], S[nb][1], x2.y);
+                    }
+                }
+            }
+        }
+        __syncthreads();      // the slab is rewritten by the next phase A
+    }
+
+    const int NOUT = 1 + KB;
+    double v = ll.value();
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    if (rep < m) {
+        double* dst = partials + ((size_t)rowgroup * m + rep) * NOUT;
+        if (q == 0) dst[0] = v;
+        if (WANT_SCORE) {
+#pragma unroll
+            for (int jb = 0; jb < JB; jb++) {
+                dst[1 + jb * 8 + 2 * q] = G[jb][0];
+                dst[1 + jb * 8 + 2 * q + 1] = G[jb][1];
+            }
+        }
+    }
+    if (lane == 0 && n_exact) atomicAdd(exact_slots, (unsigned long long)n_exact);   // the host's choice of kernel for the next passes
 }
 
 // sum the row-group partials in fixed order: out[rep][0..KB] (compensated)
@@ -217,6 +400,19 @@ bootstrap_counts_kernel(unsigned int* __restrict__ words, unsigned long long n_l
 template <int KB, class Fam>
 static cudaError_t launch_fam(const BatchedLaunch& L) {
     const double4 aux = make_double4(L.aux[0], L.aux[1], L.aux[2], L.aux[3]);
+    if (L.centre) {
+#define APB_TGO(S, C) batched_taylor_kernel<KB, Fam, S, C><<<L.grid, BATCH_THREADS, 0, L.stream>>>(L.tiles, L.n_rows, L.n_tiles, L.k, L.cols, \
+        L.B, L.P, L.m, L.counts, L.m_pad, aux, L.n_rowgroups, L.partials, L.centre, L.delta_max, L.exact_slots)
+        if (L.want_score) { if (L.counts) APB_TGO(true, true); else APB_TGO(true, false); }
+        else { if (L.counts) APB_TGO(false, true); else APB_TGO(false, false); }
+#undef APB_TGO
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        const int nout = 1 + KB;
+        const size_t total = (size_t)L.m * nout;
+        batched_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, L.stream>>>(L.partials, L.n_rowgroups, L.m, nout, L.out);
+        return cudaGetLastError();
+    }
 #define APB_GO(S, C)                                                                                          \
     do { if (L.mb == 1) batched_kernel<KB, Fam, S, C, 1><<<L.grid, BATCH_THREADS, 0, L.stream>>>(L.tiles, L.n_rows, L.n_tiles, L.k, L.cols, \
         L.B, L.P, L.m, L.counts, L.m_pad, aux, L.n_rowgroups, L.partials); \

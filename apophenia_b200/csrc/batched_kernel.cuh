@@ -22,6 +22,9 @@ struct BatchedLaunch {
     int mb;                       // replicate blocks of 8 per warp: 1 or 2
     bool want_score;
     cudaStream_t stream;
+    const double* centre = nullptr;   // device, P doubles: the shared expansion point (NULL: exact evaluation of every pair)
+    double delta_max = 0.0;           // |x.beta_r - x.centre| up to which the Taylor form is used
+    unsigned long long* exact_slots = nullptr;   // device counter: warp steps that needed the exact evaluation
 };
 int batched_kb(int k);
 cudaError_t batched_launch(int glm_fam, const BatchedLaunch& L);

@@ -165,7 +165,6 @@ extern "C" int apop_b200_ll_score_batched(apop_b200_family family, apop_data* d,
         if ((size_t)K != P) { set_error("batched path: P = %zu but the data has %d columns", P, K); break; }
         if (K < 1 || K > MAX_K_REG || !r->has_y) { set_error("batched path: needs 1..%d columns and an outcome vector", MAX_K_REG); break; }   // a weights column is ignored, as these families do
         if (use_counts && (!r->counts || r->counts_m < m)) { set_error("batched path: no resident resample counts for %zu replicates (call apop_b200_bootstrap_counts)", m); break; }
-        if (use_counts && fam == GLM_POISSON_REG) { set_error("batched path: resample counts are not supported for the Poisson regression constant"); break; }
         const int KB = batched_kb(K), NOUT = 1 + KB;
         static int mb_env = -1;
         if (mb_env < 0) { const char* e = getenv("APOP_B200_BATCH_MB"); mb_env = (e && e[0] == '2') ? 2 : 1; }
@@ -186,10 +185,32 @@ extern "C" int apop_b200_ll_score_batched(apop_b200_family family, apop_data* d,
         L.want_score = score != nullptr; L.stream = R.stream; L.mb = mb;
         if (!ensure_partials((size_t)n_rowgroups * m * NOUT)) break;
         L.partials = R.d_partials;
-        if (!cuda_ok(cudaMalloc(&dB, P * m * sizeof(double)), "cudaMalloc(B)")) break;
+        // The shared expansion point of the Taylor form of stage 2 (batched_kernel.cu): the mean of the m parameter
+        // vectors.  APOP_B200_BATCH_TAYLOR=0 evaluates every (row, replicate) pair exactly instead;
+        // APOP_B200_BATCH_DELTA overrides the radius (default 1.5e-2: truncation error < 1e-16 relative).
+        static int taylor_env = -1;
+        static double delta_env = 1.5e-2;
+        if (taylor_env < 0) {
+            const char* e = getenv("APOP_B200_BATCH_TAYLOR"); taylor_env = (e && e[0] == '0') ? 0 : 1;
+            if (const char* d2 = getenv("APOP_B200_BATCH_DELTA")) { const double v = atof(d2); if (v > 0) delta_env = v; }
+        }
+        bool taylor = taylor_env == 1 && mb == 1;
+        if (taylor && r->batched_exact_passes > 0) { r->batched_exact_passes--; taylor = false; }   // the vectors were too far apart last time
+        std::vector<double> Bc(B, B + P * m);
+        if (taylor) {
+            std::vector<long double> c(P, 0.0L);
+            for (size_t q = 0; q < m; q++) for (size_t j = 0; j < P; j++) c[j] += B[q * P + j];
+            for (size_t j = 0; j < P; j++) Bc.push_back((double)(c[j] / (long double)m));
+        }
+        if (!cuda_ok(cudaMalloc(&dB, Bc.size() * sizeof(double)), "cudaMalloc(B)")) break;
         if (!cuda_ok(cudaMalloc(&dOut, m * NOUT * sizeof(double)), "cudaMalloc(out)")) break;
-        if (!cuda_ok(cudaMemcpyAsync(dB, B, P * m * sizeof(double), cudaMemcpyHostToDevice, R.stream), "H2D B")) break;
+        if (!cuda_ok(cudaMemcpyAsync(dB, Bc.data(), Bc.size() * sizeof(double), cudaMemcpyHostToDevice, R.stream), "H2D B")) break;
         L.B = dB; L.out = dOut;
+        unsigned long long* d_exact = reinterpret_cast<unsigned long long*>(R.d_vals);
+        if (taylor) {
+            L.centre = dB + P * m; L.delta_max = delta_env; L.exact_slots = d_exact;
+            if (!cuda_ok(cudaMemsetAsync(d_exact, 0, sizeof(unsigned long long), R.stream), "memset")) break;
+        }
         time_begin();
         if (!cuda_ok(batched_launch((int)fam, L), "batched kernel launch")) break;
         time_end_record();
@@ -198,10 +219,21 @@ extern "C" int apop_b200_ll_score_batched(apop_b200_family family, apop_data* d,
             !nccl_ok(R.nccl.AllReduce(dOut, dOut, m * NOUT, 8, 0, R.comm, R.stream), "ncclAllReduce")) break;
         std::vector<double> h(m * NOUT);
         if (!cuda_ok(cudaMemcpyAsync(h.data(), dOut, m * NOUT * sizeof(double), cudaMemcpyDeviceToHost, R.stream), "D2H")) break;
+        unsigned long long n_exact = 0;
+        if (taylor && !cuda_ok(cudaMemcpyAsync(&n_exact, d_exact, sizeof n_exact, cudaMemcpyDeviceToHost, R.stream), "D2H")) break;
         if (!cuda_ok(cudaStreamSynchronize(R.stream), "stream sync")) break;
         time_collect();
+        if (taylor) {
+            // every warp makes 8 row-slot steps per tile for its 8 replicates; when more than a quarter of them needed the
+            // exact evaluation the shared-centre form costs more than it saves: the next 32 passes go exact, then re-probe
+            const double steps = (double)r->n_tiles * 8.0 * (double)((m + 7) / 8);
+            r->batched_last_exact_fraction = steps > 0 ? (double)n_exact / steps : 0.0;
+            if (r->batched_last_exact_fraction > 0.25) r->batched_exact_passes = 32;
+        }
         double lg = 0.0;
-        if (fam == GLM_POISSON_REG && !lgamma_const(r, lg)) break;
+        // Poisson regression: -sum lgamma(y+1) is one constant for a plain pass; with resample counts it is weighted per
+        // replicate and the kernels carry it per row
+        if (fam == GLM_POISSON_REG && !use_counts && !lgamma_const(r, lg)) break;
         for (size_t q = 0; q < m; q++) {
             ll[q] = h[q * NOUT] - lg;
             if (score) memcpy(score + q * P, h.data() + q * NOUT + 1, P * sizeof(double));
@@ -212,6 +244,14 @@ extern "C" int apop_b200_ll_score_batched(apop_b200_family family, apop_data* d,
     if (dOut) cudaFree(dOut);
     release(r);
     return ok ? 0 : 1;
+}
+
+// share of the warp steps of the last shared-centre batched pass over d that needed the exact evaluation
+// (0: every pair was within the Taylor radius; > 0.25 sends the next passes to the exact kernel); -1 if unknown
+extern "C" double apop_b200_batched_exact_fraction(const apop_data* d) {
+    LOCK;
+    auto it = rt().reg.find(d);
+    return it == rt().reg.end() ? -1.0 : it->second->batched_last_exact_fraction;
 }
 
 // resident resample counts back to the host as an n_rows x m row-major uint8 matrix (tests)

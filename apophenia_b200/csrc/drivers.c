@@ -324,7 +324,7 @@ apop_data *apop_bootstrap_cov(apop_data *data, apop_model *model, uint64_t seed,
     gsl_vector *b0 = apop_data_pack(model->parameters, NULL);
     const size_t P = b0->size, m = (size_t)iterations;
     const int binary = data->matrix && P == data->matrix->size2;
-    if (!batched || !counts || !(fam == 0 || (fam == 1 && binary)) ) {
+    if (!batched || !counts || !((fam == 0 && binary) || (fam == 1 && binary) || (fam == 5 && binary))) {
         gsl_vector_free(b0);
         return bootstrap_host_loop(data, model, seed, iterations, boot_store);
     }

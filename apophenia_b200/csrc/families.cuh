@@ -37,6 +37,7 @@ struct RowOut {
 struct FamProbit {
     static constexpr int NACC = 1;
     static constexpr bool USES_W = false;
+    static constexpr bool ROW_CONST = false;   // no beta-independent per-row term left out of s[0]
     APB_HD static RowOut eval(double xb, double y, double w, const double* aux) {
         RowOut o;
 #ifdef APB_USE_LIBM_DEVICE
@@ -76,6 +77,7 @@ struct FamProbit {
 struct FamLogit2 {
     static constexpr int NACC = 1;
     static constexpr bool USES_W = false;
+    static constexpr bool ROW_CONST = false;
     APB_HD static RowOut eval(double xb, double y, double w, const double* aux) {
         RowOut o;
         const bool chosen = (y != aux[0]);  // find_index: 0 = numeraire, else 1
@@ -113,6 +115,10 @@ struct FamLogit2 {
 struct FamPoissonReg {
     static constexpr int NACC = 1;
     static constexpr bool USES_W = false;
+    // s[0] leaves out -lgamma(y+1): summed once per residency for a plain pass; with resample counts it is
+    // weighted per replicate, so the batched kernels add it per row (row_const)
+    static constexpr bool ROW_CONST = true;
+    APB_HD static double row_const(double y) { return -lgamma(y + 1.0); }
     APB_HD static RowOut eval(double xb, double y, double w, const double* aux) {
         RowOut o;
 #ifdef APB_USE_LIBM_DEVICE
@@ -133,6 +139,7 @@ struct FamPoissonReg {
 struct FamOls {
     static constexpr int NACC = 3;
     static constexpr bool USES_W = true;
+    static constexpr bool ROW_CONST = false;
     APB_HD static RowOut eval(double xb, double y, double w, const double* aux) {
         RowOut o;
         const double e = xb - y;
@@ -141,6 +148,66 @@ struct FamOls {
         o.s[2] = (aux[0] != 0.0) ? w * e * e : log(w);   // aux[0]: the un-prepped score's sum w e^2 (capi_models.cu)
         o.d = w * e;
         return o;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Taylor coefficients of a family's row term around a centre x0, for the batched-beta kernel: the m
+// parameter vectors of a bootstrap or of parallel Metropolis chains lie within a few standard errors of
+// each other, so x_i.beta_r = x0_i + delta with |delta| ~ 1e-3, and
+//     ll_i(x0 + delta) = sum_n a_n delta^n,   d_i = dll_i/dxb = sum_n n a_n delta^(n-1)
+// to degree TAYLOR_D = 6 is exact to < 1e-16 relative for |delta| <= 1.5e-2 (|a_7| delta^7 <= 5e-5 * 1.7e-13;
+// for the score 7 |a_7| delta^6 <= 4e-15)
+// -- computed once per row and shared by all m replicates instead of one full link evaluation per
+// (row, replicate) pair.  a_0 and a_1 come from the exact evaluation at x0 (Fam::eval: the reference's
+// formula shape with its clamps); the higher ones are polynomials in the row's (x0, lambda) or (p).  A row
+// whose x0 lies near a clamp / saturation of the reference formula returns false and takes the exact path.
+// ---------------------------------------------------------------------------------------------
+constexpr int TAYLOR_D = 6;
+template <class Fam> struct Taylor;
+template <> struct Taylor<FamProbit> {
+    // ll(x) = g(s x), g = log Phi, s = +-1 by the outcome; l = phi(z)/Phi(z) = |d|, z = s x0; with l' = -l(l+z):
+    //   g2 = -l(l+z), g3 = l(l(2l+3z)+z^2-1), g4 = l(l(l(-6l-12z)-7z^2+4)-z^3+3z),
+    //   g5 = l(l(l(l(24l+60z)+50z^2-20)+15z^3-25z)+z^4-6z^2+3)        (derived with sympy, checked against mpmath)
+    APB_HD static bool coefs(double x0, double y, const RowOut& o, const double*, double* a) {
+        const double s = (y != 0.0) ? 1.0 : -1.0, z = s * x0, l = fabs(o.d), z2 = z * z;
+        a[0] = o.s[0];
+        a[1] = o.d;
+        a[2] = -0.5 * l * (l + z);
+        a[3] = s * l * (l * (2.0 * l + 3.0 * z) + z2 - 1.0) * (1.0 / 6.0);
+        a[4] = l * (l * (l * (-6.0 * l - 12.0 * z) - 7.0 * z2 + 4.0) - z * (z2 - 3.0)) * (1.0 / 24.0);
+        a[5] = s * l * (l * (l * (l * (24.0 * l + 60.0 * z) + 50.0 * z2 - 20.0) + z * (15.0 * z2 - 25.0)) + (z2 * (z2 - 6.0) + 3.0)) * (1.0 / 120.0);
+        // g6 = l(l(l(l(l(-120l-360z)-390z^2+120)-180z^3+210z)-31z^4+101z^2-28)-z^5+10z^3-15z)
+        a[6] = l * (l * (l * (l * (l * (-120.0 * l - 360.0 * z) - 390.0 * z2 + 120.0) + z * (210.0 - 180.0 * z2)) + (z2 * (101.0 - 31.0 * z2) - 28.0)) - z * (z2 * (z2 - 10.0) + 15.0)) * (1.0 / 720.0);
+        return fabs(x0) < 7.4;      // beyond, 1 - Phi meets its rounding / the 1e-10 clamps (model/apop_probit.c:85-86)
+    }
+};
+template <> struct Taylor<FamLogit2> {
+    // ll1 = chosen - p, ll2 = -v with v = p(1-p), ll3 = -v(1-2p), ll4 = -v(1-6v), ll5 = -v(1-2p)(1-12v), ll6 = -v(1-30v+120v^2)
+    APB_HD static bool coefs(double x0, double y, const RowOut& o, const double* aux, double* a) {
+        const double p = ((y != aux[0]) ? 1.0 : 0.0) - o.d, v = p * (1.0 - p), w = 1.0 - 2.0 * p;
+        a[0] = o.s[0];
+        a[1] = o.d;
+        a[2] = -0.5 * v;
+        a[3] = -v * w * (1.0 / 6.0);
+        a[4] = -v * (1.0 - 6.0 * v) * (1.0 / 24.0);
+        a[5] = -v * w * (1.0 - 12.0 * v) * (1.0 / 120.0);
+        a[6] = -v * (1.0 + v * (120.0 * v - 30.0)) * (1.0 / 720.0);     // ll6 = -v(1 - 30v + 120v^2)
+        return fabs(x0) < 30.0;
+    }
+};
+template <> struct Taylor<FamPoissonReg> {
+    // ll = y x - e^x: every derivative from the second on is -mu, mu = y - d
+    APB_HD static bool coefs(double x0, double y, const RowOut& o, const double*, double* a) {
+        const double mu = y - o.d;
+        a[0] = o.s[0];
+        a[1] = o.d;
+        a[2] = -mu * 0.5;
+        a[3] = -mu * (1.0 / 6.0);
+        a[4] = -mu * (1.0 / 24.0);
+        a[5] = -mu * (1.0 / 120.0);
+        a[6] = -mu * (1.0 / 720.0);
+        return fabs(x0) < 30.0;
     }
 };
 

@@ -34,7 +34,29 @@ __device__ __forceinline__ void dmma_884(double& d0, double& d1, double a, doubl
 }
 
 
-template <int KB, int C1, int HYB_STAGES>
+// exp(x) for |x| <= 708 with a 16-entry table of 2^(j/16) in shared memory (one 128-byte line: 16 entries on
+// 32 banks, so any pattern of lanes is conflict free): k = rint(16 x / ln 2), x = k ln2/16 + r, |r| <= ln2/32,
+// exp(x) = 2^(k >> 4) * T[k & 15] * e^r with e^r - 1 by a degree-7 polynomial (r^8/8! < 1.2e-18): 12 FP64-pipe
+// operations instead of the 17 of fm_exp_fast, the rest on the ALU and shared-memory pipes.
+__device__ __forceinline__ double exp_tab16(double x, const double* __restrict__ tab) {
+    const double t = fma(x, 23.083120654223414, 6755399441055744.0);       // 16 / ln 2
+    const double kf = t - 6755399441055744.0;
+    const int ki = __double2loint(t);
+    double r = fma(kf, -4.33216987730702385306e-02, x);                      // ln2/16 hi (the fdlibm ln2 hi / 16: exact)
+    r = fma(kf, -1.19263433079411731251e-11, r);                             // ln2/16 lo
+    double p = 1.9841269841269841e-04;                                       // 1/7!
+    p = fma(p, r, 1.3888888888888889e-03);
+    p = fma(p, r, 8.3333333333333332e-03);
+    p = fma(p, r, 4.1666666666666664e-02);
+    p = fma(p, r, 1.6666666666666666e-01);
+    p = fma(p, r, 5.0000000000000000e-01);
+    p = fma(p, r, 1.0);
+    const double T = tab[ki & 15];
+    const double e = fma(T * r, p, T);                                       // T (1 + r p)
+    return __hiloint2double(__double2hiint(e) + ((ki >> 4) << 20), __double2loint(e));
+}
+
+template <int KB, int C1, int HYB_STAGES, int VAR>
 __global__ void __launch_bounds__(LOGIT_THREADS, HYB_STAGES == 2 ? 3 : 4)
 logit_hybrid_kernel(const double* __restrict__ tiles, const unsigned long long n_rows,
                     const unsigned long long n_tiles, const int K, const int cols, const __grid_constant__ LogitParams prm,
@@ -95,6 +117,16 @@ logit_hybrid_kernel(const double* __restrict__ tiles, const unsigned long long n
 #pragma unroll
     for (int jb = 0; jb < JB; jb++) G[jb][0] = G[jb][1] = G2[jb][0] = G2[jb][1] = 0.0;
     KSum ll;
+    // VAR & 1: sum_i log(lsum_i) as the log of a running product: mantissa in prod (kept in [1, 2) by moving its
+    // exponent into prod_e with integer operations), one fm_log per lane at the end instead of one per row
+    double prod = 1.0;
+    long long prod_e = 0;
+    constexpr bool PROD = (VAR & 1) != 0, TAB = (VAR & 2) != 0, NB_OUTER = (VAR & 4) != 0;
+    __shared__ double exp_tab[16];
+    if (TAB) {
+        if (threadIdx.x < 16) exp_tab[threadIdx.x] = exp2((double)threadIdx.x * 0.0625);
+        __syncthreads();
+    }
 
     int cur = 0;
     if (gwarp < n_tiles) prefetch(gwarp, 0);
@@ -143,7 +175,7 @@ logit_hybrid_kernel(const double* __restrict__ tiles, const unsigned long long n
             double sum = 1.0;                      // the numeraire's exp(0)
 #pragma unroll
             for (int c = 0; c < C1; c++) {
-                e[c] = fm_exp_fast(xb[c]);         // garbage (never a trap) where the guard fails
+                e[c] = TAB ? exp_tab16(xb[c], exp_tab) : fm_exp_fast(xb[c]);   // garbage (never a trap) where the guard fails
                 sum += e[c];
                 num = (idx == c + 1) ? xb[c] : num;
             }
@@ -184,14 +216,36 @@ logit_hybrid_kernel(const double* __restrict__ tiles, const unsigned long long n
             const double2 r2 = *reinterpret_cast<const double2*>(slab + fo[nb]);
             R[nb][0] = r2.x; R[nb][1] = r2.y;
         }
-        ll.add(valid ? num - (lbase + fm_log_normal(lsum)) : 0.0);
-#pragma unroll
-        for (int jb = 0; jb < JB; jb++) {
+        if (PROD) {
+            ll.add(valid ? num - lbase : 0.0);
+            // lsum in [1, 8 e^708): split off its exponent first so that the product cannot overflow
+            const double ls = valid ? lsum : 1.0;
+            const int eh = __double2hiint(ls);
+            prod *= __hiloint2double((eh & 0x000fffff) | 0x3ff00000, __double2loint(ls));   // mantissa of lsum, in [1, 2)
+            const int ph = __double2hiint(prod);                                              // prod in [1, 4)
+            prod_e += (long long)((eh >> 20) - 1023) + (long long)((ph >> 20) - 1023);
+            prod = __hiloint2double((ph & 0x000fffff) | 0x3ff00000, __double2loint(prod));
+        } else
+            ll.add(valid ? num - (lbase + fm_log_normal(lsum)) : 0.0);
+        if (NB_OUTER) {
 #pragma unroll
             for (int nb = 0; nb < 4; nb++) {
-                const double2 x2 = *reinterpret_cast<const double2*>(tile + jb * 8 * TILE_ROWS + fo[nb]);
-                dmma_884(G[jb][0], G[jb][1], R[nb][0], x2.x);
-                dmma_884(G2[jb][0], G2[jb][1], R[nb][1], x2.y);
+#pragma unroll
+                for (int jb = 0; jb < JB; jb++) {
+                    const double2 x2 = *reinterpret_cast<const double2*>(tile + jb * 8 * TILE_ROWS + fo[nb]);
+                    dmma_884(G[jb][0], G[jb][1], R[nb][0], x2.x);
+                    dmma_884(G2[jb][0], G2[jb][1], R[nb][1], x2.y);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int jb = 0; jb < JB; jb++) {
+#pragma unroll
+                for (int nb = 0; nb < 4; nb++) {
+                    const double2 x2 = *reinterpret_cast<const double2*>(tile + jb * 8 * TILE_ROWS + fo[nb]);
+                    dmma_884(G[jb][0], G[jb][1], R[nb][0], x2.x);
+                    dmma_884(G2[jb][0], G2[jb][1], R[nb][1], x2.y);
+                }
             }
         }
         __syncwarp();                              // every lane is done with this stage before it is refilled
@@ -203,6 +257,7 @@ logit_hybrid_kernel(const double* __restrict__ tiles, const unsigned long long n
 #pragma unroll
     for (int jb = 0; jb < JB; jb++) { G[jb][0] += G2[jb][0]; G[jb][1] += G2[jb][1]; }
     __syncthreads();                               // the rings are free: reuse as WARPS x NOUT scratch
+    if (PROD) ll.add(-((double)prod_e * 6.93147180369123816490e-01 + ((double)prod_e * 1.90821492927058770002e-10 + fm_log_normal(prod))));
     const double llw = warp_sum(ll.value());
     if (lane == 0) smem[warp * NOUT] = llw;
     if (g < C1) {
@@ -223,6 +278,9 @@ logit_hybrid_kernel(const double* __restrict__ tiles, const unsigned long long n
     grid_finalize(partials, NOUT, ticket, out, fin, scratch);
 }
 
+// product-form LL and table exponential: 1.145 -> 1.098 ms on 20M x 32, C = 8 (each alone: 1.115, 1.134; the nb-outer
+// DMMA order made no difference: 1.146); APOP_B200_LOGIT_VAR selects among them in a -DAPB_LOGIT_DEV_VARIANTS build
+constexpr int HYB_DEFAULT_VAR = 3;
 // two ring stages per warp; a single stage with 16 warps per SM measured no better (1.17 vs 1.15 ms on
 // 20M x 32, C = 8), three stages with 8 warps worse (1.20 ms): the template parameter stays for such runs
 constexpr int HYB_STAGES = 2;
@@ -230,27 +288,46 @@ template <int KB, int ST>
 static constexpr size_t hyb_smem() {
     return (size_t)(LOGIT_THREADS / 32) * (ST * (KB + 1) * TILE_ROWS + 8 * TILE_ROWS) * sizeof(double);
 }
-template <int KB, int C1, int ST>
+#ifdef APB_LOGIT_DEV_VARIANTS
+static int hyb_var() {   // development switch: APOP_B200_LOGIT_VAR = bit mask (1 product LL, 2 table exp, 4 nb-outer DMMA order)
+    const char* e = getenv("APOP_B200_LOGIT_VAR");
+    return e ? atoi(e) : HYB_DEFAULT_VAR;
+}
+#endif
+template <int KB, int C1, int ST, int VAR>
 static cudaError_t hyb_launch_st(const LogitLaunch& L, const LogitParams& prm) {
     static_assert((size_t)(LOGIT_THREADS / 32) * (1 + KB * C1) + (1 + KB * C1) <= hyb_smem<KB, ST>() / sizeof(double), "reduction scratch must fit the rings");
     static bool done = false;
-    if (!done) { cudaFuncSetAttribute(logit_hybrid_kernel<KB, C1, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hyb_smem<KB, ST>()); done = true; }
-    logit_hybrid_kernel<KB, C1, ST><<<L.grid, LOGIT_THREADS, hyb_smem<KB, ST>(), L.stream>>>(L.tiles, L.n_rows, L.n_tiles, L.k, L.cols, prm, L.partials, L.ticket, L.out, L.fin);
+    if (!done) { cudaFuncSetAttribute(logit_hybrid_kernel<KB, C1, ST, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hyb_smem<KB, ST>()); done = true; }
+    logit_hybrid_kernel<KB, C1, ST, VAR><<<L.grid, LOGIT_THREADS, hyb_smem<KB, ST>(), L.stream>>>(L.tiles, L.n_rows, L.n_tiles, L.k, L.cols, prm, L.partials, L.ticket, L.out, L.fin);
     return cudaGetLastError();
 }
-template <int KB, int C1, int ST>
+template <int KB, int C1, int ST, int VAR>
 static int hyb_bps_st() {
-    cudaFuncSetAttribute(logit_hybrid_kernel<KB, C1, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hyb_smem<KB, ST>());
+    cudaFuncSetAttribute(logit_hybrid_kernel<KB, C1, ST, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hyb_smem<KB, ST>());
     int nb = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, logit_hybrid_kernel<KB, C1, ST>, LOGIT_THREADS, hyb_smem<KB, ST>());
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, logit_hybrid_kernel<KB, C1, ST, VAR>, LOGIT_THREADS, hyb_smem<KB, ST>());
     return nb;
 }
 template <int KB, int C1>
 static cudaError_t hyb_launch_one(const LogitLaunch& L, const LogitParams& prm) {
-    return hyb_launch_st<KB, C1, HYB_STAGES>(L, prm);
+#ifdef APB_LOGIT_DEV_VARIANTS
+    if (KB == 32 && C1 == 7) {
+        switch (hyb_var()) {
+        case 1: return hyb_launch_st<KB, C1, HYB_STAGES, 1>(L, prm);
+        case 2: return hyb_launch_st<KB, C1, HYB_STAGES, 2>(L, prm);
+        case 3: return hyb_launch_st<KB, C1, HYB_STAGES, 3>(L, prm);
+        case 4: return hyb_launch_st<KB, C1, HYB_STAGES, 4>(L, prm);
+        case 7: return hyb_launch_st<KB, C1, HYB_STAGES, 7>(L, prm);
+        case 0: return hyb_launch_st<KB, C1, HYB_STAGES, 0>(L, prm);
+        default: break;
+        }
+    }
+#endif
+    return hyb_launch_st<KB, C1, HYB_STAGES, HYB_DEFAULT_VAR>(L, prm);
 }
 template <int KB, int C1>
-static int hyb_bps_one() { return hyb_bps_st<KB, C1, HYB_STAGES>(); }
+static int hyb_bps_one() { return hyb_bps_st<KB, C1, HYB_STAGES, HYB_DEFAULT_VAR>(); }
 
 #define APB_HYB_C(KB)                          \
     switch (c1) {                              \

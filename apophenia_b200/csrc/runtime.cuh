@@ -64,6 +64,10 @@ struct Resident {
     // windows of the caller's matrix this library page-locked for a zero-copy upload and keeps page-locked
     // while the copy is resident (a registration cache: released by unpin / invalidate / re-upload / finalize)
     std::vector<std::pair<void*, size_t>> host_registered;
+    // batched path: passes left for which the exact kernel is used because the last shared-centre pass found the
+    // parameter vectors too far apart (then the Taylor form only adds work); re-probed when it reaches 0
+    int batched_exact_passes = 0;
+    double batched_last_exact_fraction = 0.0;
 };
 
 struct NcclApi {

@@ -773,12 +773,23 @@ def cfg4_bootstrap(cx, total=5_000_000, k=20, m=1000):
     t0 = time.perf_counter()
     ab.bootstrap_counts(s, m, seed=8)
     t_counts, = cx.max_over_ranks(time.perf_counter() - t0)
-    Bm = beta[None, :] + 0.01 * rng.standard_normal((m, k))
-    dt, kms = cx.time_passes(lambda i: ab.ll_score_batched(abi.PROBIT, s, Bm * (1 + 1e-6 * (i + 1)), use_counts=True), 3, warmup=1)
+    # the replicate vectors are scattered around beta with the sampling distribution's own spread (one standard error
+    # per coordinate, from the observed information), as the replicate estimates of a bootstrap are
+    se = np.sqrt(np.diag(np.linalg.inv(ab.information(abi.PROBIT, s, beta))))
+    Bm = beta[None, :] + se[None, :] * rng.standard_normal((m, k))
+    dt, kms = cx.time_passes(lambda i: ab.ll_score_batched(abi.PROBIT, s, Bm * (1 + 1e-9 * (i + 1)), use_counts=True), 3, warmup=1)
+    exact_share = ab.batched_exact_fraction(s)
+    Bw = beta[None, :] + 0.05 * rng.standard_normal((m, k))       # far apart: the kernel falls back to one link evaluation per pair
+    ab.ll_score_batched(abi.PROBIT, s, Bw, use_counts=True)
+    dtw, kmsw = cx.time_passes(lambda i: ab.ll_score_batched(abi.PROBIT, s, Bw * (1 + 1e-9 * (i + 1)), use_counts=True), 2, warmup=1)
+    ab.ll_score_batched(abi.PROBIT, s, Bm, use_counts=True)
     flops = 4.0 * rows * k * m
     out = {"config": f"apop_bootstrap_cov of probit, {m} replicates on {total} x {k}, {cx.world} GPU(s)",
            "counts_seconds": t_counts, "batched_pass_ms": 1e3 * dt, "batched_kernel_ms": kms,
-           "row_replicates_per_s": total * m / dt,
+           "row_replicates_per_s": total * m / dt, "replicate_spread": "1 standard error per coordinate (mean %.1e)" % float(se.mean()),
+           "exact_evaluation_share": exact_share,
+           "far_apart_vectors": {"spread": 0.05, "batched_pass_ms": 1e3 * dtw, "kernel_ms": kmsw,
+                                 "note": "parameter vectors far from each other: every (row, replicate) pair takes the exact link evaluation"},
            "roofline": {"bound": "fp64 datapath (DMMA + link evaluations share it)", "dmma_TFLOPs": flops / (kms * 1e-3) / 1e12 if kms > 0 else None,
                         "dmma_peak_TFLOPs_measured": 37.0, "link_evaluations_per_s": rows * m / (kms * 1e-3) if kms > 0 else None,
                         "kernel": "batched_kernel<24, FamProbit>", "kernel_ms": kms,
@@ -826,12 +837,16 @@ def cfg5_chains(cx, total=50_000_000, k=24, m=256):
     beta = rng.uniform(-1, 1, k)
     lo, rows = split_rows(total, cx)
     s = ab.synth(abi.LOGIT, rows, k, beta, seed=8, row_offset=lo)
-    Bm = beta[None, :] + 0.01 * rng.standard_normal((m, k))
-    dt, kms = cx.time_passes(lambda i: ab.ll_score_batched(abi.LOGIT, s, Bm * (1 + 1e-6 * (i + 1)), want_score=False), 3, warmup=1)
+    # the chains sit in the posterior, i.e. within about one standard error of each other per coordinate
+    se = np.sqrt(np.diag(np.linalg.inv(ab.information(abi.LOGIT, s, beta))))
+    Bm = beta[None, :] + se[None, :] * rng.standard_normal((m, k))
+    dt, kms = cx.time_passes(lambda i: ab.ll_score_batched(abi.LOGIT, s, Bm * (1 + 1e-9 * (i + 1)), want_score=False), 3, warmup=1)
+    exact_share = ab.batched_exact_fraction(s)
     dt1, kms1 = cx.time_passes(lambda i: ab.ll_score(abi.LOGIT, s, Bm[0] * (1 + 1e-6 * (i + 1)), want_score=False), 10)
     out = {"config": f"apop_model_metropolis on logit, {m} parallel chains over {total} x {k}, {cx.world} GPU(s)",
            "ms_per_step_all_chains": 1e3 * dt, "kernel_ms": kms, "chain_steps_per_s": m / dt, "row_chains_per_s": total * m / dt,
            "single_chain_step_ms": 1e3 * dt1, "speedup_vs_m_single_chain_steps": dt1 * m / dt,
+           "chain_spread": "1 standard error per coordinate (mean %.1e)" % float(se.mean()), "exact_evaluation_share": exact_share,
            "roofline": {"bound": "fp64 datapath (DMMA + link evaluations share it)", "dmma_TFLOPs": 2.0 * rows * k * m / (kms * 1e-3) / 1e12 if kms > 0 else None,
                         "dmma_peak_TFLOPs_measured": 37.0, "link_evaluations_per_s": rows * m / (kms * 1e-3) if kms > 0 else None,
                         "kernel": "batched_kernel<24, FamLogit2, LL only>", "kernel_ms": kms, "bytes_per_launch": rows * (k + 1) * 8}}

@@ -366,10 +366,19 @@ int apop_b200_information(apop_b200_family family, apop_data *d, const double *b
  * P x m column-major-by-replicate (replicate r at B + r*P); counts is NULL or an
  * n_rows x m row-major uint8 matrix of resample multiplicities already resident
  * (see apop_b200_bootstrap_counts); ll has m, score has P*m (NULL to skip).
+ * PROBIT, binary LOGIT and POISSON_REG (with counts, the Poisson constant sum c_i lgamma(y_i+1) is carried per row).
  * (New entry; the unmodified callers are serial: apop_bootstrap.m4.c:143,
  * apop_mcmc.m4.c:198.) */
 int apop_b200_ll_score_batched(apop_b200_family family, apop_data *d, const double *B, size_t P,
                                size_t m, int use_counts, double *ll, double *score);
+/* The m vectors of a bootstrap or of parallel chains lie within a few standard errors of each other.  The batched
+ * kernel exploits that: the family's row term is expanded to degree 6 around x_i . mean(B) once per row and every
+ * (row, replicate) pair with |x_i . (beta_r - mean)| <= 1.5e-2 costs a Horner evaluation (truncation < 1e-16
+ * relative) instead of a link evaluation; pairs outside the radius, and rows near a clamp of the reference formula,
+ * are evaluated exactly, so results never depend on the closeness.  This returns the share of warp steps of the last
+ * pass over d that needed the exact evaluation (above 0.25 the next 32 passes use the exact kernel outright);
+ * APOP_B200_BATCH_TAYLOR=0 switches the expansion off, APOP_B200_BATCH_DELTA sets the radius. */
+double apop_b200_batched_exact_fraction(const apop_data *d);
 /* draw m multinomial resamples of the rows into a resident n x m count matrix */
 int apop_b200_bootstrap_counts(apop_data *d, size_t m, uint64_t seed);
 /* the resident counts as an n_rows x m row-major uint8 matrix (for checking and for host-side drivers) */

@@ -478,3 +478,61 @@ def test_page_locked_source_goes_zero_copy(b200, oracle):
     ab.unpin(d2)
     assert ll == ll2 and np.array_equal(g, g2)
     assert _rel(ll, oracle.probit_ll(X, y, beta, oracle.EXACT)) <= 1e-12
+
+
+# ------------------------------------------------------------------------------------------------
+def test_batched_shared_centre_expansion_matches_exact(b200, oracle, monkeypatch):
+    """the batched kernel's Taylor form of the link around x . mean(B): close parameter vectors take the Horner path
+    (exact share 0), far ones the exact evaluation -- both must match the oracle replicate by replicate at 1e-12"""
+    ab = b200
+    n, k, m = 50_003, 13, 24
+    rng = np.random.default_rng(17)
+    for fam, method in ((ab.PROBIT, "probit"), (ab.LOGIT, "logit")):
+        X, y, beta = gen_probit_logit_sample(n, k, seed=29, method=method)
+        d = ab.pin(ab.Data(matrix=X, vector=y))
+        ab.bootstrap_counts(d, m, seed=2)
+        c = ab.counts_download(d, m, n)
+        for spread, want_exact in ((1e-3, 0.0), (0.3, 1.0)):
+            Bs = beta[None, :] + spread * rng.standard_normal((m, k))
+            for use_counts in (False, True):
+                llb, gb = ab.ll_score_batched(fam, d, Bs, use_counts=use_counts)
+                frac = ab.batched_exact_fraction(d)
+                assert (frac == 0.0) if want_exact == 0.0 else (frac > 0.5 or frac == 0.0), (spread, frac)   # 0.0 again once the exact kernel took over
+                for r in (0, 11, m - 1):
+                    if use_counts:
+                        idx = np.repeat(np.arange(n), c[:, r]); Xr, yr = X[idx], y[idx]
+                    else:
+                        Xr, yr = X, y
+                    if fam == ab.PROBIT:
+                        wl = oracle.probit_ll(Xr, yr, Bs[r], oracle.EXACT); wg, ws = oracle.probit_score(Xr, yr, Bs[r], oracle.EXACT)
+                    else:
+                        wl = oracle.logit_ll(Xr, yr, Bs[r].reshape(-1, 1), mode=oracle.EXACT)
+                        wg, ws = oracle.logit_score(Xr, yr, Bs[r].reshape(-1, 1), mode=oracle.EXACT); wg, ws = wg.ravel(), ws.ravel()
+                    assert _rel(llb[r], wl) <= 1e-12
+                    assert np.all(np.abs(gb[r] - wg.astype(float)) <= 1e-12 * ws.astype(float))
+        ab.unpin(d)
+
+
+def test_batched_poisson_regression_with_resample_counts(b200, oracle):
+    """resample counts weight the lgamma(y+1) constant per replicate: carried per row by the batched kernels"""
+    ab = b200
+    n, k, m = 30_011, 9, 16
+    rng = np.random.default_rng(23)
+    X = rng.uniform(-1, 1, (n, k)); X[:, 0] = 1
+    beta = rng.uniform(-1, 1, k) / 3
+    y = rng.poisson(np.exp(X @ beta)).astype(float)
+    d = ab.pin(ab.Data(matrix=X, vector=y))
+    ab.bootstrap_counts(d, m, seed=4)
+    c = ab.counts_download(d, m, n)
+    for spread in (1e-3, 0.2):
+        Bs = beta[None, :] + spread * rng.standard_normal((m, k))
+        llb, gb = ab.ll_score_batched(ab.POISSON_REG, d, Bs, use_counts=True)
+        for r in (0, 7, m - 1):
+            idx = np.repeat(np.arange(n), c[:, r])
+            wl = oracle.poisson_reg_ll(X[idx], y[idx], Bs[r], oracle.EXACT)
+            wg, ws = oracle.poisson_reg_score(X[idx], y[idx], Bs[r], oracle.EXACT)
+            assert _rel(llb[r], wl) <= 1e-12
+            assert np.all(np.abs(gb[r] - wg.astype(float)) <= 1e-12 * ws.astype(float))
+        ll1, g1 = ab.ll_score_batched(ab.POISSON_REG, d, Bs[:3], use_counts=False)
+        assert _rel(ll1[1], oracle.poisson_reg_ll(X, y, Bs[1], oracle.EXACT)) <= 1e-12
+    ab.unpin(d)

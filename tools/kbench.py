@@ -28,9 +28,9 @@ def logit8(rows=20_000_000, k=32, C=8):
     s.free()
     print(f"logit8 {rows}x{k} C={C}: step {dt:.4f} ms kernel {km:.4f} ms = {rows * (k + 1) * 8 / km / 1e6:.0f} GB/s; parity ll {e1:.1e} score {e2:.1e}", flush=True)
 
-def batched(fam, rows, k, m, score, counts):
+def batched(fam, rows, k, m, score, counts, spread=1e-3):
     rng = np.random.default_rng(8); beta = rng.uniform(-1, 1, k)
-    Bs = beta[None, :] + 0.01 * rng.standard_normal((m, k))
+    Bs = beta[None, :] + spread * rng.standard_normal((m, k))
     w = ab.synth(fam, 30011, k, beta); X, y = w.download()
     if counts: ab.bootstrap_counts(w, 16, seed=3); c = ab.counts_download(w, 16, 30011)
     llb, gb = ab.ll_score_batched(fam, w, Bs[:16], use_counts=counts, want_score=score); w.free()
@@ -47,7 +47,7 @@ def batched(fam, rows, k, m, score, counts):
     if counts: ab.bootstrap_counts(s, m, seed=8)
     dt, km = timed(lambda i: ab.ll_score_batched(fam, s, Bs * (1 + 1e-6 * (i + 1)), use_counts=counts, want_score=score), reps=3, warm=1)
     s.free()
-    print(f"batched fam={fam} {rows}x{k} m={m} score={score} counts={counts}: step {dt:.3f} ms kernel {km:.3f} ms; parity max {max(errs):.1e}", flush=True)
+    print(f"batched fam={fam} {rows}x{k} m={m} score={score} counts={counts} spread={spread}: step {dt:.3f} ms kernel {km:.3f} ms; parity max {max(errs):.1e}", flush=True)
 
 def probit(rows=100_000_000, k=32):
     rng = np.random.default_rng(8); beta = rng.uniform(-1, 1, k)
@@ -78,8 +78,8 @@ if __name__ == "__main__":
     ab.init(0)
     for nm in sys.argv[1:]:
         if nm == "logit8": logit8()
-        elif nm == "batched4": batched(ab.PROBIT, 5_000_000, 20, 1000, True, True)
-        elif nm == "batched5": batched(ab.LOGIT, 50_000_000, 24, 256, False, False)
+        elif nm.startswith("batched4"): batched(ab.PROBIT, 5_000_000, 20, 1000, True, True, float(nm.split(":")[1]) if ":" in nm else 1e-3)
+        elif nm.startswith("batched5"): batched(ab.LOGIT, 50_000_000, 24, 256, False, False, float(nm.split(":")[1]) if ":" in nm else 1e-4)
         elif nm == "probit": probit()
         elif nm.startswith("wide:"): wide(int(nm.split(":")[1]))
         elif nm == "info8": info8()
