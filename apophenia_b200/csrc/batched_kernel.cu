@@ -195,7 +195,12 @@ batched_taylor_kernel(const double* __restrict__ tiles, const unsigned long long
     constexpr int WARPS = BATCH_THREADS / 32;
     constexpr int KS = KB / 4, JB = KB / 8;
     constexpr int NC = WANT_SCORE ? 13 : 8;     // x0, a0..a6 [, 2 a2, 3 a3, 4 a4, 5 a5, 6 a6]
-    __shared__ __align__(16) double slab[WARPS][NC][TILE_ROWS];
+    constexpr int CS = BATCH_TILE_CS;           // padded column stride of a staged tile: both fragment patterns conflict free
+    extern __shared__ __align__(16) double dsm[];
+    typedef double (*SlabT)[NC][TILE_ROWS];
+    SlabT slab = reinterpret_cast<SlabT>(dsm);                       // [WARPS][NC][32]
+    double* stile = dsm + WARPS * NC * TILE_ROWS;                    // [WARPS][(K + 1) * CS]: the 8 tiles of this round
+    const int tile_d = (K + 1) * CS;
     __shared__ double s_centre[MAX_K_REG];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, q = lane & 3;
@@ -226,10 +231,24 @@ batched_taylor_kernel(const double* __restrict__ tiles, const unsigned long long
         {
             const unsigned long long t = t0 + (unsigned long long)warp * n_rowgroups;
             if (t < n_tiles) {
-                const double* tile = tiles + t * (unsigned long long)(cols * TILE_ROWS);
+                // stage the tile (K columns + y) in shared memory for all 8 warps: 16-byte chunk c = lane + 32 i is chunk
+                // (lane & 15) of column (lane >> 4) + 2 i
+                double* st = stile + warp * tile_d;
+                {
+                    const double* src = tiles + t * (unsigned long long)(cols * TILE_ROWS) + lane * 2;
+                    const unsigned sa = smem_u32(st + (lane >> 4) * CS + (lane & 15) * 2);
+                    for (int i = 0; 2 * i <= K; i++) {
+                        const int col = (lane >> 4) + 2 * i;
+                        if (col <= K)
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa + i * 2 * CS * 8), "l"(src + i * 64));
+                    }
+                    asm volatile("cp.async.commit_group;");
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");
+                    __syncwarp();
+                }
                 double x0 = 0.0;
-                for (int j = 0; j < K; j++) x0 = fma(__ldg(tile + j * TILE_ROWS + lane), s_centre[j], x0);
-                const double y = __ldg(tile + K * TILE_ROWS + lane);
+                for (int j = 0; j < K; j++) x0 = fma(st[j * CS + lane], s_centre[j], x0);
+                const double y = st[K * CS + lane];
                 const RowOut o = Fam::eval(x0, y, 1.0, aux);
                 double a[TAYLOR_D + 1];
                 const bool ok = Taylor<Fam>::coefs(x0, y, o, aux, a) && (t * TILE_ROWS + lane < n_rows);
@@ -248,7 +267,7 @@ batched_taylor_kernel(const double* __restrict__ tiles, const unsigned long long
         for (int i = 0; i < WARPS; i++) {
             const unsigned long long t = t0 + (unsigned long long)i * n_rowgroups;
             if (t >= n_tiles || rep0 >= m) break;          // (a warp beyond the last replicate only helps with phase A)
-            const double* tile = tiles + t * (unsigned long long)(cols * TILE_ROWS);
+            const double* tile = stile + i * tile_d;
             double S[4][2];
 #pragma unroll
             for (int nb = 0; nb < 4; nb++) S[nb][0] = S[nb][1] = 0.0;
@@ -257,7 +276,7 @@ batched_taylor_kernel(const double* __restrict__ tiles, const unsigned long long
                 const int j = ks * 4 + q;
                 double xf[4];
 #pragma unroll
-                for (int nb = 0; nb < 4; nb++) xf[nb] = (j < K) ? __ldg(tile + j * TILE_ROWS + nb * 8 + g) : 0.0;
+                for (int nb = 0; nb < 4; nb++) xf[nb] = (j < K) ? tile[j * CS + nb * 8 + g] : 0.0;
 #pragma unroll
                 for (int nb = 0; nb < 4; nb++) dmma_8x8x4(S[nb][0], S[nb][1], bfrag[ks], xf[nb]);
             }
@@ -300,7 +319,7 @@ batched_taylor_kernel(const double* __restrict__ tiles, const unsigned long long
                     const bool exact = !(fabs(dl) <= delta_max) && cnt != 0.0;
                     if (__any_sync(0xffffffffu, exact)) {
                         n_exact++;
-                        const double2 y2 = __ldg(reinterpret_cast<const double2*>(tile + K * TILE_ROWS + nb * 8 + 2 * q));
+                        const double2 y2 = *reinterpret_cast<const double2*>(tile + K * CS + nb * 8 + 2 * q);
                         const RowOut o = Fam::eval(xb, e ? y2.y : y2.x, 1.0, aux);
                         llv = exact ? o.s[0] + row_const_of<Fam, USE_COUNTS>(e ? y2.y : y2.x) : llv;
                         dv = exact ? o.d : dv;
@@ -317,7 +336,7 @@ batched_taylor_kernel(const double* __restrict__ tiles, const unsigned long long
 #pragma unroll
                     for (int nb = 0; nb < 4; nb++) {
                         double2 x2 = make_double2(0.0, 0.0);
-                        if (j < K) x2 = __ldg(reinterpret_cast<const double2*>(tile + j * TILE_ROWS + nb * 8 + 2 * q));
+                        if (j < K) x2 = *reinterpret_cast<const double2*>(tile + j * CS + nb * 8 + 2 * q);
                         dmma_8x8x4(G[jb][0], G[jb][1], S[nb][0], x2.x);
                         dmma_8x8x4(G[jb][0], G[jb][1], S[nb][1], x2.y);
                     }
@@ -401,8 +420,10 @@ template <int KB, class Fam>
 static cudaError_t launch_fam(const BatchedLaunch& L) {
     const double4 aux = make_double4(L.aux[0], L.aux[1], L.aux[2], L.aux[3]);
     if (L.centre) {
-#define APB_TGO(S, C) batched_taylor_kernel<KB, Fam, S, C><<<L.grid, BATCH_THREADS, 0, L.stream>>>(L.tiles, L.n_rows, L.n_tiles, L.k, L.cols, \
-        L.B, L.P, L.m, L.counts, L.m_pad, aux, L.n_rowgroups, L.partials, L.centre, L.delta_max, L.exact_slots)
+        const size_t tsm = (size_t)(BATCH_THREADS / 32) * ((L.want_score ? 13 : 8) * TILE_ROWS + (size_t)(L.k + 1) * BATCH_TILE_CS) * sizeof(double);
+#define APB_TGO(S, C) do { cudaFuncSetAttribute(batched_taylor_kernel<KB, Fam, S, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm); \
+        batched_taylor_kernel<KB, Fam, S, C><<<L.grid, BATCH_THREADS, tsm, L.stream>>>(L.tiles, L.n_rows, L.n_tiles, L.k, L.cols, \
+        L.B, L.P, L.m, L.counts, L.m_pad, aux, L.n_rowgroups, L.partials, L.centre, L.delta_max, L.exact_slots); } while (0)
         if (L.want_score) { if (L.counts) APB_TGO(true, true); else APB_TGO(true, false); }
         else { if (L.counts) APB_TGO(false, true); else APB_TGO(false, false); }
 #undef APB_TGO

@@ -5,7 +5,8 @@
 
 namespace apb {
 constexpr int BATCH_THREADS = 256;  // 8 warps, one replicate group each, all on the same tile
-constexpr int BATCH_RC_MAX = 16;    // replicates per warp: 8 (two CTAs per SM) or 16 (one)
+constexpr int BATCH_RC_MAX = 16;
+constexpr int BATCH_TILE_CS = 40;   // column stride (doubles) of a tile staged in shared memory by the shared-centre kernel    // replicates per warp: 8 (two CTAs per SM) or 16 (one)
 struct BatchedLaunch {
     const double* tiles;
     unsigned long long n_rows, n_tiles;
