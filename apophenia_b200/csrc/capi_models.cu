@@ -51,8 +51,8 @@ bool eval_glm(Resident* r, GlmFam fam, const double* beta, size_t P, const doubl
     // Poisson regression ignore d->weights exactly as the reference's do (model/apop_probit.c never touches them)
     const bool reads_w = r->has_w && fam == GLM_OLS;
     const bool has_w = r->has_w;
-    const bool wide = K > MAX_K_REG;
-    static int bps_cache[GLM_FAM_COUNT][MAX_K_REG + 1][2];
+    const bool wide = K > GLM_K_REG;
+    static int bps_cache[GLM_FAM_COUNT][GLM_K_REG + 1][2];
     int bps_wide = 0;
     int& bps = wide ? bps_wide : bps_cache[fam][K][has_w ? 1 : 0];
     int& bps_ref = bps;

@@ -13,7 +13,8 @@ namespace apb {
 // r at offset c*32 + r.  Columns: X_0..X_{k-1}, then y (if the data set has a
 // vector), then w (if it has weights).
 constexpr int TILE_ROWS = 32;
-constexpr int MAX_K_REG = 32;      // widest X for the register-resident kernels
+constexpr int MAX_K_REG = 32;      // widest X for the shared-memory / tensor kernels (logit, X'WX, batched)
+constexpr int GLM_K_REG = 48;      // widest X the fused GLM kernel keeps in registers (x[K] and g[K]: 2 CTAs of 4 warps per SM)
 constexpr int GLM_THREADS = 128;   // threads per CTA of the fused kernels
 constexpr int MAX_ACC = 3;         // scalar sums a family may produce besides the score
 
@@ -134,7 +135,17 @@ __device__ __forceinline__ void grid_finalize(const double* __restrict__ partial
         if ((int)threadIdx.x < G * nout) {
             const int v = threadIdx.x % nout, gi = threadIdx.x / nout;
             double s = 0.0, c = 0.0;
-            for (unsigned b = gi; b < gridDim.x; b += G) {
+            unsigned b = gi;
+            // eight loads in flight per dependent add chain: a plain loop pays one L2 round trip per partial
+            // (~20 us for 444 CTAs, most of the kernel's fixed cost); the order of the additions is unchanged
+            for (; b + 7 * G < gridDim.x; b += 8 * G) {
+                double x[8], e;
+#pragma unroll
+                for (int u = 0; u < 8; u++) x[u] = __ldcg(partials + (size_t)(b + u * G) * nout + v);
+#pragma unroll
+                for (int u = 0; u < 8; u++) { two_sum(s, x[u], s, e); c += e; }
+            }
+            for (; b < gridDim.x; b += G) {
                 double e;
                 two_sum(s, __ldcg(partials + (size_t)b * nout + v), s, e);
                 c += e;

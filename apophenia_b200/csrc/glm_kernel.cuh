@@ -19,7 +19,7 @@
 namespace apb {
 
 struct GlmParams {
-    double beta[MAX_K_REG];
+    double beta[GLM_K_REG];
     double aux[4];
 };
 

@@ -4,11 +4,11 @@
 // skip it (the reference's probit / logit never look at d->weights), the load is dead code there.
 namespace apb {
 cudaError_t glm_launch_probit(int k, bool has_w, const GlmLaunch& L, const GlmParams& prm) {
-    if (has_w) return GlmTable<FamProbit, true, MAX_K_REG>::launch(k, L, prm);
-    return GlmTable<FamProbit, false, MAX_K_REG>::launch(k, L, prm);
+    if (has_w) return GlmTable<FamProbit, true, GLM_K_REG>::launch(k, L, prm);
+    return GlmTable<FamProbit, false, GLM_K_REG>::launch(k, L, prm);
 }
 int glm_blocks_per_sm_probit(int k, bool has_w) {
-    if (has_w) return GlmTable<FamProbit, true, MAX_K_REG>::blocks_per_sm(k);
-    return GlmTable<FamProbit, false, MAX_K_REG>::blocks_per_sm(k);
+    if (has_w) return GlmTable<FamProbit, true, GLM_K_REG>::blocks_per_sm(k);
+    return GlmTable<FamProbit, false, GLM_K_REG>::blocks_per_sm(k);
 }
 }  // namespace apb
