@@ -13,8 +13,9 @@
 // an optional line of column names and an optional leading row-name field (both skipped: names
 // do not reach the device), a missing value (NaN) for an empty field unless the delimiter that
 // closes it is a space or a tab, text fields read as 0, C number syntax through strtod
-// (inf, nan, hex floats) with a fast exact path for plain decimals.  Quoted fields, backslash
-// escapes and fixed-width layouts are refused (NULL + message): use the reference's reader there.
+// (inf, nan, hex floats) with a fast exact path for plain decimals, quoted fields ("..." read verbatim, the
+// marks stripped) and backslash escapes.  Fixed-width layouts (.field_ends) are refused (NULL + message): use the
+// reference's reader there.
 #include "capi_internal.cuh"
 #include "host_pool.h"
 #include <fcntl.h>
@@ -22,6 +23,7 @@
 #include <sys/stat.h>
 #include <unistd.h>
 #include <atomic>
+#include <string>
 
 using namespace apb;
 
@@ -81,12 +83,68 @@ double field_value(const char* b, const char* e) {
     return converted ? v : 0.0;     // text fields are taken as zeros
 }
 
+// A line that uses quotes or backslashes (apop_conversions.m4.c:352-358): the character after a backslash is an
+// ordinary character even if it is a delimiter, # or "; a field surrounded by "s is read verbatim (delimiters and #
+// inside it are text) and the marks are stripped.  One character at a time, as the reference reads every line;
+// only lines that need it come here.  (A quoted field cannot span lines: the file is cut at newlines first.)
+long parse_line_quoted(const char* p, const char* eol, const TextRules& R, double* out, long max_fields) {
+    std::string cur;
+    bool in_q = false, had_q = false, any = false;
+    long n = 0;
+    bool skip_first = R.has_row_names;
+    auto emit = [&](int closer) {      // closer: the delimiter that ended the field, or -1 at the end of the line
+        size_t b = 0, e = cur.size();
+        if (!had_q) {
+            while (b < e && is_blank((unsigned char)cur[b])) b++;
+            while (e > b && is_blank((unsigned char)cur[e - 1])) e--;
+        }
+        const bool empty = (b == e) && !had_q;
+        const bool closed_by_space = closer == ' ' || closer == '\t';
+        if (!(empty && closed_by_space)) {
+            if (skip_first) skip_first = false;
+            else {
+                if (out && n < max_fields) out[n] = empty ? NAN : ((b == e) ? 0.0 : field_value(cur.data() + b, cur.data() + e));
+                n++;
+            }
+        }
+        cur.clear();
+        had_q = false;
+    };
+    int last_closer = -1;
+    bool pending = false;              // a field is open (something follows the last delimiter, or nothing was read yet)
+    for (const char* c = p; c < eol; c++) {
+        const unsigned char ch = (unsigned char)*c;
+        if (ch == '\\' && c + 1 < eol) { cur.push_back(c[1]); c++; any = true; pending = true; continue; }
+        if (ch == '"') { in_q = !in_q; had_q = true; any = true; pending = true; continue; }
+        if (!in_q && ch == '#') break;
+        if (!in_q && R.delim[ch]) {
+            if (!any && is_blank(ch)) continue;        // leading white space of the line, even when it is a delimiter
+            emit(ch);
+            last_closer = ch;
+            pending = false;
+            any = true;
+            continue;
+        }
+        if (!is_blank(ch)) { any = true; }
+        cur.push_back((char)ch);
+        pending = true;
+    }
+    if (!any) return 0;                                  // blank or comment-only line
+    // the last field: what follows the last delimiter; a line ending on a delimiter has a trailing missing value
+    // unless that delimiter was a space or a tab
+    bool only_blank = true;
+    for (char ch : cur) if (!is_blank((unsigned char)ch)) only_blank = false;
+    if (pending && !(only_blank && !had_q)) emit(-1);
+    else if (last_closer >= 0 && !(last_closer == ' ' || last_closer == '\t')) { cur.clear(); had_q = false; emit(-1); }
+    return n;
+}
+
 // Parse one line [p, eol).  out == NULL: only count the fields.  Returns the number of fields
-// (0 for a blank / comment-only line), or -1 if the line uses an unsupported construct.
+// (0 for a blank / comment-only line).
 long parse_line(const char* p, const char* eol, const TextRules& R, double* out, long max_fields) {
     // cut the comment
     const char* end = p;
-    while (end < eol && *end != '#') { if (*end == '"' || *end == '\\') return -1; end++; }
+    while (end < eol && *end != '#') { if (*end == '"' || *end == '\\') return parse_line_quoted(p, eol, R, out, max_fields); end++; }
     while (p < end && is_blank((unsigned char)*p)) p++;
     while (end > p && is_blank((unsigned char)end[-1])) end--;
     if (p == end) return 0;

@@ -279,8 +279,8 @@ int apop_b200_logit_expected(apop_data *d, apop_model *m, double *probs, double 
  * (apop_conversions.m4.c:339-403) that are honoured: delimiter set (NULL = "|,\t"), '#' comments, blank
  * lines, white space around fields, has_col_names (1/'y': the first non-blank line is skipped),
  * has_row_names (1/'y': the first field of every row is skipped), an empty field = NaN unless the
- * delimiter closing it is a space or tab, text fields = 0, strtod number syntax.  Quoted fields,
- * backslash escapes and fixed-width fields are refused.  outcome_col0 != 0: column 0 is the outcome
+ * delimiter closing it is a space or tab, text fields = 0, strtod number syntax, quoted fields ("..." read
+ * verbatim with the marks stripped) and backslash escapes.  Fixed-width fields (.field_ends) are refused.  outcome_col0 != 0: column 0 is the outcome
  * (ols_shuffle while tiling).  Returns a device-only header (sizes set, data pointers NULL) that is
  * resident; free it with apop_b200_synth_free.  NULL on error. */
 apop_data *apop_b200_text_to_resident(const char *path, int has_row_names, int has_col_names,

@@ -49,8 +49,21 @@ def test_text_rules_on_host(ab, tmp_path):
     # CRLF line ends and no final newline
     p = _write(tmp_path, "c.csv", "a,b\r\n1,2\r\n3,4")
     assert np.array_equal(ab.text_to_host(p), [[1, 2], [3, 4]])
-    # refused: quotes, over-long rows, missing file
-    for bad in ('a,b\n1,"2,5"\n', "a,b\n1,2\n3,4,5\n"):
+    # quoted fields and backslash escapes (apop_conversions.m4.c:352-358): the marks are stripped and the text is read
+    # verbatim (a delimiter or # inside is text; a quoted number is a number, other text reads as 0); the character
+    # after a backslash is an ordinary character
+    p = _write(tmp_path, "q.csv", "\n".join([
+        '"Males, 30-40",plain,"with # inside"',
+        '"2.5",3,4  # comment',
+        '1,"text, with comma",7',
+        '" 6 ",\\-2,"8"',                       # inner spaces stay inside the field (still the number 6); \- is a plain minus
+        '5,\\,,9',                              # an escaped comma is text (0), then an ordinary field
+        '"",1,2',                                 # an empty quoted field is text, not a missing value
+    ]) + "\n")
+    got = ab.text_to_host(p)
+    assert np.array_equal(got, [[2.5, 3, 4], [1, 0, 7], [6, -2, 8], [5, 0, 9], [0, 1, 2]], equal_nan=True)
+    # refused: over-long rows, missing file
+    for bad in ("a,b\n1,2\n3,4,5\n",):
         with pytest.raises(ab.B200Error):
             ab.text_to_host(_write(tmp_path, "bad.csv", bad))
     with pytest.raises(ab.B200Error):
