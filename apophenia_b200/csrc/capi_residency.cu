@@ -79,8 +79,8 @@ struct Registrar {
             t_register += dt;
             int st = 1;
             bool ours = true;
-            if (e == cudaErrorHostMemoryAlreadyRegistered) { ours = false; cudaGetLastError(); }   // the caller pinned it: even better
-            else if (e != cudaSuccess) { st = 2; cudaGetLastError(); }
+            // (a range somebody else registered, possibly a stale registration of freed memory, is not trusted: staged path)
+            if (e != cudaSuccess) { st = 2; cudaGetLastError(); }
             std::lock_guard<std::mutex> lk(m);
             x.state = st; x.ours = ours;
             // the rate the decision is taken on: the best of the first two windows (the very first call also pays
@@ -118,15 +118,20 @@ static size_t upload_registered(Resident* r, const apop_data* d, bool col0, int 
         if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
         return a.type == cudaMemoryTypeHost;
     };
-    const bool pinned_src = pinned_ptr(d->matrix->data) && pinned_ptr((const char*)d->matrix->data + total - 1);
-    // pageable memory is page-locked here only on request (APOP_B200_PIN_MODE=register): measured on the pool
-    // boxes it loses to the staged path for one rank and does not scale over the ranks of one host (see above)
-    if (!pinned_src && mode != 2) return 0;
     const size_t PAGE = 4096, ALIGN = (size_t)2 << 20;
     size_t WB = (size_t)128 << 20;                                    // window: a multiple of the 2 MB huge-page size
     if (const char* e = getenv("APOP_B200_PIN_WINDOW_MB")) { const long mb = atol(e); if (mb >= 2) WB = (size_t)(mb / 2 * 2) << 20; }
     const uintptr_t base = (uintptr_t)d->matrix->data;
-    const uintptr_t lo = base & ~(uintptr_t)(PAGE - 1), hi = (base + total + PAGE - 1) & ~(uintptr_t)(PAGE - 1);
+    // Only pages that lie entirely inside the matrix are page-locked / read in place: a first or last page shared
+    // with a neighbouring allocation (two arrays side by side on the heap) would otherwise be registered twice.
+    // The partial head and tail (< one page each) travel through a small pinned scratch.
+    const uintptr_t lo = (base + PAGE - 1) & ~(uintptr_t)(PAGE - 1), hi = (base + total) & ~(uintptr_t)(PAGE - 1);
+    if (hi <= lo + PAGE) return 0;
+    bool pinned_src = pinned_ptr((const void*)base) && pinned_ptr((const void*)(base + total - 1));
+    for (uintptr_t a = lo; pinned_src && a < hi; a += WB) pinned_src = pinned_ptr((const void*)a);   // every window start, too
+    // pageable memory is page-locked here only on request (APOP_B200_PIN_MODE=register): measured on the pool
+    // boxes it loses to the staged path for one rank and does not scale over the ranks of one host (see above)
+    if (!pinned_src && mode != 2) return 0;
     Registrar G;
     G.device = R.device;
     if (const char* e = getenv("APOP_B200_PIN_AHEAD")) { const int a = atoi(e); if (a >= 2) G.ahead = a; }
@@ -143,7 +148,11 @@ static size_t upload_registered(Resident* r, const apop_data* d, bool col0, int 
     const size_t carry_cap = ((33 * rb) + 255) / 256 * 256;
     const size_t max_rows = WB / rb + 66;
     const size_t yw_bytes = max_rows * sizeof(double) * ((hy ? 1 : 0) + (hw ? 1 : 0));
-    const size_t dev_need = carry_cap + WB + PAGE + yw_bytes + 512;
+    const size_t dev_need = carry_cap + PAGE + WB + 2 * PAGE + yw_bytes + 512;
+    if (!R.reg_edge && !cuda_ok(cudaHostAlloc(&R.reg_edge, 2 * PAGE, cudaHostAllocDefault), "cudaHostAlloc(edge scratch)")) { ok = false; return 0; }
+    const size_t head_len = lo - base, tail_len = base + total - hi;
+    memcpy(R.reg_edge, (const void*)base, head_len);
+    memcpy(R.reg_edge + PAGE, (const void*)hi, tail_len);
     if (R.reg_dev_cap < dev_need) {
         for (int b2 = 0; b2 < 2; b2++) { if (R.reg_dev[b2]) cudaFree(R.reg_dev[b2]); R.reg_dev[b2] = nullptr; }
         R.reg_dev_cap = 0;
@@ -190,7 +199,7 @@ static size_t upload_registered(Resident* r, const apop_data* d, bool col0, int 
         finish(false);
         return 0;
     }
-    size_t row_cursor = 0, carry_len = 0, prev_rows = 0, prev_carry = 0;
+    size_t row_cursor = 0, carry_len = head_len, prev_rows = 0, prev_carry = 0;   // the partial first page counts as carried-over bytes
     size_t wi = 0;
     for (; ok && wi < nw; wi++) {
         {
@@ -208,12 +217,11 @@ static size_t upload_registered(Resident* r, const apop_data* d, bool col0, int 
         }
         { std::lock_guard<std::mutex> lk(G.m); G.consumed = wi; G.cv.notify_all(); }   // the helper stays `ahead` windows in front
         const auto ti = std::chrono::steady_clock::now();
-        const uintptr_t hs = G.w[wi].lo < base ? base : G.w[wi].lo;
-        const uintptr_t he = G.w[wi].hi > base + total ? base + total : G.w[wi].hi;
-        const size_t len = he - hs;
-        char* win = R.reg_dev[slot] + carry_cap;
-        const size_t avail = carry_len + len;
+        const uintptr_t hs = G.w[wi].lo, he = G.w[wi].hi;
         const bool last = (wi + 1 == nw);
+        const size_t wlen = he - hs, len = wlen + (last ? tail_len : 0);   // the last window is followed by the partial last page
+        char* win = R.reg_dev[slot] + carry_cap + PAGE;
+        const size_t avail = carry_len + len;
         size_t rows = avail / rb;
         if (!last) rows = rows / TILE_ROWS * TILE_ROWS;
         // outcome / weights of these rows through the pinned staging slot
@@ -222,15 +230,19 @@ static size_t upload_registered(Resident* r, const apop_data* d, bool col0, int 
         if (hy && rows) memcpy(hyv, d->vector->data + row_cursor, rows * sizeof(double));
         if (hw && rows) memcpy(hwv, d->weights->data + row_cursor, rows * sizeof(double));
         if (wi >= 2) ok = ok && cuda_ok(cudaStreamWaitEvent(R.copy_stream, R.reg_packed[slot], 0), "stream wait");
-        ok = ok && cuda_ok(cudaMemcpyAsync(win, (const void*)hs, len, cudaMemcpyHostToDevice, R.copy_stream), "H2D window");
-        if (carry_len) {   // the rows the previous window left incomplete, placed right before this window's bytes
-            const char* prev_win = R.reg_dev[slot ^ 1] + carry_cap;
+        ok = ok && cuda_ok(cudaMemcpyAsync(win, (const void*)hs, wlen, cudaMemcpyHostToDevice, R.copy_stream), "H2D window");
+        if (last && tail_len)
+            ok = ok && cuda_ok(cudaMemcpyAsync(win + wlen, R.reg_edge + PAGE, tail_len, cudaMemcpyHostToDevice, R.copy_stream), "H2D tail");
+        if (wi == 0) {     // the partial first page, from the pinned scratch
+            if (carry_len) ok = ok && cuda_ok(cudaMemcpyAsync(win - carry_len, R.reg_edge, carry_len, cudaMemcpyHostToDevice, R.copy_stream), "H2D head");
+        } else if (carry_len) {   // the rows the previous window left incomplete, placed right before this window's bytes
+            const char* prev_win = R.reg_dev[slot ^ 1] + carry_cap + PAGE;
             const char* left = prev_win - prev_carry + prev_rows * rb;
             ok = ok && cuda_ok(cudaMemcpyAsync(win - carry_len, left, carry_len, cudaMemcpyDeviceToDevice, R.copy_stream), "carry");
         }
         ok = ok && cuda_ok(cudaEventRecord(R.reg_copied[slot], R.copy_stream), "event");
         ok = ok && cuda_ok(cudaStreamWaitEvent(R.stream, R.reg_copied[slot], 0), "stream wait");
-        double* dy = (double*)(win + ((WB + PAGE + 255) / 256 * 256));
+        double* dy = (double*)(win + ((WB + 2 * PAGE + 255) / 256 * 256));
         double* dw = dy + (hy ? rows : 0);
         if (yw_bytes && rows)
             ok = ok && cuda_ok(cudaMemcpyAsync(dy, hyv, rows * sizeof(double) * ((hy ? 1 : 0) + (hw ? 1 : 0)), cudaMemcpyHostToDevice, R.stream), "H2D outcome");

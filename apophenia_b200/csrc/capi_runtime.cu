@@ -146,6 +146,7 @@ extern "C" void apop_b200_finalize(void) {
         if (R.reg_copied[b2]) { cudaEventDestroy(R.reg_copied[b2]); R.reg_copied[b2] = nullptr; }
         if (R.reg_packed[b2]) { cudaEventDestroy(R.reg_packed[b2]); R.reg_packed[b2] = nullptr; }
     }
+    if (R.reg_edge) { cudaFreeHost(R.reg_edge); R.reg_edge = nullptr; }
     R.reg_dev_cap = R.reg_hy_cap = 0;
     cudaFree(R.d_vals);
     if (R.d_beta) { cudaFree(R.d_beta); R.d_beta = nullptr; }

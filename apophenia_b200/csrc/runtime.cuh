@@ -109,6 +109,7 @@ struct Runtime {
     // staging buffers for the outcome / weights of a window, and their events
     char* reg_dev[2] = {nullptr, nullptr};
     double* reg_hy[2] = {nullptr, nullptr};
+    char* reg_edge = nullptr;                 // pinned, two pages: the partial first / last page of a zero-copy source
     size_t reg_dev_cap = 0, reg_hy_cap = 0;   // bytes
     cudaEvent_t reg_copied[2] = {nullptr, nullptr}, reg_packed[2] = {nullptr, nullptr};
     int last_pin_mode = 0;                    // 0 staged, 1 registered windows (apop_b200_last_pin_mode)
