@@ -146,7 +146,7 @@ static size_t upload_registered(Resident* r, const apop_data* d, bool col0, int 
     const size_t nw = G.w.size();
     // landing buffers: [carry: up to 32 rows + a partial one][window][y][w]
     const size_t carry_cap = ((33 * rb) + 255) / 256 * 256;
-    const size_t max_rows = WB / rb + 66;
+    const size_t max_rows = (WB + 2 * PAGE) / rb + 66;
     const size_t yw_bytes = max_rows * sizeof(double) * ((hy ? 1 : 0) + (hw ? 1 : 0));
     const size_t dev_need = carry_cap + PAGE + WB + 2 * PAGE + yw_bytes + 512;
     if (!R.reg_edge && !cuda_ok(cudaHostAlloc(&R.reg_edge, 2 * PAGE, cudaHostAllocDefault), "cudaHostAlloc(edge scratch)")) { ok = false; return 0; }
