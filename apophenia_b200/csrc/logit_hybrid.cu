@@ -96,7 +96,11 @@ logit_hybrid_kernel(const double* __restrict__ tiles, const unsigned long long n
         const unsigned sy = smem_u32(ring + stage * TILE_D + pf_y);
 #pragma unroll
         for (int i = 0; i < (KB + 2) / 2; i++) {
-            // (a branch-free, predicated form of this loop costs 48 more registers and measured 11 % slower)
+            // (a branch-free, predicated form of this loop costs 48 more registers and measured 11 % slower.  Round 2:
+            // ncu's source view puts 22 % of the stall samples on this loop -- ~12 issue slots per copy, VIADD / ISETP /
+            // BRA chains -- yet a K == KB specialisation without any column test, 17 copies back to back or spread in
+            // three portions over stage 1, measured 1.21-1.22 ms against 1.085-1.14 for this form on the same boxes:
+            // 168 registers and spills instead of 136.  It stays as it is.)
             const int col = par + 2 * i;
             if (col < K)
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sx + i * 2 * TILE_ROWS * 8), "l"(src + i * 64));
