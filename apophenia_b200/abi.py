@@ -159,6 +159,7 @@ SIGNATURES = {
     "apop_b200_ll_score_batched": (C.c_int, [C.c_int, _PD, _dp, C.c_size_t, C.c_size_t, C.c_int, _dp, _dp]),
     "apop_b200_bootstrap_counts": (C.c_int, [_PD, C.c_size_t, C.c_uint64]),
     "apop_b200_batched_exact_fraction": (C.c_double, [_PD]),
+    "apop_b200_set_replicate": (C.c_int, [_PD, C.c_long]),
     "apop_b200_counts_download": (C.c_int, [_PD, C.c_size_t, C.POINTER(C.c_ubyte)]),
     "apop_b200_register": (C.c_int, [_PM, C.c_int]),
     "apop_b200_unregister": (C.c_int, [_PM]),

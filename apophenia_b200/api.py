@@ -22,7 +22,7 @@ __all__ = ["init", "finalize", "pin", "unpin", "invalidate", "is_pinned", "last_
            "PROBIT", "LOGIT", "POISSON", "NORMAL", "OLS", "POISSON_REG", "EXPONENTIAL", "GAMMA", "LOGNORMAL",
            "BERNOULLI", "BETA", "ZIPF", "DIRICHLET", "TDIST", "YULE", "comm_init_from_torch",
            "comm_finalize", "set_auto_pin", "last_error", "information", "ols_gram",
-           "dot", "col_sums", "probit_start", "prep_outcome", "logit_expected", "text_to_host", "text_to_resident", "ll_score_batched", "batched_exact_fraction", "bootstrap_counts", "counts_download",
+           "dot", "col_sums", "probit_start", "prep_outcome", "logit_expected", "text_to_host", "text_to_resident", "ll_score_batched", "batched_exact_fraction", "set_replicate", "bootstrap_counts", "counts_download",
            "MAP_IDENTITY", "MAP_DEV", "MAP_DEV2", "MAP_POISSON", "MAP_LOG", "MAP_EXP", "MAP_ABS", "MAP_SQRT",
            "MAP_SCALE", "MAP_POW", "ROW_SUM", "ROW_MEAN", "ROW_SUMSQ", "ROW_MAX", "ROW_MIN", "ROW_DOT",
            "ROW_PROBIT_LL", "ROW_LOGIT2_LL", "ROW_POISSON_REG_LL", "ROW_OLS_ERROR", "map", "map_rows", "global_rows"]
@@ -199,6 +199,11 @@ def ll_score_batched(family, d, B, use_counts=False, want_score=True):
 def batched_exact_fraction(d):
     """share of the last shared-centre batched pass over d that needed the exact link evaluation"""
     return float(_lib().apop_b200_batched_exact_fraction(_ptr(d)))
+
+
+def set_replicate(d, replicate):
+    """weight the single-beta multinomial logit passes over d by one bootstrap replicate's counts (-1: off)"""
+    abi.check(_lib().apop_b200_set_replicate(_ptr(d), int(replicate)), "apop_b200_set_replicate")
 
 
 def bootstrap_counts(d, m, seed=8):

@@ -254,6 +254,20 @@ extern "C" double apop_b200_batched_exact_fraction(const apop_data* d) {
     return it == rt().reg.end() ? -1.0 : it->second->batched_last_exact_fraction;
 }
 
+// Select one bootstrap replicate on a resident data set with resample counts: the single-beta multinomial logit passes
+// (apop_b200_logit_ll / _score through any unmodified optimizer) then weight every row by that replicate's multiplicity,
+// i.e. evaluate the resampled data set of apop_bootstrap.m4.c:143-149 without copying a row.  replicate < 0: off.
+extern "C" int apop_b200_set_replicate(apop_data* d, long replicate) {
+    LOCK;
+    auto it = rt().reg.find(d);
+    if (it == rt().reg.end()) { set_error("apop_b200_set_replicate: the data set is not resident"); return 1; }
+    Resident* r = it->second;
+    if (replicate >= 0 && (!r->counts || (size_t)replicate >= r->counts_m)) { set_error("apop_b200_set_replicate: no resident counts for replicate %ld", replicate); return 1; }
+    r->active_replicate = replicate < 0 ? -1 : replicate;
+    r->memo_valid = false;
+    return 0;
+}
+
 // resident resample counts back to the host as an n_rows x m row-major uint8 matrix (tests)
 extern "C" int apop_b200_counts_download(const apop_data* d, size_t m, unsigned char* out) {
     LOCK;

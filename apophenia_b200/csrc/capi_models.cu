@@ -40,6 +40,7 @@ bool eval_glm(Resident* r, GlmFam fam, const double* beta, size_t P, const doubl
     if ((size_t)K != P) return set_error("parameter count %zu does not match the %d data columns", P, K);
     if (K < 1 || K > GLM_WIDE_MAX_K) return set_error("k = %d columns: the fused kernels cover 1..%d", K, GLM_WIDE_MAX_K);
     if (!r->has_y) return set_error("the data set has no outcome vector (run the model's prep first)");
+    if (r->active_replicate >= 0) return set_error("a bootstrap replicate is selected on this data set (apop_b200_set_replicate): the binary families take their replicates through apop_b200_ll_score_batched");
     std::vector<double> key(beta, beta + P);
     for (int a = 0; a < 4; a++) key.push_back(aux ? aux[a] : 0.0);
     if (r->memo_valid && r->memo_fam == (int)fam && r->memo_beta.size() == key.size() &&
@@ -213,6 +214,9 @@ bool eval_logit(Resident* r, const std::vector<double>& B, size_t C1, const std:
     if (!r->has_y) return set_error("logit needs an outcome vector (run the model's prep first)");
     std::vector<double> key(B);
     key.insert(key.end(), cats.begin(), cats.end());
+    key.push_back((double)r->active_replicate);
+    if (r->active_replicate >= 0 && (!r->counts || (size_t)r->active_replicate >= r->counts_m))
+        return set_error("replicate %ld selected but the data set has resample counts for %zu replicates (apop_b200_bootstrap_counts)", r->active_replicate, r->counts_m);
     if (r->memo_valid && r->memo_fam == 200 + (int)C1 && r->memo_beta.size() == key.size() &&
         memcmp(r->memo_beta.data(), key.data(), key.size() * sizeof(double)) == 0) {
         out = r->memo_out;
@@ -227,6 +231,7 @@ bool eval_logit(Resident* r, const std::vector<double>& B, size_t C1, const std:
     LogitLaunch L;
     L.tiles = r->tiles; L.n_rows = r->n_rows; L.n_tiles = r->n_tiles; L.k = K; L.cols = r->cols;   // a weights column only widens the tile stride
     L.grid = grid_for(bps, r->n_tiles, LOGIT_THREADS / 32);
+    if (r->active_replicate >= 0) { L.counts = r->counts; L.m_pad = (int)r->counts_m; L.replicate = (int)r->active_replicate; }
     if (!ensure_partials((size_t)L.grid * NOUT)) return false;
     L.partials = R.d_partials; L.ticket = R.d_ticket; L.out = R.d_out; L.stream = R.stream;
     L.fin = make_fin(NOUT);

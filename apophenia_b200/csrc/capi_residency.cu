@@ -297,6 +297,7 @@ bool upload(Resident* r, const apop_data* d) {
     // resample counts and the per-row lgamma column belong to the rows that were resident before
     if (r->counts) { cudaFree(r->counts); r->counts = nullptr; }
     r->counts_m = 0;
+    r->active_replicate = -1;
     if (r->lgy) { cudaFree(r->lgy); r->lgy = nullptr; }
     if (!need) return true;
 

@@ -6,9 +6,11 @@
  *                             rows into a scratch set and runs a full apop_estimate per
  *                             replicate.  Here the resamples are multiplicity counts resident
  *                             next to the data and all replicates are fitted in lock-step, one
- *                             batched device pass per optimizer step (DMMA path).  Models the
- *                             batched path does not cover fall back to the reference's own loop
- *                             (resample on the host, apop_b200_invalidate, apop_estimate).
+ *                             batched device pass per optimizer step (DMMA path).  The multinomial
+ *                             logit takes the reference's own loop -- one fit per replicate -- over the
+ *                             same resident data, each row weighted by its resample count
+ *                             (apop_b200_set_replicate); anything else resamples on the host
+ *                             (apop_b200_invalidate, apop_estimate).
  *   apop_model_metropolis     apop_mcmc.m4.c:281-340: one chain, one LL pass per step, MVN
  *                             proposal centred on the last accepted draw, variance scaled by
  *                             sigma_adapt (:18-32) on every acceptance.
@@ -311,6 +313,42 @@ static apop_data *bootstrap_host_loop(apop_data *data, apop_model *model, uint64
     return cov;
 }
 
+/* Families the batched kernel does not cover but whose single-beta kernel takes resample counts (the multinomial
+ * logit): the reference's own loop -- one full fit per replicate (apop_bootstrap.m4.c:143-159) -- over the SAME resident
+ * data: replicate r is selected with apop_b200_set_replicate, which weights every row by its multiplicity in that
+ * resample, so no row is copied and nothing is re-uploaded.  Every fit is warm-started at the full-sample estimate. */
+static apop_data *bootstrap_replicate_loop(apop_data *data, apop_model *model, uint64_t seed, int iterations, apop_data **boot_store) {
+    counts_fn counts = (counts_fn)dev("apop_b200_bootstrap_counts");
+    int (*set_rep)(apop_data *, long) = (int (*)(apop_data *, long))dev("apop_b200_set_replicate");
+    if (!counts || !set_rep) return NULL;
+    if (counts(data, (size_t)iterations, seed)) return NULL;
+    gsl_vector *b0 = apop_data_pack(model->parameters, NULL);
+    const size_t P = b0->size;
+    apop_data *boots = apop_data_calloc(iterations, P, 0);
+    int ok = 1;
+    for (int i = 0; ok && i < iterations; i++) {
+        if (set_rep(data, i)) { ok = 0; break; }
+        apop_model *e = apop_model_copy(model);
+        e->data = data;
+        apop_mle_settings *mp = apop_settings_get_grp(e, "apop_mle");
+        if (!mp) { apop_mle_settings s = apop_mle_settings_defaults(); mp = apop_mle_settings_add(e, s); }
+        mp->starting_pt = b0->data;                                  /* warm start: the full-sample estimate */
+        if (!mp->method[0]) snprintf(mp->method, sizeof mp->method, "BFGS cg");
+        if (mp->tolerance >= 1e-5 && !mp->relative_tolerance) { mp->tolerance = 1e-9; mp->relative_tolerance = 1; }
+        apop_maximum_likelihood(data, e);
+        gsl_vector *p = apop_data_pack(e->parameters, NULL);
+        memcpy(boots->matrix->data + (size_t)i * P, p->data, sizeof(double) * P);
+        if (e->error) ok = 0;
+        gsl_vector_free(p);
+        apop_model_free(e);
+    }
+    set_rep(data, -1);
+    gsl_vector_free(b0);
+    apop_data *cov = ok ? apop_data_covariance(boots) : NULL;
+    if (boot_store && ok) *boot_store = boots; else apop_data_free(boots);
+    return cov;
+}
+
 /* Bootstrap covariance of the parameter estimates.  `model` must be estimated already
  * (its parameters are the warm start of every replicate) and carry a registered device
  * likelihood; `data` must be pinned. */
@@ -324,6 +362,10 @@ apop_data *apop_bootstrap_cov(apop_data *data, apop_model *model, uint64_t seed,
     gsl_vector *b0 = apop_data_pack(model->parameters, NULL);
     const size_t P = b0->size, m = (size_t)iterations;
     const int binary = data->matrix && P == data->matrix->size2;
+    if (fam == 1 && !binary && data->matrix && P % data->matrix->size2 == 0) {       /* multinomial logit */
+        gsl_vector_free(b0);
+        return bootstrap_replicate_loop(data, model, seed, iterations, boot_store);
+    }
     if (!batched || !counts || !((fam == 0 && binary) || (fam == 1 && binary) || (fam == 5 && binary))) {
         gsl_vector_free(b0);
         return bootstrap_host_loop(data, model, seed, iterations, boot_store);

@@ -56,10 +56,14 @@ __device__ __forceinline__ double exp_tab16(double x, const double* __restrict__
     return __hiloint2double(__double2hiint(e) + ((ki >> 4) << 20), __double2loint(e));
 }
 
-template <int KB, int C1, int HYB_STAGES, int VAR>
+// WEIGHTED: every row enters with the multiplicity a bootstrap replicate gives it (the resident resample counts of
+// apop_b200_bootstrap_counts, one byte per (row, replicate), layout of batched_kernel.cu): LL and score are those of
+// the resampled data set without a single row being copied (apop_bootstrap.m4.c:143-149 copies all N).
+template <int KB, int C1, int HYB_STAGES, int VAR, bool WEIGHTED>
 __global__ void __launch_bounds__(LOGIT_THREADS, HYB_STAGES == 2 ? 3 : 4)
 logit_hybrid_kernel(const double* __restrict__ tiles, const unsigned long long n_rows,
-                    const unsigned long long n_tiles, const int K, const int cols, const __grid_constant__ LogitParams prm,
+                    const unsigned long long n_tiles, const int K, const int cols, const unsigned char* __restrict__ counts,
+                    const int m_pad, const int replicate, const __grid_constant__ LogitParams prm,
                     double* __restrict__ partials, unsigned int* __restrict__ ticket,
                     double* __restrict__ out, const __grid_constant__ FinalizeCtx fin) {
     constexpr int WARPS = LOGIT_THREADS / 32;
@@ -125,7 +129,9 @@ logit_hybrid_kernel(const double* __restrict__ tiles, const unsigned long long n
     // exponent into prod_e with integer operations), one fm_log per lane at the end instead of one per row
     double prod = 1.0;
     long long prod_e = 0;
-    constexpr bool PROD = (VAR & 1) != 0, TAB = (VAR & 2) != 0, NB_OUTER = (VAR & 4) != 0;
+    constexpr bool PROD = (VAR & 1) != 0 && !WEIGHTED, TAB = (VAR & 2) != 0, NB_OUTER = (VAR & 4) != 0;
+    // this lane's byte inside a replicate's 32-byte count record (count_pos of batched_kernel.cu)
+    const int cpos = ((lane & 7) >> 1) * 8 + (lane >> 3) * 2 + (lane & 1);
     __shared__ double exp_tab[16];
     if (TAB) {
         if (threadIdx.x < 16) exp_tab[threadIdx.x] = exp2((double)threadIdx.x * 0.0625);
@@ -166,7 +172,10 @@ logit_hybrid_kernel(const double* __restrict__ tiles, const unsigned long long n
         int idx = C1;
 #pragma unroll
         for (int c = C1 - 1; c >= 0; c--) idx = (y == prm.cats[c]) ? c : idx;
-        const bool valid = t * TILE_ROWS + lane < n_rows;
+        const bool in_range = t * TILE_ROWS + lane < n_rows;
+        double wrow = 1.0;
+        if (WEIGHTED) wrow = (double)__ldg(counts + (t * (unsigned long long)m_pad + replicate) * TILE_ROWS + cpos);
+        const bool valid = in_range && (!WEIGHTED || wrow != 0.0);
 
         // ---- soft-max
         bool fast = true;
@@ -205,10 +214,10 @@ logit_hybrid_kernel(const double* __restrict__ tiles, const unsigned long long n
             inv = over ? 0.0 : fm_rcp(sum + e0);
         }
         // (the slab's previous contents were read before the barrier that ended the last iteration)
-        inv = valid ? inv : 0.0;
+        inv = valid ? inv * wrow : 0.0;
 #pragma unroll
         for (int c = 0; c < C1; c++) {
-            const double ind = (valid && idx == c + 1) ? 1.0 : 0.0;
+            const double ind = (valid && idx == c + 1) ? wrow : 0.0;
             slab[c * TILE_ROWS + ((c & 1) ? row_off1 : row_off0)] = fma(-e[c], inv, ind);
         }
         __syncwarp();
@@ -230,7 +239,7 @@ logit_hybrid_kernel(const double* __restrict__ tiles, const unsigned long long n
             prod_e += (long long)((eh >> 20) - 1023) + (long long)((ph >> 20) - 1023);
             prod = __hiloint2double((ph & 0x000fffff) | 0x3ff00000, __double2loint(prod));
         } else
-            ll.add(valid ? num - (lbase + fm_log_normal(lsum)) : 0.0);
+            ll.add(valid ? wrow * (num - (lbase + fm_log_normal(lsum))) : 0.0);
         if (NB_OUTER) {
 #pragma unroll
             for (int nb = 0; nb < 4; nb++) {
@@ -302,15 +311,22 @@ template <int KB, int C1, int ST, int VAR>
 static cudaError_t hyb_launch_st(const LogitLaunch& L, const LogitParams& prm) {
     static_assert((size_t)(LOGIT_THREADS / 32) * (1 + KB * C1) + (1 + KB * C1) <= hyb_smem<KB, ST>() / sizeof(double), "reduction scratch must fit the rings");
     static bool done = false;
-    if (!done) { cudaFuncSetAttribute(logit_hybrid_kernel<KB, C1, ST, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hyb_smem<KB, ST>()); done = true; }
-    logit_hybrid_kernel<KB, C1, ST, VAR><<<L.grid, LOGIT_THREADS, hyb_smem<KB, ST>(), L.stream>>>(L.tiles, L.n_rows, L.n_tiles, L.k, L.cols, prm, L.partials, L.ticket, L.out, L.fin);
+    if (!done) {
+        cudaFuncSetAttribute(logit_hybrid_kernel<KB, C1, ST, VAR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hyb_smem<KB, ST>());
+        cudaFuncSetAttribute(logit_hybrid_kernel<KB, C1, ST, VAR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hyb_smem<KB, ST>());
+        done = true;
+    }
+    if (L.counts)
+        logit_hybrid_kernel<KB, C1, ST, VAR, true><<<L.grid, LOGIT_THREADS, hyb_smem<KB, ST>(), L.stream>>>(L.tiles, L.n_rows, L.n_tiles, L.k, L.cols, L.counts, L.m_pad, L.replicate, prm, L.partials, L.ticket, L.out, L.fin);
+    else
+        logit_hybrid_kernel<KB, C1, ST, VAR, false><<<L.grid, LOGIT_THREADS, hyb_smem<KB, ST>(), L.stream>>>(L.tiles, L.n_rows, L.n_tiles, L.k, L.cols, nullptr, 0, 0, prm, L.partials, L.ticket, L.out, L.fin);
     return cudaGetLastError();
 }
 template <int KB, int C1, int ST, int VAR>
 static int hyb_bps_st() {
-    cudaFuncSetAttribute(logit_hybrid_kernel<KB, C1, ST, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hyb_smem<KB, ST>());
+    cudaFuncSetAttribute(logit_hybrid_kernel<KB, C1, ST, VAR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hyb_smem<KB, ST>());
     int nb = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, logit_hybrid_kernel<KB, C1, ST, VAR>, LOGIT_THREADS, hyb_smem<KB, ST>());
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, logit_hybrid_kernel<KB, C1, ST, VAR, false>, LOGIT_THREADS, hyb_smem<KB, ST>());
     return nb;
 }
 template <int KB, int C1>

@@ -14,6 +14,8 @@ struct LogitLaunch {
     const double* tiles;
     unsigned long long n_rows, n_tiles;
     int k, cols;           // cols = resident columns per tile (k + y [+ w, ignored])
+    const unsigned char* counts = nullptr;   // resample multiplicities of one bootstrap replicate (NULL: every row once)
+    int m_pad = 0, replicate = 0;
     double* partials;      // [grid][1 + KB*(C-1)]
     unsigned int* ticket;
     double* out;           // [1 + KB*(C-1)]: LL, then G[j][c] at 1 + j*(C-1) + c

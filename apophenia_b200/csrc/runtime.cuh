@@ -66,6 +66,7 @@ struct Resident {
     std::vector<std::pair<void*, size_t>> host_registered;
     // batched path: passes left for which the exact kernel is used because the last shared-centre pass found the
     // parameter vectors too far apart (then the Taylor form only adds work); re-probed when it reaches 0
+    long active_replicate = -1;   // >= 0: single-beta multinomial passes weight every row by this replicate's resample count
     int batched_exact_passes = 0;
     double batched_last_exact_fraction = 0.0;
 };

@@ -379,6 +379,11 @@ int apop_b200_ll_score_batched(apop_b200_family family, apop_data *d, const doub
  * pass over d that needed the exact evaluation (above 0.25 the next 32 passes use the exact kernel outright);
  * APOP_B200_BATCH_TAYLOR=0 switches the expansion off, APOP_B200_BATCH_DELTA sets the radius. */
 double apop_b200_batched_exact_fraction(const apop_data *d);
+/* Families outside the batched kernel (the multinomial logit) take their bootstrap replicates one at a time: with a
+ * replicate selected, apop_b200_logit_ll / _score weight every row by that replicate's resident resample count -- the
+ * LL and score of the resampled data set of apop_bootstrap.m4.c:143-149 without copying a row -- so the unmodified
+ * optimizer fits replicate after replicate on the same resident data.  replicate < 0 switches it off. */
+int apop_b200_set_replicate(apop_data *d, long replicate);
 /* draw m multinomial resamples of the rows into a resident n x m count matrix */
 int apop_b200_bootstrap_counts(apop_data *d, size_t m, uint64_t seed);
 /* the resident counts as an n_rows x m row-major uint8 matrix (for checking and for host-side drivers) */

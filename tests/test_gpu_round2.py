@@ -536,3 +536,43 @@ def test_batched_poisson_regression_with_resample_counts(b200, oracle):
         ll1, g1 = ab.ll_score_batched(ab.POISSON_REG, d, Bs[:3], use_counts=False)
         assert _rel(ll1[1], oracle.poisson_reg_ll(X, y, Bs[1], oracle.EXACT)) <= 1e-12
     ab.unpin(d)
+
+
+def test_multinomial_logit_replicate_weighted_pass_and_bootstrap(b200, oracle):
+    """apop_b200_set_replicate: LL and score of the multinomial logit over the resident data weighted by one bootstrap
+    replicate's counts == the oracle on the physically resampled rows; apop_bootstrap_cov of a multinomial model loops
+    the replicates over that (no row copies) and lands near the inverse observed information"""
+    from apophenia_b200 import abi, host
+    ab = b200
+    n, k, Cn, m = 40_003, 7, 4, 40
+    X, y, B = gen_probit_logit_sample(n, k, seed=61, method="logit", ncat=Cn)
+    d = ab.pin(ab.Data(matrix=X, vector=y))
+    ab.bootstrap_counts(d, m, seed=9)
+    c = ab.counts_download(d, m, n)
+    base = ab.ll_score(ab.LOGIT, d, B.ravel())
+    for r in (0, 17, m - 1):
+        ab.set_replicate(d, r)
+        ll, g = ab.ll_score(ab.LOGIT, d, B.ravel())
+        idx = np.repeat(np.arange(n), c[:, r])
+        wl = oracle.logit_ll(X[idx], y[idx], B, mode=oracle.EXACT)
+        wg, ws = oracle.logit_score(X[idx], y[idx], B, mode=oracle.EXACT)
+        assert _rel(ll, wl) <= 1e-12
+        assert np.all(np.abs(g - wg.astype(float).ravel()) <= 1e-12 * ws.astype(float).ravel())
+    ab.set_replicate(d, -1)
+    again = ab.ll_score(ab.LOGIT, d, B.ravel())
+    assert again[0] == base[0] and np.array_equal(again[1], base[1])
+    with pytest.raises(ab.B200Error):
+        ab.set_replicate(d, m + 8)
+    ab.unpin(d)
+    # the driver: fit, then bootstrap covariance through the replicate loop
+    raw = X.copy(); raw[:, 0] = y
+    dd = host.data_from_numpy(raw)
+    est, params, rep = host.estimate(abi.LOGIT, dd, method="BFGS cg", tolerance=1e-10, relative_tolerance=True, max_iterations=500)
+    assert rep["status"] == 0
+    cov, boots = host.bootstrap_cov(dd, est, iterations=60, seed=3)
+    Hw = oracle.logit_information(X, params.reshape(k, Cn - 1), Cn).astype(float)
+    want = np.diag(np.linalg.inv(Hw))
+    assert boots.shape == (60, k * (Cn - 1))
+    assert np.all(np.abs(boots.mean(0) - params) < 5 * np.sqrt(want / 60) + 0.2 * np.sqrt(want))
+    ratio = np.diag(cov) / want
+    assert 0.4 < ratio.min() and ratio.max() < 2.2, ratio        # 60 replicates: chi-square spread around 1
