@@ -179,7 +179,11 @@ template <> struct Taylor<FamProbit> {
         a[5] = s * l * (l * (l * (l * (24.0 * l + 60.0 * z) + 50.0 * z2 - 20.0) + z * (15.0 * z2 - 25.0)) + (z2 * (z2 - 6.0) + 3.0)) * (1.0 / 120.0);
         // g6 = l(l(l(l(l(-120l-360z)-390z^2+120)-180z^3+210z)-31z^4+101z^2-28)-z^5+10z^3-15z)
         a[6] = l * (l * (l * (l * (l * (-120.0 * l - 360.0 * z) - 390.0 * z2 + 120.0) + z * (210.0 - 180.0 * z2)) + (z2 * (101.0 - 31.0 * z2) - 28.0)) - z * (z2 * (z2 - 10.0) + 15.0)) * (1.0 / 720.0);
-        return fabs(x0) < 7.4;      // beyond, 1 - Phi meets its rounding / the 1e-10 clamps (model/apop_probit.c:85-86)
+        // On the unlikely side (z < 0) the reference forms P(observed) = 1 - n from the ROUNDED n = Phi(-x.b): its row
+        // term carries a rounding noise of 2^-53 / Phi(z) (8e-4 at z = -7.3, the knife edge of DESIGN.md section 2).  An
+        // expansion is smooth where the formula is not, so such rows keep the formula itself: expanded only while that
+        // noise is below 5e-13 (z > -3.5); on the likely side up to the saturation / clamp region.
+        return z > -3.5 && z < 7.4;
     }
 };
 template <> struct Taylor<FamLogit2> {

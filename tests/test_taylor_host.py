@@ -34,7 +34,7 @@ def _coefs(fn, x0, y, D):
 
 
 FUNCS = {
-    "probit": (lambda y: (lambda x: mp.log(mp.ncdf(x if y else -x))), "t_probit_coefs", (-6.0, 6.0), (0.0, 1.0)),
+    "probit": (lambda y: (lambda x: mp.log(mp.ncdf(x if y else -x))), "t_probit_coefs", (-3.4, 3.4), (0.0, 1.0)),
     "logit2": (lambda y: (lambda x: (x if y else 0) - mp.log(1 + mp.exp(x))), "t_logit2_coefs", (-12.0, 12.0), (0.0, 1.0)),
     "poisson": (lambda y: (lambda x: y * x - mp.exp(x)), "t_poisson_coefs", (-3.0, 3.0), (0.0, 2.0, 5.0)),
 }
@@ -84,5 +84,7 @@ def test_truncation_at_the_radius(lib, fam):
 def test_rows_near_the_clamps_are_not_expanded(lib):
     D = lib.t_degree()
     assert not _coefs(lib.t_probit_coefs, 7.5, 1.0, D)[0] and not _coefs(lib.t_probit_coefs, -8.3, 1.0, D)[0]
-    assert _coefs(lib.t_probit_coefs, 7.3, 0.0, D)[0]
+    assert _coefs(lib.t_probit_coefs, 7.3, 1.0, D)[0] and _coefs(lib.t_probit_coefs, -7.3, 0.0, D)[0]       # likely side: up to the clamps
+    assert not _coefs(lib.t_probit_coefs, -3.6, 1.0, D)[0] and not _coefs(lib.t_probit_coefs, 3.6, 0.0, D)[0]  # unlikely side: formula noise
+    assert _coefs(lib.t_probit_coefs, -3.4, 1.0, D)[0]
     assert not _coefs(lib.t_logit2_coefs, 31.0, 1.0, D)[0]

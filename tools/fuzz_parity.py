@@ -22,6 +22,10 @@ t_end = time.time() + budget
 count = {}
 
 
+def _report_last_error():
+    print("last_error:", ab.last_error(), flush=True)
+
+
 def ll_ok(got, want, what, slack=0.0):
     """slack: absolute allowance for terms that vanish below double resolution of their operands
     (x.b - (x.b + log(1 + e^-x.b)) is exactly 0 in the reference's double arithmetic for x.b > 37)"""
@@ -30,6 +34,8 @@ def ll_ok(got, want, what, slack=0.0):
         return
     if np.isinf(want) and got == want:
         return
+    if not abs(got - want) <= 1e-12 * abs(want) + slack + 1e-300:
+        _report_last_error()
     assert abs(got - want) <= 1e-12 * abs(want) + slack + 1e-300, (what, got, want)
 
 
@@ -40,11 +46,78 @@ def sc_ok(got, want, scale, what, slack=0.0):
 
 
 while time.time() < t_end:
-    fam = rng.choice(["probit", "logit2", "logitC", "poisson_reg", "ols", "normal", "poisson", "gamma", "beta", "t", "yule", "dirichlet"])
+    fam = rng.choice(["probit", "logit2", "logitC", "poisson_reg", "ols", "normal", "poisson", "gamma", "beta", "t", "yule", "dirichlet",
+                      "batched", "batched", "infoC"])
     n = int(rng.choice([1, 31, 32, 33, 1000, 4097, 30011, 100003]))
     scale = float(rng.choice([0.0, 0.1, 1.0, 4.0, 30.0]))
     count[fam] = count.get(fam, 0) + 1
-    if fam in ("probit", "logit2", "poisson_reg", "ols"):
+    if fam == "batched":
+        # the batched-beta path: random replicate counts, spreads from far inside the Taylor radius to far outside it,
+        # with and without resample counts and a weights column (ignored), every checked replicate against the oracle
+        k = int(rng.integers(1, 33)); m = int(rng.choice([1, 7, 8, 9, 63, 64, 65, 130]))
+        which = rng.choice(["probit", "logit", "poisson_reg"])
+        n = min(n, 30011)
+        X, y, beta = gen_probit_logit_sample(n, k, seed=int(rng.integers(1 << 30)), method="probit" if which == "probit" else "logit")
+        b = beta * min(scale, 4.0)
+        if which == "poisson_reg":
+            b = b / (4 * np.sqrt(k)); y = rng.poisson(np.exp(X @ b)).astype(float)
+        F = {"probit": ab.PROBIT, "logit": ab.LOGIT, "poisson_reg": ab.POISSON_REG}[which]
+        spread = float(rng.choice([0.0, 1e-4, 3e-3, 2e-2, 0.5]))
+        Bs = b[None, :] + spread * rng.standard_normal((m, k))
+        w = rng.uniform(0.5, 2.0, n) if rng.uniform() < 0.3 else None
+        d = ab.pin(ab.Data(matrix=X, vector=y, weights=w))
+        use_counts = bool(rng.integers(0, 2))
+        if use_counts:
+            ab.bootstrap_counts(d, m, seed=int(rng.integers(1 << 30))); cnt = ab.counts_download(d, m, n)
+        want_score = bool(rng.integers(0, 2))
+        llb, gb = ab.ll_score_batched(F, d, Bs, use_counts=use_counts, want_score=want_score)
+        for r in sorted(set([0, m // 2, m - 1])):
+            if use_counts:
+                idx = np.repeat(np.arange(n), cnt[:, r]); Xr, yr = X[idx], y[idx]
+            else:
+                Xr, yr = X, y
+            if Xr.shape[0] == 0:
+                assert llb[r] == 0.0; continue
+            eps = np.finfo(float).eps
+            if which == "probit":
+                from scipy.special import ndtr
+                # the reference clamps n only where the rounded double IS 0 or 1 (model/apop_probit.c:85-86); below that, 1 - n
+                # keeps its rounding noise of eps / (1 - n)
+                xb = Xr @ Bs[r]; nn = ndtr(-xb); nn = np.where(nn == 0, 1e-10, nn); nn = np.where(nn < 1, nn, 1 - 1e-10); arg = np.where(yr != 0, 1 - nn, nn)
+                slack = float(np.sum(8 * eps * np.where(yr != 0, nn / arg, 1.0)))
+                want = float(o.probit_ll(Xr, yr, Bs[r], o.FAITHFUL))
+                # the shared-centre expansion truncates at |a_7| delta^7 <= 5e-5 * 1.7e-13 per row in absolute terms (a row
+                # far on the likely side has a term of 1e-6 and below, so relative to a one-row LL that is not 1e-12)
+                slack += 3e-17 * Xr.shape[0]
+                if not abs(llb[r] - want) <= slack + 1e-12 * abs(want):
+                    ll1 = ab.ll_score(ab.PROBIT, d, Bs[r])[0] if not use_counts else float("nan")
+                    print("DIAG", which, n, k, m, "spread", spread, "scale", scale, "counts", use_counts, "score", want_score, "r", r, "batched", llb[r], "faithful", want,
+                          "exact-oracle", float(o.probit_ll(Xr, yr, Bs[r], o.EXACT)), "single kernel", ll1, "slack", slack, "max|xb|", float(np.max(np.abs(xb))),
+                          "exact share", ab.batched_exact_fraction(d), flush=True)
+                    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+                    np.savez_compressed(os.path.join(ROOT, "gpurun_out", "fuzz_fail.npz"), X=X, y=y, Bs=Bs, r=r, llb=llb)
+                assert abs(llb[r] - want) <= slack + 1e-12 * abs(want), (fam, which, n, k, m, spread, use_counts, r, llb[r], want)
+                if want_score and np.max(np.abs(xb)) < 6:
+                    ge, sc = o.probit_score(Xr, yr, Bs[r], o.EXACT); sc_ok(gb[r], ge, sc, (fam, which, n, k, m, spread, r), slack=8 * eps * np.abs(Xr).sum(0))
+            elif which == "logit":
+                ll_ok(llb[r], o.logit_ll(Xr, yr, Bs[r].reshape(k, 1), mode=o.EXACT), (fam, which, n, k, m, spread, r), slack=4 * Xr.shape[0] * eps * max(1.0, float(np.max(np.abs(Xr @ Bs[r])))))
+                if want_score:
+                    ge, sc = o.logit_score(Xr, yr, Bs[r].reshape(k, 1), mode=o.EXACT); sc_ok(gb[r], ge, sc, (fam, which, n, k, m, spread, r), slack=4 * eps * np.abs(Xr).sum(0))
+            else:
+                ll_ok(llb[r], o.poisson_reg_ll(Xr, yr, Bs[r], o.EXACT), (fam, which, n, k, m, spread, r))
+                if want_score:
+                    ge, sc = o.poisson_reg_score(Xr, yr, Bs[r], o.EXACT); sc_ok(gb[r], ge, sc, (fam, which, n, k, m, spread, r))
+        ab.unpin(d)
+    elif fam == "infoC":
+        k = int(rng.integers(1, 13)); C = int(rng.integers(3, 9)); n = min(n, 4097)
+        X, y, B = gen_probit_logit_sample(n, k, seed=int(rng.integers(1 << 30)), method="logit", ncat=C)
+        Bm = B * min(scale, 4.0)
+        d = ab.pin(ab.Data(matrix=X, vector=y))
+        H = ab.information(ab.LOGIT, d, Bm.ravel()); want = o.logit_information(X, Bm, C).astype(float)
+        assert np.max(np.abs(H - want)) <= 1e-11 * max(np.abs(want).max(), 1e-300), (fam, n, k, C, scale)
+        assert np.array_equal(H, H.T)
+        ab.unpin(d)
+    elif fam in ("probit", "logit2", "poisson_reg", "ols"):
         k = int(rng.integers(1, 41))
         X, y, beta = gen_probit_logit_sample(n, k, seed=int(rng.integers(1 << 30)), method="probit" if fam == "probit" else "logit")
         b = beta * scale
@@ -86,6 +159,10 @@ while time.time() < t_end:
             X[n // 2, -1] = 900.0 * rng.choice([-1, 1])
         d = ab.pin(ab.Data(matrix=X, vector=y))
         ll, g = ab.ll_score(ab.LOGIT, d, Bm.ravel())
+        if np.isnan(ll):
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+            np.savez_compressed(os.path.join(ROOT, "gpurun_out", "fuzz_fail_logitC.npz"), X=X, y=y, Bm=Bm)
+            print("DIAG logitC nan: second call", ab.ll_score(ab.LOGIT, d, Bm.ravel() * (1 + 1e-12))[0], "unpinned copy", ab.ll_score(ab.LOGIT, ab.Data(matrix=X.copy(), vector=y.copy()), Bm.ravel())[0], flush=True)
         ll_ok(ll, o.logit_ll(X, y, Bm, mode=o.EXACT), (fam, n, k, C, scale), slack=4 * n * np.finfo(float).eps * max(1.0, float(np.max(np.abs(X @ Bm)))))
         ge, sc = o.logit_score(X, y, Bm, mode=o.EXACT); sc_ok(g, ge, sc, (fam, n, k, C, scale), slack=np.repeat(4 * np.finfo(float).eps * np.abs(X).sum(0), C - 1))
         ab.unpin(d)
