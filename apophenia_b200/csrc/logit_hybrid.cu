@@ -156,7 +156,11 @@ logit_hybrid_kernel(const double* __restrict__ tiles, const unsigned long long n
         double xb[C1];
 #pragma unroll
         for (int c = 0; c < C1; c++) xb[c] = 0.0;
-        constexpr int XBLK = (KB >= 16) ? 16 : 8;
+        // (XBLK must divide KB: a 16-wide block over KB = 24 read columns 24..31 -- the y column and the other ring
+        // stage, times the zero padding of B -- and turned the LL into NaN whenever that stage had never been filled
+        // and held a NaN bit pattern: found by tools/fuzz_parity.py at n = 4097, k = 18)
+        constexpr int XBLK = (KB % 16 == 0) ? 16 : 8;
+        static_assert(KB % XBLK == 0, "register block must tile the staged columns exactly");
 #pragma unroll
         for (int j0 = 0; j0 < KB; j0 += XBLK) {
             double xv[XBLK];

@@ -576,3 +576,26 @@ def test_multinomial_logit_replicate_weighted_pass_and_bootstrap(b200, oracle):
     assert np.all(np.abs(boots.mean(0) - params) < 5 * np.sqrt(want / 60) + 0.2 * np.sqrt(want))
     ratio = np.diag(cov) / want
     assert 0.4 < ratio.min() and ratio.max() < 2.2, ratio        # 60 replicates: chi-square spread around 1
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,k,C", [(4097, 18, 3), (30011, 21, 5), (33, 24, 8), (2049, 17, 2), (5000, 32, 4), (4097, 9, 6)])
+def test_multinomial_logit_single_tile_per_warp(b200, oracle, n, k, C):
+    """Few tiles on a full grid: every warp sees at most one tile, so the second ring stage of logit_hybrid_kernel is
+    never filled.  A register block that overran KB = 24 read that stage (times B's zero padding) and returned NaN
+    whenever it held a NaN bit pattern; other kernels run first here so that shared memory is not clean."""
+    ab = b200
+    X, y, B = gen_probit_logit_sample(n, k, seed=n + k, method="logit", ncat=C)
+    nj = 32 * 148 * 32 * 2 + 7                                                  # two tiles per warp: both stages
+    junk = ab.pin(ab.Data(matrix=np.full((nj, 32), np.nan), vector=np.arange(nj) % 3.0))
+    try:
+        ab.ll_score(ab.LOGIT, junk, np.ones(32 * 2))                               # NaN rows through the ring
+    except Exception:
+        pass
+    ab.unpin(junk)
+    d = ab.pin(ab.Data(matrix=X, vector=y))
+    ll, g = ab.ll_score(ab.LOGIT, d, B.ravel())
+    assert _rel(ll, oracle.logit_ll(X, y, B, mode=oracle.EXACT)) <= 1e-12
+    wg, ws = oracle.logit_score(X, y, B, mode=oracle.EXACT)
+    assert np.all(np.abs(g - wg.astype(float).ravel()) <= 1e-12 * ws.astype(float).ravel())
+    ab.unpin(d)

@@ -84,7 +84,9 @@ while time.time() < t_end:
                 # the reference clamps n only where the rounded double IS 0 or 1 (model/apop_probit.c:85-86); below that, 1 - n
                 # keeps its rounding noise of eps / (1 - n)
                 xb = Xr @ Bs[r]; nn = ndtr(-xb); nn = np.where(nn == 0, 1e-10, nn); nn = np.where(nn < 1, nn, 1 - 1e-10); arg = np.where(yr != 0, 1 - nn, nn)
-                slack = float(np.sum(8 * eps * np.where(yr != 0, nn / arg, 1.0)))
+                # (absolute noise of log(1 - n) is ulp(1)/2 / (1 - n) per row whatever the size of n: a one-row LL of -3.8e-11
+                # carries 1e-16 of it, which is 3e-6 of its value)
+                slack = float(np.sum(2 * eps * np.where(yr != 0, 1.0 / arg, 1.0)))
                 want = float(o.probit_ll(Xr, yr, Bs[r], o.FAITHFUL))
                 # the shared-centre expansion truncates at |a_7| delta^7 <= 5e-5 * 1.7e-13 per row in absolute terms (a row
                 # far on the likely side has a term of 1e-6 and below, so relative to a one-row LL that is not 1e-12)
@@ -97,8 +99,13 @@ while time.time() < t_end:
                     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
                     np.savez_compressed(os.path.join(ROOT, "gpurun_out", "fuzz_fail.npz"), X=X, y=y, Bs=Bs, r=r, llb=llb)
                 assert abs(llb[r] - want) <= slack + 1e-12 * abs(want), (fam, which, n, k, m, spread, use_counts, r, llb[r], want)
-                if want_score and np.max(np.abs(xb)) < 6:
-                    ge, sc = o.probit_score(Xr, yr, Bs[r], o.EXACT); sc_ok(gb[r], ge, sc, (fam, which, n, k, m, spread, r), slack=8 * eps * np.abs(Xr).sum(0))
+                if want_score and np.max(np.abs(xb)) < 8:
+                    # the reference's weight pdf / (1 - cdf) (model/apop_probit.c:147-149) inherits the same rounding of the
+                    # double cdf: relative eps / (1 - cdf) on a y = 1 row
+                    dabs = np.exp(-0.5 * xb * xb) * 0.3989422804014327 / arg
+                    noise = dabs * 2 * eps * np.where(yr != 0, 1.0 / arg, 1.0)
+                    ge, sc = o.probit_score(Xr, yr, Bs[r], o.EXACT)
+                    sc_ok(gb[r], ge, sc, (fam, which, n, k, m, spread, r), slack=8 * eps * np.abs(Xr).sum(0) + (np.abs(Xr) * noise[:, None]).sum(0))
             elif which == "logit":
                 ll_ok(llb[r], o.logit_ll(Xr, yr, Bs[r].reshape(k, 1), mode=o.EXACT), (fam, which, n, k, m, spread, r), slack=4 * Xr.shape[0] * eps * max(1.0, float(np.max(np.abs(Xr @ Bs[r])))))
                 if want_score:
