@@ -86,6 +86,7 @@ static bool eval_logit_info(Resident* r, const double* B, size_t C1, double* H) 
         }
         LogitLaunch L;
         L.tiles = r->tiles; L.n_rows = r->n_rows; L.n_tiles = r->n_tiles; L.k = K; L.cols = r->cols;
+        L.swz = r->swz ? 1 : 0;   // the kernel stages either resident form
         L.grid = grid_for(bps, r->n_tiles, LOGIT_INFO_THREADS / 32);
         if (!ensure_partials((size_t)L.grid * NOUT)) return false;
         L.partials = R.d_partials; L.ticket = R.d_ticket; L.out = R.d_out; L.stream = R.stream;
@@ -115,7 +116,7 @@ static bool eval_logit_info(Resident* r, const double* B, size_t C1, double* H) 
 extern "C" int apop_b200_information(apop_b200_family family, apop_data* d, const double* beta, size_t P, double* H) {
     LOCK;
     if (!d || !beta || !H) { set_error("apop_b200_information: NULL argument"); return 1; }
-    Resident* r = acquire(d);
+    Resident* r = acquire(d, family == APOP_B200_LOGIT ? LAYOUT_ANY : LAYOUT_PLAIN);
     if (!r) return 1;
     bool ok = false;
     std::vector<double> out;
@@ -125,6 +126,7 @@ extern "C" int apop_b200_information(apop_b200_family family, apop_data* d, cons
         release(r);
         return okm ? 0 : 1;
     }
+    if (!ensure_layout(r, false)) { release(r); return 1; }
     if ((size_t)r->k != P) set_error("apop_b200_information: P = %zu but the data has %d columns", P, r->k);
     else if (family == APOP_B200_PROBIT) ok = eval_xtwx(r, XTWX_PROBIT, beta, nullptr, out);
     else if (family == APOP_B200_LOGIT) ok = eval_xtwx(r, XTWX_LOGIT2, beta, nullptr, out);

@@ -27,7 +27,11 @@ bool allreduce_scalar(double* v);
 // residency (capi_residency.cu)
 bool upload(apb::Resident* r, const apop_data* d);
 apb::HostSig host_sig(const apop_data* d);
-apb::Resident* acquire(apop_data* d);
+// layout the caller's kernels read: every kernel but the multinomial logit's takes the plain tiles; LAYOUT_ANY leaves
+// the copy as it is (the caller converts with ensure_layout once it knows)
+enum { LAYOUT_PLAIN = 0, LAYOUT_SWZ = 1, LAYOUT_ANY = 2 };
+apb::Resident* acquire(apop_data* d, int layout = LAYOUT_PLAIN);
+bool ensure_layout(apb::Resident* r, bool swz);
 void release(apb::Resident* r);
 // evaluators (capi_models.cu, capi_batched.cu)
 int grid_for(int blocks_per_sm, size_t n_tiles, int warps_per_block);

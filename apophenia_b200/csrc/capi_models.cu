@@ -228,8 +228,10 @@ bool eval_logit(Resident* r, const std::vector<double>& B, size_t C1, const std:
     if (bps <= 0) return set_error("multinomial logit kernel unavailable for k=%d, C=%zu", K, C1 + 1);
     const int KB = logit_kb(K);
     const int NOUT = 1 + KB * (int)C1;
+    if (!ensure_layout(r, logit_wants_swizzled())) return false;
     LogitLaunch L;
     L.tiles = r->tiles; L.n_rows = r->n_rows; L.n_tiles = r->n_tiles; L.k = K; L.cols = r->cols;   // a weights column only widens the tile stride
+    L.swz = r->swz ? 1 : 0;
     L.grid = grid_for(bps, r->n_tiles, LOGIT_THREADS / 32);
     if (r->active_replicate >= 0) { L.counts = r->counts; L.m_pad = (int)r->counts_m; L.replicate = (int)r->active_replicate; }
     if (!ensure_partials((size_t)L.grid * NOUT)) return false;
@@ -275,7 +277,7 @@ extern "C" long double apop_b200_logit_ll(apop_data* d, apop_model* m) {
     }
     std::vector<double> B, out;
     pack_parameters(m->parameters, B);
-    Resident* r = acquire(d);
+    Resident* r = acquire(d, LAYOUT_ANY);   // eval_logit converts to the layout its kernel reads
     if (!r) { d->error = 'a'; return NAN; }
     const bool ok = eval_logit(r, B, C1, cats, out);
     release(r);
@@ -299,7 +301,7 @@ extern "C" void apop_b200_logit_score(apop_data* d, gsl_vector* g, apop_model* m
     }
     std::vector<double> B, out;
     pack_parameters(m->parameters, B);
-    Resident* r = acquire(d);
+    Resident* r = acquire(d, LAYOUT_ANY);   // eval_logit converts to the layout its kernel reads
     if (!r) { fill_nan(g); return; }
     const bool ok = eval_logit(r, B, C1, cats, out);
     release(r);
@@ -399,6 +401,7 @@ static bool ols_input_term(apop_data* d, Resident* r, apop_model* id, long doubl
         R.reg[&view] = &tmp;
         const long double v = id->log_likelihood(&view, id);
         R.reg.erase(&view);
+        r->swz = tmp.swz;   // the view shares the tiles: a layout change made through it is the owner's too
         term = v;
         return !std::isnan((double)v);
     }

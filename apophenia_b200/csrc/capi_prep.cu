@@ -88,6 +88,7 @@ static int prep_outcome_locked(apop_data* d, double* cats_out, size_t max_cats, 
         // already tiled and shuffled, and there is no host copy to mirror anything into
         if (!r->has_y) { set_error("apop_b200_prep_outcome: the device-only data set has no outcome column (ingest it with outcome_col0)"); return 1; }
         sync_host = 0;
+        if (!ensure_layout(r, false)) return 1;   // the category kernels mask rows by position
     } else {
         r->y_col0 = (d->vector == nullptr);
         r->recoded = false;   // a fresh prep reads the raw outcomes of the host copy

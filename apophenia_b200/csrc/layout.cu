@@ -66,6 +66,39 @@ tile_unpack_kernel(const double* __restrict__ tiles, unsigned long long rows, in
     if (has_w && ty == 1 && row0 + tx < rows && ws) ws[row0 + tx] = src[col * TILE_ROWS + tx];
 }
 
+// ---------------------------------------------------------------------------
+// Swizzled form of the resident layout (the multinomial logit kernels'): the 16-byte chunk c of column j of a
+// tile is stored at chunk c ^ sw(j), sw(j) = ((j & 1) << 2) | (j & 2) -- i.e. row r at position
+// r ^ (8 (j & 1) + 4 ((j >> 1) & 1)).  A tile brought into shared memory by ONE bulk copy is then bank-conflict
+// free for all three access patterns of logit_stream.cu: lane = row (any permutation inside a 256-byte column
+// is), the 16-byte DMMA fragments of the score (columns g, g+1 of a fragment land in different halves of a
+// 128-byte bank row) and the 8-byte fragments of X.B (the four columns of a k-step land in different quarters).
+// The map is an involution: the same kernel converts in either direction, in place, one warp per column.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+tile_swizzle_kernel(double* __restrict__ tiles, unsigned long long n_tiles, int cols) {
+    const int lane = threadIdx.x & 31;
+    const unsigned long long total = n_tiles * (unsigned long long)cols;
+    const unsigned long long nw = (unsigned long long)gridDim.x * (blockDim.x >> 5);
+    for (unsigned long long w = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < total; w += nw) {
+        const int c = (int)(w % (unsigned long long)cols);
+        const int rx = ((c & 1) << 3) | ((c & 2) << 1);
+        if (!rx) continue;                       // every fourth column stays as it is
+        double* p = tiles + w * TILE_ROWS;      // column c of tile w / cols
+        const double v = p[lane ^ rx];
+        __syncwarp();
+        p[lane] = v;
+    }
+}
+cudaError_t tile_swizzle(double* tiles, size_t n_tiles, int cols, cudaStream_t st) {
+    if (!n_tiles || cols < 2) return cudaSuccess;
+    const unsigned long long total = (unsigned long long)n_tiles * cols;
+    const unsigned long long want = (total + 7) / 8;
+    const unsigned grid = (unsigned)(want < 148ull * 32 ? (want ? want : 1) : 148ull * 32);
+    tile_swizzle_kernel<<<grid, 256, 0, st>>>(tiles, n_tiles, cols);
+    return cudaGetLastError();
+}
+
 cudaError_t tile_pack(const double* Xs, const double* ys, const double* ws, size_t rows, int k,
                       int cols, double* tiles, cudaStream_t st, bool y_col0) {
     const size_t nt = (rows + TILE_ROWS - 1) / TILE_ROWS;

@@ -21,6 +21,8 @@ struct CatTable { double v[PREP_MAX_CATS]; int n; };
 cudaError_t recode_launch(double* tiles, size_t n_rows, size_t n_tiles, int ycol, int cols, const CatTable& cats, cudaStream_t st);
 cudaError_t tile_unpack(const double* tiles, size_t rows, int k, int cols, bool has_y, bool has_w,
                         double* Xs, double* ys, double* ws, cudaStream_t st);
+// in-place conversion between the plain and the swizzled resident layout (an involution; see layout.cu)
+cudaError_t tile_swizzle(double* tiles, size_t n_tiles, int cols, cudaStream_t st);
 cudaError_t synth_fill(int family, size_t n_rows, int k, int cols, int ncat, const SynthParams& prm,
                        unsigned long long seed, unsigned long long row_offset, double* tiles,
                        cudaStream_t st);

@@ -27,35 +27,6 @@
 
 namespace apb {
 
-__device__ __forceinline__ void dmma_884(double& d0, double& d1, double a, double b) {
-    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-        : "+d"(d0), "+d"(d1)
-        : "d"(a), "d"(b));
-}
-
-
-// exp(x) for |x| <= 708 with a 16-entry table of 2^(j/16) in shared memory (one 128-byte line: 16 entries on
-// 32 banks, so any pattern of lanes is conflict free): k = rint(16 x / ln 2), x = k ln2/16 + r, |r| <= ln2/32,
-// exp(x) = 2^(k >> 4) * T[k & 15] * e^r with e^r - 1 by a degree-7 polynomial (r^8/8! < 1.2e-18): 12 FP64-pipe
-// operations instead of the 17 of fm_exp_fast, the rest on the ALU and shared-memory pipes.
-__device__ __forceinline__ double exp_tab16(double x, const double* __restrict__ tab) {
-    const double t = fma(x, 23.083120654223414, 6755399441055744.0);       // 16 / ln 2
-    const double kf = t - 6755399441055744.0;
-    const int ki = __double2loint(t);
-    double r = fma(kf, -4.33216987730702385306e-02, x);                      // ln2/16 hi (the fdlibm ln2 hi / 16: exact)
-    r = fma(kf, -1.19263433079411731251e-11, r);                             // ln2/16 lo
-    double p = 1.9841269841269841e-04;                                       // 1/7!
-    p = fma(p, r, 1.3888888888888889e-03);
-    p = fma(p, r, 8.3333333333333332e-03);
-    p = fma(p, r, 4.1666666666666664e-02);
-    p = fma(p, r, 1.6666666666666666e-01);
-    p = fma(p, r, 5.0000000000000000e-01);
-    p = fma(p, r, 1.0);
-    const double T = tab[ki & 15];
-    const double e = fma(T * r, p, T);                                       // T (1 + r p)
-    return __hiloint2double(__double2hiint(e) + ((ki >> 4) << 20), __double2loint(e));
-}
-
 // WEIGHTED: every row enters with the multiplicity a bootstrap replicate gives it (the resident resample counts of
 // apop_b200_bootstrap_counts, one byte per (row, replicate), layout of batched_kernel.cu): LL and score are those of
 // the resampled data set without a single row being copied (apop_bootstrap.m4.c:143-149 copies all N).

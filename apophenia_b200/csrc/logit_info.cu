@@ -31,7 +31,7 @@ constexpr int INFO_CS = 36;   // padded column stride of a staged tile (doubles)
 template <int KB, int C1>
 __global__ void __launch_bounds__(LOGIT_INFO_THREADS, 2)
 logit_info_kernel(const double* __restrict__ tiles, const unsigned long long n_rows, const unsigned long long n_tiles,
-                  const int K, const int cols, const __grid_constant__ LogitParams prm, const __grid_constant__ LogitInfoPairs pairs,
+                  const int K, const int cols, const int swz, const __grid_constant__ LogitParams prm, const __grid_constant__ LogitInfoPairs pairs,
                   double* __restrict__ partials, unsigned int* __restrict__ ticket, double* __restrict__ out,
                   const __grid_constant__ FinalizeCtx fin) {
     constexpr int WARPS = LOGIT_INFO_THREADS / 32;
@@ -61,12 +61,16 @@ logit_info_kernel(const double* __restrict__ tiles, const unsigned long long n_r
     for (unsigned long long t = gwarp; t < n_tiles; t += nwarps) {
         {   // stage the K columns of X: 16-byte chunk `lane + 32 i` lies in resident column (lane >> 4) + 2 i
             const double* src = tiles + t * (unsigned long long)(cols * TILE_ROWS) + lane * 2;
-            const unsigned sa = smem_u32(tile + (lane >> 4) * INFO_CS + (lane & 15) * 2);
+            // (swizzled resident form, layout.cu: chunk c of column j holds the rows of chunk c ^ sw(j) -- undone on the
+            // way in; the column of copy i is (lane >> 4) + 2 i, so sw = ((lane >> 4) << 2) | ((i & 1) << 1))
+            const int ch = (lane & 15) ^ ((swz & (lane >> 4)) << 2);
+            const unsigned sa0 = smem_u32(tile + (lane >> 4) * INFO_CS + ch * 2);
+            const unsigned sa1 = smem_u32(tile + (lane >> 4) * INFO_CS + (ch ^ (swz << 1)) * 2);
 #pragma unroll
             for (int i = 0; i < KB / 2; i++) {
                 const int col = (lane >> 4) + 2 * i;
                 if (col < K)
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa + i * 2 * INFO_CS * 8), "l"(src + i * 64));
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(((i & 1) ? sa1 : sa0) + i * 2 * INFO_CS * 8), "l"(src + i * 64));
             }
             asm volatile("cp.async.commit_group;");
             asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -162,7 +166,7 @@ template <int KB, int C1>
 static cudaError_t info_launch_one(const LogitLaunch& L, const LogitParams& prm, const LogitInfoPairs& pairs) {
     static bool done = false;
     if (!done) { cudaFuncSetAttribute(logit_info_kernel<KB, C1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)info_smem<KB>()); done = true; }
-    logit_info_kernel<KB, C1><<<L.grid, LOGIT_INFO_THREADS, info_smem<KB>(), L.stream>>>(L.tiles, L.n_rows, L.n_tiles, L.k, L.cols, prm, pairs,
+    logit_info_kernel<KB, C1><<<L.grid, LOGIT_INFO_THREADS, info_smem<KB>(), L.stream>>>(L.tiles, L.n_rows, L.n_tiles, L.k, L.cols, L.swz, prm, pairs,
                                                                                       L.partials, L.ticket, L.out, L.fin);
     return cudaGetLastError();
 }

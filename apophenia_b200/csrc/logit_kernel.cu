@@ -20,7 +20,16 @@ int logit_kb(int k) { return k <= 8 ? 8 : k <= 16 ? 16 : k <= 24 ? 24 : 32; }
 
 // (An all-DMMA variant, 1.14 ms against the hybrid's 1.12-1.165, and a TMA-streamed probit kernel, slower than
 // the register-resident one, are kept out of the build under tools/experiments/.)
-cudaError_t logit_launch(int c1, const LogitLaunch& L, const LogitParams& prm) { return logit_hybrid_launch(c1, L, prm); }
-int logit_blocks_per_sm(int k, int c1) { return logit_hybrid_blocks_per_sm(k, c1); }
+// Default: logit_stream.cu (swizzled resident tiles, one bulk copy per tile).  APOP_B200_LOGIT_KERNEL=hybrid selects
+// the cp.async kernel of logit_hybrid.cu (plain tiles) for A/B measurements.
+static bool use_hybrid() {
+    static const int v = [] { const char* e = getenv("APOP_B200_LOGIT_KERNEL"); return (e && !strcmp(e, "hybrid")) ? 1 : 0; }();
+    return v != 0;
+}
+cudaError_t logit_launch(int c1, const LogitLaunch& L, const LogitParams& prm) {
+    return use_hybrid() ? logit_hybrid_launch(c1, L, prm) : logit_stream_launch(c1, L, prm);
+}
+int logit_blocks_per_sm(int k, int c1) { return use_hybrid() ? logit_hybrid_blocks_per_sm(k, c1) : logit_stream_blocks_per_sm(k, c1); }
+bool logit_wants_swizzled() { return !use_hybrid(); }
 
 }  // namespace apb

@@ -28,6 +28,7 @@ struct Resident {
     int cols = 0;           // k + has_y + has_w
     size_t n_tiles = 0;
     double* tiles = nullptr;
+    bool swz = false;        // tiles are in the swizzled form (rows r ^ 8 in odd columns): only the multinomial logit kernels read it
     bool synthetic = false;
     bool y_col0 = false;     // pinned by the device prep: column 0 of the host matrix is the outcome (ols_shuffle done here)
     bool dirty = false;      // host copy changed: re-upload before next use
