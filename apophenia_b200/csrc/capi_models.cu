@@ -232,7 +232,7 @@ bool eval_logit(Resident* r, const std::vector<double>& B, size_t C1, const std:
     LogitLaunch L;
     L.tiles = r->tiles; L.n_rows = r->n_rows; L.n_tiles = r->n_tiles; L.k = K; L.cols = r->cols;   // a weights column only widens the tile stride
     L.swz = r->swz ? 1 : 0;
-    L.grid = grid_for(bps, r->n_tiles, LOGIT_THREADS / 32);
+    L.grid = grid_for(bps, r->n_tiles, logit_warps_per_block());
     if (r->active_replicate >= 0) { L.counts = r->counts; L.m_pad = (int)r->counts_m; L.replicate = (int)r->active_replicate; }
     if (!ensure_partials((size_t)L.grid * NOUT)) return false;
     L.partials = R.d_partials; L.ticket = R.d_ticket; L.out = R.d_out; L.stream = R.stream;

@@ -31,5 +31,6 @@ cudaError_t logit_launch(int c1, const LogitLaunch& L, const LogitParams& prm) {
 }
 int logit_blocks_per_sm(int k, int c1) { return use_hybrid() ? logit_hybrid_blocks_per_sm(k, c1) : logit_stream_blocks_per_sm(k, c1); }
 bool logit_wants_swizzled() { return !use_hybrid(); }
+int logit_warps_per_block() { return use_hybrid() ? LOGIT_THREADS / 32 : logit_stream_warps_per_block(); }
 
 }  // namespace apb

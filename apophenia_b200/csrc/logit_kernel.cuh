@@ -29,6 +29,7 @@ int logit_kb(int k);
 // logit_stream.cu: the default kernel (bulk-copy ring, both contractions on the FP64 MMA path, lane = row soft-max)
 cudaError_t logit_stream_launch(int c1, const LogitLaunch& L, const LogitParams& prm);
 int logit_stream_blocks_per_sm(int k, int c1);
+int logit_stream_warps_per_block();
 // logit_hybrid.cu: the round-1/2 kernel (lane = row X.B and soft-max, DMMA score, cp.async ring; plain tiles)
 cudaError_t logit_hybrid_launch(int c1, const LogitLaunch& L, const LogitParams& prm);
 int logit_hybrid_blocks_per_sm(int k, int c1);
@@ -42,6 +43,7 @@ int logit_info_blocks_per_sm(int k, int c1);
 cudaError_t logit_launch(int c1, const LogitLaunch& L, const LogitParams& prm);
 int logit_blocks_per_sm(int k, int c1);
 bool logit_wants_swizzled();
+int logit_warps_per_block();   // of the kernel logit_launch picks (grid sizing)
 
 #ifdef __CUDACC__
 __device__ __forceinline__ void dmma_884(double& d0, double& d1, double a, double b) {

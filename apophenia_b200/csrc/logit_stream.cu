@@ -13,11 +13,17 @@
 //   soft-max  lane = row through an 8 x 32 slab: one_logit_row (model/apop_probit.c:212-229) with the table
 //             exponential and the product-form LL of logit_hybrid.cu;
 //   stage 3   G^T[c][j] += R^T[c][row] . X[row][j] as 32 DMMA.8x8x4, X fragments 16-byte shared loads.
+// Occupancy.  A warp with a private two-slot ring needs 19 KB of shared memory: 12 warps per SM, 3 per scheduler, and
+// ncu shows the shared FP64 datapath 77 % busy (0.97 ms) -- the rest is latency no third warp was there to cover.
+// The PAIRED form lets two warps share a THREE-slot ring (the pair's tiles alternate between them; whoever finishes
+// a slot refills it for its partner) and keeps the slab at 7 rows: 28.9 KB per pair, 16 warps per SM as ONE CTA of
+// 512 threads at 128 registers.
 // Datapath: 64 DMMA x 16 + ~110 FP64 x 2 cycles = ~1250 cycles per tile and scheduler, against 1330 cycles of
 // HBM time at 7.3 TB/s.  X and y are read from HBM exactly once: 8(k+1) bytes per row.
 #include "logit_kernel.cuh"
 #include "fastmath.cuh"
 #include <stdlib.h>
+#include <string.h>
 
 namespace apb {
 
@@ -29,52 +35,70 @@ __device__ __forceinline__ void dmma_884v(double& d0, double& d1, double a, doub
                  : "d"(a), "d"(b));
 }
 
-constexpr int STREAM_STAGES = 2;
+// PAIRED: 16 warps in 8 pairs, 3 slots per pair, one CTA per SM.  Otherwise 4 warps with 2 private slots each, 3 CTAs per SM.
+template <bool PAIRED> struct StreamCfg {
+    static constexpr int WARPS = PAIRED ? 16 : 4;      // per CTA
+    static constexpr int GROUP = PAIRED ? 2 : 1;       // warps sharing a ring
+    static constexpr int SLOTS = PAIRED ? 3 : 2;       // tiles in a ring
+    static constexpr int SLAB_ROWS = PAIRED ? 7 : 8;   // category rows of a warp's slab
+    static constexpr int CTAS = PAIRED ? 1 : 3;        // per SM
+};
 
-template <int KB, int C1, bool WEIGHTED>
-__global__ void __launch_bounds__(LOGIT_THREADS, 3)
+template <int KB, int C1, bool WEIGHTED, bool PAIRED>
+__global__ void __launch_bounds__(StreamCfg<PAIRED>::WARPS * 32, StreamCfg<PAIRED>::CTAS)
 logit_stream_kernel(const double* __restrict__ tiles, const unsigned long long n_rows,
                     const unsigned long long n_tiles, const int K, const int cols, const unsigned char* __restrict__ counts,
                     const int m_pad, const int replicate, const __grid_constant__ LogitParams prm,
                     double* __restrict__ partials, unsigned int* __restrict__ ticket,
                     double* __restrict__ out, const __grid_constant__ FinalizeCtx fin) {
-    constexpr int WARPS = LOGIT_THREADS / 32;
+    using Cfg = StreamCfg<PAIRED>;
+    constexpr int WARPS = Cfg::WARPS, GROUP = Cfg::GROUP, SLOTS = Cfg::SLOTS, SLAB_ROWS = Cfg::SLAB_ROWS;
+    constexpr int THREADS = WARPS * 32, NGROUPS = WARPS / GROUP;
     constexpr int JB = KB / 8, KS = KB / 4;
     constexpr int TILE_D = (KB + 1) * TILE_ROWS;          // staged tile: the resident K + 1 columns, byte for byte
-    constexpr int WARP_D = STREAM_STAGES * TILE_D + 8 * TILE_ROWS;
+    constexpr int SLAB_D = SLAB_ROWS * TILE_ROWS;
+    constexpr int GROUP_D = SLOTS * TILE_D + GROUP * SLAB_D;
     constexpr int NOUT = 1 + KB * C1;
     extern __shared__ __align__(16) double smem[];
-    __shared__ __align__(8) unsigned long long bars[WARPS * STREAM_STAGES];
+    __shared__ __align__(8) unsigned long long bars[NGROUPS * SLOTS];
     __shared__ double exp_tab[16];
+    __shared__ unsigned seen[NGROUPS * SLOTS];            // PAIRED: fills of each slot seen complete by their consumers
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int grp = warp / GROUP, wg = warp % GROUP;      // ring, and this warp's turn inside it
     const int g = lane >> 2, q = lane & 3;
-    double* ring = smem + warp * WARP_D;
-    double* slab = ring + STREAM_STAGES * TILE_D;         // [category][row], swizzled like a tile column
-    const unsigned long long gwarp = (unsigned long long)blockIdx.x * WARPS + warp;
-    const unsigned long long nwarps = (unsigned long long)gridDim.x * WARPS;
+    double* ring = smem + grp * GROUP_D;
+    double* slab = ring + SLOTS * TILE_D + wg * SLAB_D;   // [category][row], swizzled like a tile column
+    // the ring's tiles: item i is tile ggrp + i * ngrps; warp wg of the ring takes the items i = wg (mod GROUP);
+    // item i lives in slot i % SLOTS and is the (i / SLOTS)-th fill of that slot
+    const unsigned ggrp = blockIdx.x * NGROUPS + grp, ngrps = gridDim.x * NGROUPS;
 
     // the bulk copy writes columns 0..K (X and y); K+1..KB stay zero for the whole kernel, and so do the slab
     // rows of the padding categories
-    for (int i = lane; i < STREAM_STAGES * TILE_D; i += 32)
+    for (int i = wg * 32 + lane; i < SLOTS * TILE_D; i += GROUP * 32)
         if ((i % TILE_D) / TILE_ROWS > K) ring[i] = 0.0;
-    for (int i = C1 * TILE_ROWS + lane; i < 8 * TILE_ROWS; i += 32) slab[i] = 0.0;
-    if (lane < STREAM_STAGES) mbar_init(bars + warp * STREAM_STAGES + lane, 1);
+    for (int i = C1 * TILE_ROWS + lane; i < SLAB_D; i += 32) slab[i] = 0.0;
+    if (wg == 0 && lane < SLOTS) { mbar_init(bars + grp * SLOTS + lane, 1); seen[grp * SLOTS + lane] = 0; }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     if (threadIdx.x < 16) exp_tab[threadIdx.x] = exp2((double)threadIdx.x * 0.0625);
     __syncthreads();
 
-    const unsigned bar_u32 = smem_u32(bars + warp * STREAM_STAGES), ring_u32 = smem_u32(ring);
+    const unsigned bar_u32 = smem_u32(bars + grp * SLOTS), ring_u32 = smem_u32(ring), seen_u32 = smem_u32(seen + grp * SLOTS);
     const unsigned tile_bytes = (unsigned)(K + 1) * TILE_ROWS * sizeof(double);
-    unsigned phases = 0;                                  // bit s: parity the next wait on stage s expects
-    auto prefetch = [&](unsigned long long tt, int stage) {
+    // fill slot `slot` with tile tt: one lane, one UBLKCP; completion (all bytes landed) flips the slot's barrier phase
+    auto fill = [&](unsigned long long tt, int slot) {
         if (lane == 0) {
-            const unsigned bar = bar_u32 + stage * 8, dst = ring_u32 + stage * (TILE_D * 8);
+            const unsigned bar = bar_u32 + slot * 8, dst = ring_u32 + slot * (TILE_D * 8);
             const double* src = tiles + tt * (unsigned long long)(cols * TILE_ROWS);
-            fence_proxy_async();   // this stage's reads (generic proxy, before the last __syncwarp) precede the async writes
+            fence_proxy_async();   // the slot's reads (generic proxy, before the last __syncwarp) precede the async writes
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(tile_bytes) : "memory");
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                          ::"r"(dst), "l"(src), "r"(tile_bytes), "r"(bar) : "memory");
         }
+    };
+    auto wait_fill = [&](int slot, unsigned parity) {
+        const unsigned bar = bar_u32 + slot * 8;
+        asm volatile("{\n\t.reg .pred p;\n\tWAIT_TILE:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra TILE_READY;\n\tbra WAIT_TILE;\n\tTILE_READY:\n\t}"
+                     ::"r"(bar), "r"(parity) : "memory");
     };
 
     // swizzle of column (or slab row) n: chunk ^ sw(n); as a row offset, row ^ (sw(n) << 1)
@@ -102,27 +126,39 @@ logit_stream_kernel(const double* __restrict__ tiles, const unsigned long long n
     // this lane's byte inside a replicate's 32-byte count record (count_pos of batched_kernel.cu)
     const int cpos = ((lane & 7) >> 1) * 8 + (lane >> 3) * 2 + (lane & 1);
 
-    double G[JB][2], G2[JB][2];
+    double G[JB][2];
 #pragma unroll
-    for (int jb = 0; jb < JB; jb++) G[jb][0] = G[jb][1] = G2[jb][0] = G2[jb][1] = 0.0;
+    for (int jb = 0; jb < JB; jb++) G[jb][0] = G[jb][1] = 0.0;
     KSum ll;
     // sum_i log(lsum_i) as the log of a running product: mantissa in prod (kept in [1, 2) by moving its exponent
     // into prod_e with integer operations), one fm_log per lane at the end instead of one per row
     constexpr bool PROD = !WEIGHTED;
     double prod = 1.0;
-    long long prod_e = 0;
+    int prod_e = 0;   // (a lane's rows x 1025 stay far below 2^31: the grid spreads 10^11 rows before it would not)
 
-    int cur = 0;
-    if (gwarp < n_tiles) prefetch(gwarp, 0);
-    for (unsigned long long t = gwarp; t < n_tiles; t += nwarps) {
-        if (t + nwarps < n_tiles) prefetch(t + nwarps, cur ^ 1);
-        {
-            const unsigned bar = bar_u32 + cur * 8, parity = (phases >> cur) & 1u;
-            asm volatile("{\n\t.reg .pred p;\n\tWAIT_TILE:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra TILE_READY;\n\tbra WAIT_TILE;\n\tTILE_READY:\n\t}"
-                         ::"r"(bar), "r"(parity) : "memory");
-            phases ^= 1u << cur;
+    // the first SLOTS items of the ring
+    if (wg == 0) {
+#pragma unroll
+        for (int i = 0; i < SLOTS; i++)
+            if (ggrp + (unsigned long long)i * ngrps < n_tiles) fill(ggrp + (unsigned long long)i * ngrps, i);
+    }
+    for (unsigned i = wg;; i += GROUP) {
+        const unsigned long long t = ggrp + (unsigned long long)i * ngrps;
+        if (t >= n_tiles) break;
+        const int slot = (int)(i % SLOTS);
+        const unsigned nfill = i / SLOTS;
+        // PAIRED: the previous fill of this slot was the partner's, so this warp has not seen it complete, and a parity
+        // wait cannot tell "fill n-1 still in flight" from "fill n done" (same parity two phases apart).  The consumer
+        // of every fill therefore publishes the number of fills it has seen land; the barrier is then known to be in
+        // phase n or n+1 when the parity wait below starts.
+        if (GROUP > 1 && nfill > 0) {
+            unsigned have;
+            do asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(have) : "r"(seen_u32 + slot * 4) : "memory");
+            while (have < nfill);
         }
-        const double* tile = ring + cur * TILE_D;
+        wait_fill(slot, nfill & 1u);
+        if (GROUP > 1 && lane == 0) asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(seen_u32 + slot * 4), "r"(nfill + 1) : "memory");
+        const double* tile = ring + slot * TILE_D;
 
         // ---- stage 1 on the MMA path: 4 accumulator chains (one per row block), consecutive DMMAs of a chain are
         // 4 issue slots = 64 cycles apart (latency 26)
@@ -140,7 +176,8 @@ logit_stream_kernel(const double* __restrict__ tiles, const unsigned long long n
         }
         // C fragments S^T[c = g][rows nb*8 + 2q + {0,1}] -> slab (the padding rows receive zeros)
 #pragma unroll
-        for (int nb = 0; nb < 4; nb++) *reinterpret_cast<double2*>(slab + fo[nb]) = make_double2(S[nb][0], S[nb][1]);
+        for (int nb = 0; nb < 4; nb++)
+            if (g < SLAB_ROWS) *reinterpret_cast<double2*>(slab + fo[nb]) = make_double2(S[nb][0], S[nb][1]);
         __syncwarp();
         double xb[C1];
 #pragma unroll
@@ -202,7 +239,8 @@ logit_stream_kernel(const double* __restrict__ tiles, const unsigned long long n
         double R[4][2];
 #pragma unroll
         for (int nb = 0; nb < 4; nb++) {
-            const double2 r2 = *reinterpret_cast<const double2*>(slab + fo[nb]);
+            double2 r2 = make_double2(0.0, 0.0);
+            if (g < SLAB_ROWS) r2 = *reinterpret_cast<const double2*>(slab + fo[nb]);
             R[nb][0] = r2.x; R[nb][1] = r2.y;
         }
         if (PROD) {
@@ -212,28 +250,26 @@ logit_stream_kernel(const double* __restrict__ tiles, const unsigned long long n
             const int eh = __double2hiint(ls);
             prod *= __hiloint2double((eh & 0x000fffff) | 0x3ff00000, __double2loint(ls));   // mantissa of lsum, in [1, 2)
             const int ph = __double2hiint(prod);                                              // prod in [1, 4)
-            prod_e += (long long)((eh >> 20) - 1023) + (long long)((ph >> 20) - 1023);
+            prod_e += ((eh >> 20) - 1023) + ((ph >> 20) - 1023);
             prod = __hiloint2double((ph & 0x000fffff) | 0x3ff00000, __double2loint(prod));
         } else
             ll.add(valid ? wrow * (num - (lbase + fm_log_normal(lsum))) : 0.0);
 #pragma unroll
-        for (int nb = 0; nb < 4; nb++) {           // 2 JB chains; consecutive DMMAs of a chain are 2 JB slots apart
+        for (int nb = 0; nb < 4; nb++) {           // JB chains; consecutive DMMAs of a chain are JB slots (64 cycles) apart
             double2 x2[JB];
 #pragma unroll
             for (int jb = 0; jb < JB; jb++) x2[jb] = *reinterpret_cast<const double2*>(tile + jb * 8 * TILE_ROWS + fo[nb]);
 #pragma unroll
             for (int jb = 0; jb < JB; jb++) dmma_884v(G[jb][0], G[jb][1], R[nb][0], x2[jb].x);
 #pragma unroll
-            for (int jb = 0; jb < JB; jb++) dmma_884v(G2[jb][0], G2[jb][1], R[nb][1], x2[jb].y);
+            for (int jb = 0; jb < JB; jb++) dmma_884v(G[jb][0], G[jb][1], R[nb][1], x2[jb].y);
             __syncwarp();   // scheduling fence, as in stage 1
         }
-        __syncwarp();                              // every lane is done with this stage before it is refilled
-        cur ^= 1;
+        __syncwarp();                              // every lane is done with this slot before it is refilled
+        if (t + (unsigned long long)SLOTS * ngrps < n_tiles) fill(t + (unsigned long long)SLOTS * ngrps, slot);   // item i + SLOTS: the partner's, when PAIRED
     }
 
     // ---- CTA reduction: lane (g, q) holds G^T[c = g][j = jb*8 + 2q + {0,1}]
-#pragma unroll
-    for (int jb = 0; jb < JB; jb++) { G[jb][0] += G2[jb][0]; G[jb][1] += G2[jb][1]; }
     __syncthreads();                               // the rings are free: reuse as WARPS x NOUT scratch
     if (PROD) ll.add(-((double)prod_e * 6.93147180369123816490e-01 + ((double)prod_e * 1.90821492927058770002e-10 + fm_log_normal(prod))));
     const double llw = warp_sum(ll.value());
@@ -248,7 +284,7 @@ logit_stream_kernel(const double* __restrict__ tiles, const unsigned long long n
     }
     __syncthreads();
     double* scratch = smem + WARPS * NOUT;
-    for (int v = threadIdx.x; v < NOUT; v += LOGIT_THREADS) {
+    for (int v = threadIdx.x; v < NOUT; v += THREADS) {
         double s = 0.0;
 #pragma unroll
         for (int wv = 0; wv < WARPS; wv++) s += smem[wv * NOUT + v];
@@ -257,32 +293,46 @@ logit_stream_kernel(const double* __restrict__ tiles, const unsigned long long n
     grid_finalize(partials, NOUT, ticket, out, fin, scratch);
 }
 
-template <int KB>
+template <int KB, bool PAIRED>
 static constexpr size_t stream_smem() {
-    return (size_t)(LOGIT_THREADS / 32) * (STREAM_STAGES * (KB + 1) * TILE_ROWS + 8 * TILE_ROWS) * sizeof(double);
+    using Cfg = StreamCfg<PAIRED>;
+    return (size_t)(Cfg::WARPS / Cfg::GROUP) * (Cfg::SLOTS * (KB + 1) * TILE_ROWS + Cfg::GROUP * Cfg::SLAB_ROWS * TILE_ROWS) * sizeof(double);
 }
-template <int KB, int C1>
-static cudaError_t stream_launch_one(const LogitLaunch& L, const LogitParams& prm) {
-    static_assert((size_t)(LOGIT_THREADS / 32) * (1 + KB * C1) + (1 + KB * C1) <= stream_smem<KB>() / sizeof(double), "reduction scratch must fit the rings");
+// APOP_B200_LOGIT_STREAM=quad selects the 4-warp CTAs (12 warps per SM) for A/B runs
+static bool stream_paired() {
+    static const int v = [] { const char* e = getenv("APOP_B200_LOGIT_STREAM"); return (e && !strcmp(e, "quad")) ? 0 : 1; }();
+    return v != 0;
+}
+int logit_stream_warps_per_block() { return stream_paired() ? StreamCfg<true>::WARPS : StreamCfg<false>::WARPS; }
+template <int KB, int C1, bool PAIRED>
+static cudaError_t stream_launch_p(const LogitLaunch& L, const LogitParams& prm) {
+    using Cfg = StreamCfg<PAIRED>;
+    static_assert((size_t)Cfg::WARPS * (1 + KB * C1) + (1 + KB * C1) <= stream_smem<KB, PAIRED>() / sizeof(double), "reduction scratch must fit the rings");
     static bool done = false;
     if (!done) {
-        cudaFuncSetAttribute(logit_stream_kernel<KB, C1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stream_smem<KB>());
-        cudaFuncSetAttribute(logit_stream_kernel<KB, C1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stream_smem<KB>());
+        cudaFuncSetAttribute(logit_stream_kernel<KB, C1, false, PAIRED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stream_smem<KB, PAIRED>());
+        cudaFuncSetAttribute(logit_stream_kernel<KB, C1, true, PAIRED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stream_smem<KB, PAIRED>());
         done = true;
     }
     if (L.counts)
-        logit_stream_kernel<KB, C1, true><<<L.grid, LOGIT_THREADS, stream_smem<KB>(), L.stream>>>(L.tiles, L.n_rows, L.n_tiles, L.k, L.cols, L.counts, L.m_pad, L.replicate, prm, L.partials, L.ticket, L.out, L.fin);
+        logit_stream_kernel<KB, C1, true, PAIRED><<<L.grid, Cfg::WARPS * 32, stream_smem<KB, PAIRED>(), L.stream>>>(L.tiles, L.n_rows, L.n_tiles, L.k, L.cols, L.counts, L.m_pad, L.replicate, prm, L.partials, L.ticket, L.out, L.fin);
     else
-        logit_stream_kernel<KB, C1, false><<<L.grid, LOGIT_THREADS, stream_smem<KB>(), L.stream>>>(L.tiles, L.n_rows, L.n_tiles, L.k, L.cols, nullptr, 0, 0, prm, L.partials, L.ticket, L.out, L.fin);
+        logit_stream_kernel<KB, C1, false, PAIRED><<<L.grid, Cfg::WARPS * 32, stream_smem<KB, PAIRED>(), L.stream>>>(L.tiles, L.n_rows, L.n_tiles, L.k, L.cols, nullptr, 0, 0, prm, L.partials, L.ticket, L.out, L.fin);
     return cudaGetLastError();
 }
 template <int KB, int C1>
-static int stream_bps_one() {
-    cudaFuncSetAttribute(logit_stream_kernel<KB, C1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stream_smem<KB>());
+static cudaError_t stream_launch_one(const LogitLaunch& L, const LogitParams& prm) {
+    return stream_paired() ? stream_launch_p<KB, C1, true>(L, prm) : stream_launch_p<KB, C1, false>(L, prm);
+}
+template <int KB, int C1, bool PAIRED>
+static int stream_bps_p() {
+    cudaFuncSetAttribute(logit_stream_kernel<KB, C1, false, PAIRED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stream_smem<KB, PAIRED>());
     int nb = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, logit_stream_kernel<KB, C1, false>, LOGIT_THREADS, stream_smem<KB>());
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, logit_stream_kernel<KB, C1, false, PAIRED>, StreamCfg<PAIRED>::WARPS * 32, stream_smem<KB, PAIRED>());
     return nb;
 }
+template <int KB, int C1>
+static int stream_bps_one() { return stream_paired() ? stream_bps_p<KB, C1, true>() : stream_bps_p<KB, C1, false>(); }
 
 #define APB_STREAM_C(KB)                       \
     switch (c1) {                              \
