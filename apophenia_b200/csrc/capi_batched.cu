@@ -71,6 +71,10 @@ static bool eval_logit_info(Resident* r, const double* B, size_t C1, double* H) 
     if (bps <= 0) return set_error("multinomial information kernel unavailable for k=%d, C=%zu", K, C1 + 1);
     const int KB = logit_kb(K), NOUT = LOGIT_INFO_NP * KB * KB;
     const size_t P = (size_t)K * C1;
+    // the information follows a multinomial fit, whose kernel keeps the tiles swizzled; the bulk-copy form of the
+    // information kernel reads that layout (APOP_B200_INFO_PLAIN=1: convert back and take the cp.async form, for A/B runs)
+    static const bool plain = getenv("APOP_B200_INFO_PLAIN") != nullptr;
+    if (!ensure_layout(r, !plain)) return false;
     LogitParams prm;
     memset(&prm, 0, sizeof prm);
     memcpy(prm.B, B, P * sizeof(double));

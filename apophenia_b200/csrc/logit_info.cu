@@ -28,7 +28,11 @@ __device__ __forceinline__ void dmma_info(double& d0, double& d1, double a, doub
 }
 constexpr int INFO_CS = 36;   // padded column stride of a staged tile (doubles)
 
-template <int KB, int C1>
+// BULK: the resident tiles are in the swizzled form (layout.cu) and arrive by one TMA bulk copy per tile into a
+// two-slot ring per warp, the next tile in flight while this one is contracted; the swizzle makes the 8-byte fragment
+// loads below conflict free without padding (the four columns g = 0..3 of a half-warp land in different quarters of a
+// bank row).  Otherwise (plain tiles): 16-byte cp.async into a padded buffer, no overlap inside the warp.
+template <int KB, int C1, bool BULK>
 __global__ void __launch_bounds__(LOGIT_INFO_THREADS, 2)
 logit_info_kernel(const double* __restrict__ tiles, const unsigned long long n_rows, const unsigned long long n_tiles,
                   const int K, const int cols, const int swz, const __grid_constant__ LogitParams prm, const __grid_constant__ LogitInfoPairs pairs,
@@ -39,14 +43,16 @@ logit_info_kernel(const double* __restrict__ tiles, const unsigned long long n_r
     constexpr int JB = KB / 8;
     constexpr int NTRI = JB * (JB + 1) / 2;
     constexpr int NOUT = NP * KB * KB;
-    constexpr int TILE_D = KB * INFO_CS;           // X only: the information does not depend on the outcomes
+    constexpr int CS = BULK ? TILE_ROWS : INFO_CS;                       // column stride of a staged tile
+    constexpr int NSLOT = BULK ? 2 : 1;
+    constexpr int TILE_D = BULK ? (KB + 1) * TILE_ROWS : KB * INFO_CS;   // bulk: X and y as resident; else X only
     extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, q = lane & 3;
     const unsigned long long gwarp = (unsigned long long)blockIdx.x * WARPS + warp;
     const unsigned long long nwarps = (unsigned long long)gridDim.x * WARPS;
-    double* tile = smem + warp * (TILE_D + NP * 32 + 8 * 32);
-    double* wbuf = tile + TILE_D;
+    double* ring = smem + warp * (NSLOT * TILE_D + NP * 32 + 8 * 32);
+    double* wbuf = ring + NSLOT * TILE_D;
     double* pbuf = wbuf + NP * 32;                 // p[c][row]: the pair weights pick their two categories by address
 
     double acc[NP][NTRI][2];
@@ -54,12 +60,40 @@ logit_info_kernel(const double* __restrict__ tiles, const unsigned long long n_r
     for (int i = 0; i < NP; i++)
 #pragma unroll
         for (int b = 0; b < NTRI; b++) acc[i][b][0] = acc[i][b][1] = 0.0;
-    // columns K..KB-1 are never staged: zero them once
-    for (int i = lane; i < TILE_D; i += 32) tile[i] = 0.0;
+    // columns K..KB-1 are never staged (bulk: K+1..KB; column K receives y and contracts into entries nobody reads): zero them once
+    for (int i = lane; i < NSLOT * TILE_D; i += 32)
+        if (!BULK || (i % TILE_D) / TILE_ROWS > K) ring[i] = 0.0;
+    __shared__ __align__(8) unsigned long long bars[WARPS * 2];
+    if (BULK) {
+        if (lane < 2) mbar_init(bars + warp * 2 + lane, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncwarp();
+    const unsigned bar_u32 = smem_u32(bars + warp * 2), ring_u32 = smem_u32(ring);
+    const unsigned tile_bytes = (unsigned)(K + 1) * TILE_ROWS * sizeof(double);
+    auto fill = [&](unsigned long long tt, int slot) {
+        if (lane == 0) {
+            const unsigned bar = bar_u32 + slot * 8, dst = ring_u32 + slot * (TILE_D * 8);
+            const double* src = tiles + tt * (unsigned long long)(cols * TILE_ROWS);
+            fence_proxy_async();
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(tile_bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(dst), "l"(src), "r"(tile_bytes), "r"(bar) : "memory");
+        }
+    };
+    // swizzled positions: row r of column j at j*32 + (r ^ rx(j)), rx(j) = 8 (j & 1) + 4 ((j >> 1) & 1); rx(.. + g) = rxg
+    const int rxg = BULK ? (((g & 1) << 3) | ((g & 2) << 1)) : 0;
 
-    for (unsigned long long t = gwarp; t < n_tiles; t += nwarps) {
-        {   // stage the K columns of X: 16-byte chunk `lane + 32 i` lies in resident column (lane >> 4) + 2 i
+    unsigned it = 0;
+    if (BULK && gwarp < n_tiles) fill(gwarp, 0);
+    for (unsigned long long t = gwarp; t < n_tiles; t += nwarps, it++) {
+        double* tile = ring + (BULK ? (int)(it & 1u) : 0) * TILE_D;
+        if (BULK) {
+            if (t + nwarps < n_tiles) fill(t + nwarps, (int)((it + 1) & 1u));   // that slot was consumed in the last iteration
+            const unsigned bar = bar_u32 + (it & 1u) * 8, parity = (it >> 1) & 1u;
+            asm volatile("{\n\t.reg .pred p;\n\tWAIT_TILE:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra TILE_READY;\n\tbra WAIT_TILE;\n\tTILE_READY:\n\t}"
+                         ::"r"(bar), "r"(parity) : "memory");
+        } else {   // stage the K columns of X: 16-byte chunk `lane + 32 i` lies in resident column (lane >> 4) + 2 i
             const double* src = tiles + t * (unsigned long long)(cols * TILE_ROWS) + lane * 2;
             // (swizzled resident form, layout.cu: chunk c of column j holds the rows of chunk c ^ sw(j) -- undone on the
             // way in; the column of copy i is (lane >> 4) + 2 i, so sw = ((lane >> 4) << 2) | ((i & 1) << 1))
@@ -83,7 +117,7 @@ logit_info_kernel(const double* __restrict__ tiles, const unsigned long long n_r
             for (int c = 0; c < C1; c++) xb[c] = 0.0;
 #pragma unroll
             for (int j = 0; j < KB; j++) {
-                const double x = tile[j * INFO_CS + lane];
+                const double x = tile[j * CS + (BULK ? (lane ^ (((j & 1) << 3) | ((j & 2) << 1))) : lane)];
 #pragma unroll
                 for (int c = 0; c < C1; c++) xb[c] = fma(x, prm.B[j * C1 + c], xb[c]);
             }
@@ -111,7 +145,7 @@ logit_info_kernel(const double* __restrict__ tiles, const unsigned long long n_r
         for (int ks = 0; ks < 8; ks++) {
             double xf[JB];
 #pragma unroll
-            for (int jb = 0; jb < JB; jb++) xf[jb] = tile[(jb * 8 + g) * INFO_CS + ks * 4 + q];
+            for (int jb = 0; jb < JB; jb++) xf[jb] = tile[(jb * 8 + g) * CS + ((ks * 4 + q) ^ rxg)];
 #pragma unroll
             for (int i = 0; i < NP; i++) {
                 const double wv = wbuf[i * 32 + ks * 4 + q];
@@ -156,26 +190,33 @@ logit_info_kernel(const double* __restrict__ tiles, const unsigned long long n_r
     grid_finalize(partials, NOUT, ticket, out, fin, red);
 }
 
-template <int KB>
+template <int KB, bool BULK>
 static constexpr size_t info_smem() {
-    const size_t ring = (size_t)(LOGIT_INFO_THREADS / 32) * (KB * INFO_CS + LOGIT_INFO_NP * 32 + 8 * 32) * sizeof(double);
+    const size_t ring = (size_t)(LOGIT_INFO_THREADS / 32) * ((BULK ? 2 * (KB + 1) * TILE_ROWS : KB * INFO_CS) + LOGIT_INFO_NP * 32 + 8 * 32) * sizeof(double);
     const size_t red = (size_t)LOGIT_INFO_NP * KB * KB * sizeof(double);
     return ring > red ? ring : red;
 }
+template <int KB, int C1, bool BULK>
+static cudaError_t info_launch_b(const LogitLaunch& L, const LogitParams& prm, const LogitInfoPairs& pairs) {
+    static bool done = false;
+    if (!done) { cudaFuncSetAttribute(logit_info_kernel<KB, C1, BULK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)info_smem<KB, BULK>()); done = true; }
+    logit_info_kernel<KB, C1, BULK><<<L.grid, LOGIT_INFO_THREADS, info_smem<KB, BULK>(), L.stream>>>(L.tiles, L.n_rows, L.n_tiles, L.k, L.cols, L.swz, prm, pairs,
+                                                                                                 L.partials, L.ticket, L.out, L.fin);
+    return cudaGetLastError();
+}
+// swizzled tiles take the bulk-copy ring, plain tiles the cp.async form
 template <int KB, int C1>
 static cudaError_t info_launch_one(const LogitLaunch& L, const LogitParams& prm, const LogitInfoPairs& pairs) {
-    static bool done = false;
-    if (!done) { cudaFuncSetAttribute(logit_info_kernel<KB, C1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)info_smem<KB>()); done = true; }
-    logit_info_kernel<KB, C1><<<L.grid, LOGIT_INFO_THREADS, info_smem<KB>(), L.stream>>>(L.tiles, L.n_rows, L.n_tiles, L.k, L.cols, L.swz, prm, pairs,
-                                                                                      L.partials, L.ticket, L.out, L.fin);
-    return cudaGetLastError();
+    return L.swz ? info_launch_b<KB, C1, true>(L, prm, pairs) : info_launch_b<KB, C1, false>(L, prm, pairs);
 }
 template <int KB, int C1>
 static int info_bps_one() {
-    cudaFuncSetAttribute(logit_info_kernel<KB, C1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)info_smem<KB>());
-    int nb = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, logit_info_kernel<KB, C1>, LOGIT_INFO_THREADS, info_smem<KB>());
-    return nb;
+    int nb = 0, nb2 = 0;
+    cudaFuncSetAttribute(logit_info_kernel<KB, C1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)info_smem<KB, true>());
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, logit_info_kernel<KB, C1, true>, LOGIT_INFO_THREADS, info_smem<KB, true>());
+    cudaFuncSetAttribute(logit_info_kernel<KB, C1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)info_smem<KB, false>());
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb2, logit_info_kernel<KB, C1, false>, LOGIT_INFO_THREADS, info_smem<KB, false>());
+    return nb < nb2 ? nb : nb2;
 }
 
 #define APB_INFO_C(KB)                         \
