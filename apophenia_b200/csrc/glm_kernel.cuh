@@ -135,7 +135,7 @@ struct GlmTable<Fam, HAS_W, 0> {
 constexpr int GLM_WIDE_MAX_K = 1024;
 cudaError_t glm_wide_launch(GlmFam fam, int k, int cols, bool has_w, const GlmLaunch& L, const double* beta, const double* aux);
 int glm_wide_blocks_per_sm(GlmFam fam, int k);
-int glm_wide_tiles_per_block(int k);   // 1 for the cooperative variant (k <= 256), else warps per block
+int glm_wide_tiles_per_block(int k);   // tiles a CTA works on at a time (1: all its warps share a tile)
 
 // defined in glm_<family>.cu
 cudaError_t glm_launch(GlmFam fam, int k, bool has_w, const GlmLaunch& L, const GlmParams& prm);

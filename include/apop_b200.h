@@ -219,7 +219,7 @@ int apop_b200_download(const apop_data *d, double *X_rowmajor, double *y, double
 /* ------------------------------------------------------------------ *
  *  The path: log likelihood and score, reference signatures
  *  Column counts: probit / binary logit / Poisson regression / OLS take 1..1024 columns
- *  (1..32 on the register-resident kernels, wider data on a two-sweep kernel);
+ *  (1..48 on the register-resident kernel, wider data on a kernel whose lanes tile rows x columns);
  *  multinomial logit, the information matrix and the batched path take 1..32 and up to
  *  8 outcome categories.  Anything else is refused with NaN and model->error = 'd'.
  *  A weights column is read by OLS only; probit, logit and the Poisson regression ignore it,

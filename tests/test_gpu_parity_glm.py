@@ -399,10 +399,12 @@ def test_empty_and_too_wide_inputs(b200):
 
 @pytest.mark.parametrize("fam,n,k", [("probit", 20011, 40), ("probit", 5000, 33), ("logit", 9000, 64), ("poisson_reg", 6000, 100),
                                      ("ols", 7000, 48), ("probit", 3000, 257), ("probit", 4001, 129), ("logit", 3000, 160),
-                                     ("poisson_reg", 2500, 200), ("ols", 3001, 225), ("probit", 2000, 256), ("logit", 2000, 700)])
+                                     ("poisson_reg", 2500, 200), ("ols", 3001, 225), ("probit", 2000, 256), ("logit", 2000, 700),
+                                     ("logit", 4001, 49), ("probit", 1500, 513), ("poisson_reg", 1200, 1024), ("ols", 2001, 1000),
+                                     ("probit", 31, 300), ("ols", 45, 520), ("probit", 1999, 768)])
 def test_wide_data_beyond_32_columns(b200, oracle, fam, n, k):
-    """k > 32: the cooperative kernel (one CTA of ceil(k/32) warps per tile, k <= 256) and the two-sweep
-    kernel beyond (glm_wide.cu); same parity bar"""
+    """k > 32: the register-resident kernel to k = 48, then glm_wide.cu (the lanes of a warp tile a rows x columns
+    patch: whole tiles to k = 256, half tiles in CTAs of up to 8 warps to 512 and up to 16 warps to 1024); same parity bar"""
     ab = b200
     rng = np.random.default_rng(n + k)
     X = rng.uniform(-1, 1, (n, k)); X[:, 0] = 1

@@ -140,6 +140,22 @@ def cfg_logit8_fit(rows=20_000_000, k=32, C=8):
     return out
 
 
+def cfg_logit8_info(rows=20_000_000, k=32, C=8):
+    """the P x P observed information of the multinomial logit (BASELINE config 2), all launches of one evaluation"""
+    rng = np.random.default_rng(8)
+    B = rng.uniform(-1, 1, k * (C - 1))
+    s = ab.synth(ab.LOGIT, rows, k, B, ncat=C)
+    ab.information(ab.LOGIT, s, B)
+    t0 = time.perf_counter()
+    for i in range(3):
+        ab.information(ab.LOGIT, s, B * (1 + 1e-6 * (i + 1)))
+    dt = (time.perf_counter() - t0) / 3
+    s.free()
+    P = k * (C - 1)
+    return {"config": f"multinomial logit information, C={C}, {rows}x{k}, P={P}", "ms_per_information": 1e3 * dt,
+            "dmma_TFLOPs": 2.0 * rows * (C - 1) * C / 2 * (k * (k + 8) / 2) / dt / 1e12}
+
+
 def cfg_bootstrap_cov(rows=5_000_000, k=20, m=1000):
     """BASELINE config 4 end to end: apop_bootstrap_cov of a probit fit (counts + lock-step replicate fits)"""
     from apophenia_b200 import host
@@ -274,7 +290,7 @@ def cfg_ingest(rows=2_000_000, k=16):
             "speedup_vs_pandas_plus_pin": (t_pandas + t_pin) / t_dev, "identical": ok}
 
 
-ALL = {"logit8_fit": cfg_logit8_fit, "ingest": cfg_ingest, "prep": cfg_prep, "config1": cfg_config1, "bootstrap_cov": cfg_bootstrap_cov, "metropolis": cfg_metropolis, "logit8": cfg_logit8, "bootstrap": cfg_bootstrap, "chains": cfg_chains, "poisson": cfg_poisson, "newton": cfg_newton}
+ALL = {"logit8_fit": cfg_logit8_fit, "logit8_info": cfg_logit8_info, "ingest": cfg_ingest, "prep": cfg_prep, "config1": cfg_config1, "bootstrap_cov": cfg_bootstrap_cov, "metropolis": cfg_metropolis, "logit8": cfg_logit8, "bootstrap": cfg_bootstrap, "chains": cfg_chains, "poisson": cfg_poisson, "newton": cfg_newton}
 
 if __name__ == "__main__":
     ab.init(0)

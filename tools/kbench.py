@@ -57,14 +57,23 @@ def probit(rows=100_000_000, k=32):
     print(f"probit {rows}x{k}: step {dt:.4f} ms kernel {km:.4f} ms = {rows * (k + 1) * 8 / km / 1e6:.0f} GB/s", flush=True)
 
 def wide(k, rows=None):
-    rows = rows or int(5.2e9 / ((k + 1) * 8))
     rng = np.random.default_rng(8); beta = rng.uniform(-1, 1, k) / np.sqrt(k / 32)
-    w = ab.synth(ab.PROBIT, 10007, k, beta); X, y = w.download(); ll, g = ab.ll_score(ab.PROBIT, w, beta); w.free()
+    def make(n):
+        if k <= 480: return ab.synth(ab.PROBIT, n, k, beta), None
+        X = rng.random((n, k)) * 2 - 1; X[:, 0] = 1   # the data generator stops at 480 parameters: host data, pinned
+        y = (rng.standard_normal(n) > -(X @ beta)).astype(float)
+        d = ab.pin(ab.Data(matrix=X, vector=y))
+        return d, (X, y)
+    w, h = make(10007)
+    X, y = h if h else w.download()
+    ll, g = ab.ll_score(ab.PROBIT, w, beta)
+    w.free() if h is None else ab.unpin(w)
     want = o.probit_ll(X, y, beta, o.EXACT); ge, sc = o.probit_score(X, y, beta, o.EXACT)
     e1 = abs(ll - float(want)) / abs(float(want)); e2 = float(np.max(np.abs(g - ge.astype(float)) / sc.astype(float)))
-    s = ab.synth(ab.PROBIT, rows, k, beta)
+    rows = rows or int((5.2e9 if k <= 480 else 2.0e9) / ((k + 1) * 8))
+    s, h = make(rows)
     dt, km = timed(lambda i: ab.ll_score(ab.PROBIT, s, beta * (1 + 1e-6 * (i + 1))))
-    s.free()
+    s.free() if h is None else ab.unpin(s)
     print(f"probit wide {rows}x{k}: step {dt:.4f} ms kernel {km:.4f} ms = {rows * (k + 1) * 8 / km / 1e6:.0f} GB/s; parity ll {e1:.1e} score {e2:.1e}", flush=True)
 
 def info8(rows=20_000_000, k=32, C=8):
