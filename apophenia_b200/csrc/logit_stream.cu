@@ -1,7 +1,7 @@
 // logit_stream.cu -- multinomial logit, default kernel: one TMA bulk copy per tile, both contractions on the
 // FP64 MMA path, the soft-max lane = row in between.
 //
-// What the cp.async kernel of logit_hybrid.cu spends its time on (ncu source view, profiles/r03_*): 30 % of a
+// What the cp.async kernel of logit_hybrid.cu spends its time on (ncu source view, profiles/r02_ncu_logit8_source_sass_top.csv): 30 % of a
 // warp's cycles go to issuing the 17 LDGSTS of a tile and their column tests, and stage 1 needs ~430
 // instructions (224 DFMA, 112 uniform loads of B, 33 shared loads).  Neither is arithmetic.  Here
 //   prefetch  ONE cp.async.bulk (UBLKCP) per tile, issued by one lane and completing on an mbarrier: the
