@@ -194,7 +194,7 @@ batched_taylor_kernel(const double* __restrict__ tiles, const unsigned long long
                       const double delta_max, unsigned long long* __restrict__ exact_slots) {
     constexpr int WARPS = BATCH_THREADS / 32;
     constexpr int KS = KB / 4, JB = KB / 8;
-    constexpr int NC = WANT_SCORE ? 13 : 8;     // x0, a0..a6 [, 2 a2, 3 a3, 4 a4, 5 a5, 6 a6]
+    constexpr int NC = 8;                       // x0, a0..a6 (the derivative comes out of the same Horner recurrence)
     constexpr int CS = BATCH_TILE_CS;           // padded column stride of a staged tile: both fragment patterns conflict free
     extern __shared__ __align__(16) double dsm[];
     typedef double (*SlabT)[NC][TILE_ROWS];
@@ -256,10 +256,6 @@ batched_taylor_kernel(const double* __restrict__ tiles, const unsigned long long
                 slab[warp][0][lane] = ok ? x0 : __longlong_as_double(0x7ff8000000000000ll);   // NaN: every pair of the row goes exact
 #pragma unroll
                 for (int n = 0; n <= TAYLOR_D; n++) slab[warp][1 + n][lane] = a[n];
-                if (WANT_SCORE) {
-#pragma unroll
-                    for (int n = 2; n <= TAYLOR_D; n++) slab[warp][6 + n][lane] = (double)n * a[n];
-                }
             }
         }
         __syncthreads();
@@ -298,20 +294,21 @@ batched_taylor_kernel(const double* __restrict__ tiles, const unsigned long long
 #define APB_C(n) (e ? c[n].y : c[n].x)
                     const double xb = S[nb][e];
                     const double dl = xb - APB_C(0);
+                    // Horner for the polynomial and, from the same partial results, for its derivative
+                    // (dv_k = dv_{k-1} dl + p_k): 11 FMA as two separate recurrences would take, without the
+                    // five extra coefficients n a_n to read back per row
                     double llv = fma(dl, APB_C(7), APB_C(6));
+                    double dv = APB_C(7);
+                    if (WANT_SCORE) dv = fma(dl, dv, llv);
                     llv = fma(dl, llv, APB_C(5));
+                    if (WANT_SCORE) dv = fma(dl, dv, llv);
                     llv = fma(dl, llv, APB_C(4));
+                    if (WANT_SCORE) dv = fma(dl, dv, llv);
                     llv = fma(dl, llv, APB_C(3));
+                    if (WANT_SCORE) dv = fma(dl, dv, llv);
                     llv = fma(dl, llv, APB_C(2));
+                    if (WANT_SCORE) dv = fma(dl, dv, llv);
                     llv = fma(dl, llv, APB_C(1));
-                    double dv = 0.0;
-                    if (WANT_SCORE) {
-                        dv = fma(dl, APB_C(12), APB_C(11));
-                        dv = fma(dl, dv, APB_C(10));
-                        dv = fma(dl, dv, APB_C(9));
-                        dv = fma(dl, dv, APB_C(8));
-                        dv = fma(dl, dv, APB_C(2));
-                    }
 #undef APB_C
                     // outside the radius (also: the NaN of a row outside the Taylor range): the exact evaluation.  The
                     // branch is taken by the whole warp (Fam::eval votes warp-wide for its fast exponential), each
@@ -420,7 +417,7 @@ template <int KB, class Fam>
 static cudaError_t launch_fam(const BatchedLaunch& L) {
     const double4 aux = make_double4(L.aux[0], L.aux[1], L.aux[2], L.aux[3]);
     if (L.centre) {
-        const size_t tsm = (size_t)(BATCH_THREADS / 32) * ((L.want_score ? 13 : 8) * TILE_ROWS + (size_t)(L.k + 1) * BATCH_TILE_CS) * sizeof(double);
+        const size_t tsm = (size_t)(BATCH_THREADS / 32) * (8 * TILE_ROWS + (size_t)(L.k + 1) * BATCH_TILE_CS) * sizeof(double);
 #define APB_TGO(S, C) do { cudaFuncSetAttribute(batched_taylor_kernel<KB, Fam, S, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm); \
         batched_taylor_kernel<KB, Fam, S, C><<<L.grid, BATCH_THREADS, tsm, L.stream>>>(L.tiles, L.n_rows, L.n_tiles, L.k, L.cols, \
         L.B, L.P, L.m, L.counts, L.m_pad, aux, L.n_rowgroups, L.partials, L.centre, L.delta_max, L.exact_slots); } while (0)

@@ -12,9 +12,10 @@
 //   * x.beta: 4 partial sums per lane, a butterfly reduce-scatter over the lanes of different columns
 //     (3-4 shuffle-adds), then one shared-memory exchange between the warps (one barrier per step,
 //     ping-pong buffers);
-//   * lanes 0..RH-1 of EVERY warp evaluate the family for their row (redundant across warps: ~100 issue
-//     slots against the 64 DFMA of the step, well under the HBM time of RH x k x 8 bytes) and hand the
-//     four d_i a lane needs back by shuffle;
+//   * EVERY warp evaluates the family for the RH rows of the step, lane and lane + RH on the same row
+//     (redundant: ~100 issue slots against the 64 DFMA of the step, well under the HBM time of
+//     RH x k x 8 bytes; all 32 lanes take part because Fam::eval votes warp-wide) and hands the four d_i
+//     a lane needs back by shuffle;
 //   * the score accumulators are 8 registers per lane (its columns, its rows), summed over the LPC lanes
 //     of a column once, at the end.
 // HBM traffic is 8(k+1) bytes per row, nothing is read twice, nothing is transposed through shared memory.
@@ -77,11 +78,11 @@ glm_cols_kernel(const double* __restrict__ tiles, const unsigned long long n_row
                 if (j < nown) ld_stream_v4(cp + (size_t)j * CPI * TILE_ROWS, x[j][0], x[j][1], x[j][2], x[j][3]);
                 else x[j][0] = x[j][1] = x[j][2] = x[j][3] = 0.0;
             }
-            double y = 0.0, w = 1.0;
-            if (lane < RH) {
-                y = ld_stream(tb + (size_t)K * TILE_ROWS + r0 + lane);
-                if (has_w) w = ld_stream(tb + (size_t)(K + 1) * TILE_ROWS + r0 + lane);
-            }
+            // every lane takes part in the family evaluation (Fam::eval votes warp-wide): lane and lane + RH both
+            // work on row lane of the step, the copy's sums are dropped
+            const int er = lane & (RH - 1);
+            const double y = ld_stream(tb + (size_t)K * TILE_ROWS + r0 + er);
+            const double w = has_w ? ld_stream(tb + (size_t)(K + 1) * TILE_ROWS + r0 + er) : 1.0;
             // partial x.beta over this lane's columns, for its 4 rows
             double p[4];
 #pragma unroll
@@ -103,18 +104,15 @@ glm_cols_kernel(const double* __restrict__ tiles, const unsigned long long n_row
             }
             if (publisher) part[(pp * NW + warp) * RH + myrow] = p[0];
             __syncthreads();
-            double d = 0.0;
-            if (lane < RH) {
-                double xb = 0.0;
-                for (int wv = 0; wv < NW; wv++) xb += part[(pp * NW + wv) * RH + lane];   // fixed order: the same x.beta in every warp
-                RowOut o = Fam::eval(xb, y, w, aux);
-                const bool valid = t * TILE_ROWS + r0 + lane < n_rows;
-                if (warp == 0) {
+            double xb = 0.0;
+            for (int wv = 0; wv < NW; wv++) xb += part[(pp * NW + wv) * RH + er];   // fixed order: the same x.beta in every warp
+            const RowOut o = Fam::eval(xb, y, w, aux);
+            const bool valid = t * TILE_ROWS + r0 + er < n_rows;
+            if (warp == 0) {
 #pragma unroll
-                    for (int a = 0; a < Fam::NACC; a++) acc[a].add(valid ? o.s[a] : 0.0);
-                }
-                d = valid ? o.d : 0.0;
+                for (int a = 0; a < Fam::NACC; a++) acc[a].add(valid && lane < RH ? o.s[a] : 0.0);
             }
+            const double d = valid ? o.d : 0.0;
             pp ^= 1;
 #pragma unroll
             for (int i = 0; i < 4; i++) {
