@@ -14,6 +14,9 @@ KERNELS = [
     ("batched_kernel.o", r"batched_taylor_kernelILi24ENS_9FamProbitELb1ELb1E", "batched_taylor_kernel_k24_probit_score_counts"),
     ("batched_kernel.o", r"batched_kernelILi24ENS_9FamProbitELb1ELb1ELi1E", "batched_kernel_k24_probit_score_counts_exact"),
     ("logit_info.o", r"logit_info_kernelILi32ELi7E", "logit_info_kernel_k32_c8"),
+    ("logit_stream.o", r"logit_stream_kernelILi32ELi7ELb0ELb1E", "logit_stream_kernel_k32_c8_paired"),
+    ("glm_wide.o", r"glm_cols_kernelILi32ELb0ENS_9FamProbitE", "glm_cols_kernel_rh32_probit"),
+    ("glm_wide.o", r"glm_cols_kernelILi16ELb1ENS_9FamProbitE", "glm_cols_kernel_rh16_big_probit"),
 ]
 os.makedirs(OUT, exist_ok=True)
 for obj, pat, name in KERNELS:
