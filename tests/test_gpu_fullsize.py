@@ -7,7 +7,7 @@ replicates against single passes."""
 import numpy as np
 import pytest
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900)]   # full-size passes + oracle passes on the host cores
 
 
 def _additive(ab, fam, n, k, beta, ncat=2, rtol=1e-12):

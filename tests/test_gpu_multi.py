@@ -16,6 +16,7 @@ def _gpus():
     return torch.cuda.device_count()
 
 
+@pytest.mark.timeout(700)      # the subprocess has its own 600 s limit
 @pytest.mark.parametrize("mode", ["p2p", "nccl"])
 def test_two_rank_parity(mode):
     if _gpus() < 2:
