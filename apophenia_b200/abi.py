@@ -147,6 +147,8 @@ SIGNATURES = {
     "apop_b200_poisson_reg_score": (None, [_PD, _PV, _PM]),
     "apop_b200_text_to_resident": (_PD, [C.c_char_p, C.c_int, C.c_int, C.c_char_p, C.c_int]),
     "apop_b200_text_to_host": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_char_p, C.POINTER(_dp), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+    "apop_b200_text_to_resident_fixed": (_PD, [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int, C.c_int]),
+    "apop_b200_text_to_host_fixed": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int, C.POINTER(_dp), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "apop_b200_prep_outcome": (C.c_int, [_PD, _dp, C.c_size_t, C.POINTER(C.c_size_t), _dp, C.c_int]),
     "apop_b200_logit_expected": (C.c_int, [_PD, _PM, _dp, _dp]),
     "apop_b200_map_sum": (C.c_double, [_PD, C.c_int, C.c_double, C.c_char]),

@@ -242,12 +242,18 @@ def probit_start(d, k):
     return out
 
 
-def text_to_host(path, has_row_names=False, has_col_names=True, delimiters=None):
-    """apop_text_to_data's matrix for a numeric file, parsed by the library's multi-threaded reader"""
+def text_to_host(path, has_row_names=False, has_col_names=True, delimiters=None, field_ends=None):
+    """apop_text_to_data's matrix for a numeric file, parsed by the library's multi-threaded reader;
+    field_ends (1-based end positions) selects the fixed-width layout"""
     out = _dp(); n = C.c_size_t(0); k = C.c_size_t(0)
-    abi.check(_lib().apop_b200_text_to_host(str(path).encode(), int(has_row_names), int(has_col_names),
-                                            delimiters.encode() if delimiters else None, C.byref(out), C.byref(n), C.byref(k)),
-              "apop_b200_text_to_host")
+    if field_ends is not None:
+        fe = (C.c_int * len(field_ends))(*[int(v) for v in field_ends])
+        abi.check(_lib().apop_b200_text_to_host_fixed(str(path).encode(), int(has_row_names), int(has_col_names), fe, len(field_ends),
+                                                      C.byref(out), C.byref(n), C.byref(k)), "apop_b200_text_to_host_fixed")
+    else:
+        abi.check(_lib().apop_b200_text_to_host(str(path).encode(), int(has_row_names), int(has_col_names),
+                                                delimiters.encode() if delimiters else None, C.byref(out), C.byref(n), C.byref(k)),
+                  "apop_b200_text_to_host")
     a = np.ctypeslib.as_array(out, shape=(n.value, k.value)).copy() if n.value else np.zeros((0, k.value))
     C.CDLL(None).free(out)
     return a
@@ -377,9 +383,14 @@ def synth(family, n_rows, k, beta_true, ncat=2, seed=8, row_offset=0):
 class TextData(SynthData):
     """A numeric text file ingested straight into the resident layout (apop_b200_text_to_resident)."""
 
-    def __init__(self, path, has_row_names=False, has_col_names=True, delimiters=None, outcome_col0=False):
-        self._p = _lib().apop_b200_text_to_resident(str(path).encode(), int(has_row_names), int(has_col_names),
-                                                    delimiters.encode() if delimiters else None, int(outcome_col0))
+    def __init__(self, path, has_row_names=False, has_col_names=True, delimiters=None, outcome_col0=False, field_ends=None):
+        if field_ends is not None:
+            fe = (C.c_int * len(field_ends))(*[int(v) for v in field_ends])
+            self._p = _lib().apop_b200_text_to_resident_fixed(str(path).encode(), int(has_row_names), int(has_col_names), fe,
+                                                              len(field_ends), int(outcome_col0))
+        else:
+            self._p = _lib().apop_b200_text_to_resident(str(path).encode(), int(has_row_names), int(has_col_names),
+                                                        delimiters.encode() if delimiters else None, int(outcome_col0))
         if not self._p:
             raise B200Error("apop_b200_text_to_resident failed: " + abi.last_error())
         m = self._p.contents.matrix.contents
@@ -387,8 +398,8 @@ class TextData(SynthData):
         self.family, self.ncat = None, 0
 
 
-def text_to_resident(path, has_row_names=False, has_col_names=True, delimiters=None, outcome_col0=False):
-    return TextData(path, has_row_names, has_col_names, delimiters, outcome_col0)
+def text_to_resident(path, has_row_names=False, has_col_names=True, delimiters=None, outcome_col0=False, field_ends=None):
+    return TextData(path, has_row_names, has_col_names, delimiters, outcome_col0, field_ends)
 
 
 # ---- multi-GPU plumbing: torch.distributed carries the NCCL id ----------------------

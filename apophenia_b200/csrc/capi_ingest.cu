@@ -12,10 +12,12 @@
 // delimiter set (default "|,\t"), '#' comments, blank lines, white space and NULs around fields,
 // an optional line of column names and an optional leading row-name field (both skipped: names
 // do not reach the device), a missing value (NaN) for an empty field unless the delimiter that
-// closes it is a space or a tab, text fields read as 0, C number syntax through strtod
-// (inf, nan, hex floats) with a fast exact path for plain decimals, quoted fields ("..." read verbatim, the
-// marks stripped) and backslash escapes.  Fixed-width layouts (.field_ends) are refused (NULL + message): use the
-// reference's reader there.
+// closes it is a space or a tab, C number syntax through strtod (inf, nan, hex floats; a leading number
+// followed by other characters converts, as strtod does) with a fast exact path for plain decimals, NaN for a
+// field strtod cannot convert -- what the reference's CODE does (apop_conversions.m4.c:659-666, "trouble
+// converting data item ...; writing NaN"); its format page still says text is "taken as zeros" (:363) --
+// quoted fields ("..." read verbatim, the marks stripped) and backslash escapes.  Fixed-width layouts
+// (.field_ends, parse_a_fixed_line, apop_conversions.m4.c:434-464) through the _fixed entry points.
 #include "capi_internal.cuh"
 #include "host_pool.h"
 #include <fcntl.h>
@@ -32,6 +34,8 @@ namespace {
 struct TextRules {
     bool delim[256];
     bool has_row_names;
+    const int* field_ends = nullptr;    // fixed-width layout: 1-based position of the last character of each field
+    int n_ends = 0;
 };
 inline bool is_blank(unsigned char c) { return c == ' ' || c == '\t' || c == '\r' || c == '\0' || c == '\v' || c == '\f'; }
 
@@ -39,7 +43,7 @@ inline bool is_blank(unsigned char c) { return c == ' ' || c == '\t' || c == '\r
 // |exponent| <= 22 is one correctly rounded multiplication or division of two exact doubles
 const double P10[23] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
 
-// one field [b, e) (already trimmed, not empty) -> double; text reads as 0 (the reference's rule)
+// one field [b, e) (already trimmed, not empty) -> double; NaN when strtod converts nothing (apop_conversions.m4.c:659-666)
 double field_value(const char* b, const char* e) {
     const char* p = b;
     bool neg = false;
@@ -80,7 +84,7 @@ double field_value(const char* b, const char* e) {
     const double v = strtod(s, &end);
     const bool converted = end != s;
     if (heap) free(heap);
-    return converted ? v : 0.0;     // text fields are taken as zeros
+    return converted ? v : NAN;     // "trouble converting data item ...; writing NaN"
 }
 
 // A line that uses quotes or backslashes (apop_conversions.m4.c:352-358): the character after a backslash is an
@@ -103,7 +107,7 @@ long parse_line_quoted(const char* p, const char* eol, const TextRules& R, doubl
         if (!(empty && closed_by_space)) {
             if (skip_first) skip_first = false;
             else {
-                if (out && n < max_fields) out[n] = empty ? NAN : ((b == e) ? 0.0 : field_value(cur.data() + b, cur.data() + e));
+                if (out && n < max_fields) out[n] = (b == e) ? NAN : field_value(cur.data() + b, cur.data() + e);   // "" has length 0: NaN
                 n++;
             }
         }
@@ -139,9 +143,39 @@ long parse_line_quoted(const char* p, const char* eol, const TextRules& R, doubl
     return n;
 }
 
+// A line of a fixed-width file (parse_a_fixed_line, apop_conversions.m4.c:434-464): every character up to the
+// newline belongs to a field -- no comments, quotes or delimiters -- field i ends with the character at position
+// field_ends[i] (1-based), and what follows the last given end is one more field.  A line without characters is
+// blank.  Each field then goes through the same conversion as any other (:655-666): strtod skips leading white
+// space, an empty or unconvertible field is NaN.
+long parse_line_fixed(const char* p, const char* eol, const TextRules& R, double* out, long max_fields) {
+    if (p == eol) return 0;
+    long n = 0;
+    bool skip_first = R.has_row_names;
+    const char* f = p;
+    for (int i = 0; f < eol; i++) {
+        const char* g = (i < R.n_ends && p + R.field_ends[i] < eol) ? p + R.field_ends[i] : eol;
+        if (g <= f) {                                   // ends must increase; a repeated or decreasing one never matches again
+            g = eol;
+        }
+        const char* fb = f;
+        const char* fe = g;
+        while (fb < fe && is_blank((unsigned char)*fb)) fb++;
+        while (fe > fb && is_blank((unsigned char)fe[-1])) fe--;
+        if (skip_first) skip_first = false;
+        else {
+            if (out && n < max_fields) out[n] = (fb == fe) ? NAN : field_value(fb, fe);
+            n++;
+        }
+        f = g;
+    }
+    return n;
+}
+
 // Parse one line [p, eol).  out == NULL: only count the fields.  Returns the number of fields
 // (0 for a blank / comment-only line).
 long parse_line(const char* p, const char* eol, const TextRules& R, double* out, long max_fields) {
+    if (R.field_ends) return parse_line_fixed(p, eol, R, out, max_fields);
     // cut the comment
     const char* end = p;
     while (end < eol && *end != '#') { if (*end == '"' || *end == '\\') return parse_line_quoted(p, eol, R, out, max_fields); end++; }
@@ -222,7 +256,12 @@ template <class F>
 void parallel_for(size_t n, F fn) { HostPool::get().run(n, fn); }
 
 // first pass: rules, header, width, segmentation and the number of data rows of every segment
-bool make_plan(const Mapped& M, int has_row_names, int has_col_names, const char* delimiters, size_t seg_bytes, Plan& P) {
+bool make_plan(const Mapped& M, int has_row_names, int has_col_names, const char* delimiters, const int* field_ends, int n_ends,
+               size_t seg_bytes, Plan& P) {
+    if (n_ends < 0 || (n_ends > 0 && !field_ends)) return set_error("field_ends: %d ends but no array", n_ends);
+    for (int i = 0; i < n_ends; i++) if (field_ends[i] <= 0) return set_error("field_ends[%d] = %d: positions are counted from 1", i, field_ends[i]);
+    P.rules.field_ends = n_ends > 0 ? field_ends : nullptr;
+    P.rules.n_ends = n_ends > 0 ? n_ends : 0;
     memset(P.rules.delim, 0, sizeof P.rules.delim);
     const char* dl = delimiters ? delimiters : "|,\t";      // apop_opts.input_delimiters default
     for (const char* c = dl; *c; c++) P.rules.delim[(unsigned char)*c] = true;
@@ -238,7 +277,8 @@ bool make_plan(const Mapped& M, int has_row_names, int has_col_names, const char
             const char* eol = (nl > p && nl[-1] == '\n') ? nl - 1 : nl;
             // names may be quoted text: only count them when the line is plain
             bool blank = true;
-            for (const char* c = p; c < eol && *c != '#'; c++) if (!is_blank((unsigned char)*c)) { blank = false; break; }
+            if (P.rules.field_ends) blank = (eol == p);      // a fixed-width line is blank only when it has no characters
+            else for (const char* c = p; c < eol && *c != '#'; c++) if (!is_blank((unsigned char)*c)) { blank = false; break; }
             p = nl;
             if (!blank) break;
         }
@@ -304,14 +344,14 @@ void parse_segment(const Plan& P, size_t s, double* dst) {
 
 // Host-only reader with the same rules (what apop_text_to_data returns in ->matrix): *out is a
 // malloc'ed row-major n x k buffer the caller frees.  Used by the CPU tests; no device needed.
-extern "C" int apop_b200_text_to_host(const char* path, int has_row_names, int has_col_names, const char* delimiters,
-                                      double** out, size_t* n_rows, size_t* k) {
+static int text_to_host_impl(const char* path, int has_row_names, int has_col_names, const char* delimiters,
+                             const int* field_ends, int n_ends, double** out, size_t* n_rows, size_t* k) {
     LOCK;
     if (!path || !out || !n_rows || !k) { set_error("apop_b200_text_to_host: NULL argument"); return 1; }
     Mapped M;
     if (!M.open(path)) { set_error("trouble opening %s", path); return 1; }
     Plan P;
-    if (!make_plan(M, has_row_names, has_col_names, delimiters, (size_t)8 << 20, P)) return 1;
+    if (!make_plan(M, has_row_names, has_col_names, delimiters, field_ends, n_ends, (size_t)8 << 20, P)) return 1;
     double* buf = (double*)malloc(sizeof(double) * std::max<size_t>(P.n_rows * (size_t)P.k, 1));
     if (!buf) { set_error("out of host memory"); return 1; }
     std::vector<size_t> start(P.seg_rows.size() + 1, 0);
@@ -321,8 +361,19 @@ extern "C" int apop_b200_text_to_host(const char* path, int has_row_names, int h
     return 0;
 }
 
-extern "C" apop_data* apop_b200_text_to_resident(const char* path, int has_row_names, int has_col_names,
-                                                 const char* delimiters, int outcome_col0) {
+extern "C" int apop_b200_text_to_host(const char* path, int has_row_names, int has_col_names, const char* delimiters,
+                                      double** out, size_t* n_rows, size_t* k) {
+    return text_to_host_impl(path, has_row_names, has_col_names, delimiters, nullptr, 0, out, n_rows, k);
+}
+// the fixed-width form (.field_ends of apop_text_to_data): n_field_ends 1-based end positions
+extern "C" int apop_b200_text_to_host_fixed(const char* path, int has_row_names, int has_col_names, const int* field_ends,
+                                            int n_field_ends, double** out, size_t* n_rows, size_t* k) {
+    if (!field_ends || n_field_ends <= 0) { set_error("apop_b200_text_to_host_fixed: no field ends"); return 1; }
+    return text_to_host_impl(path, has_row_names, has_col_names, nullptr, field_ends, n_field_ends, out, n_rows, k);
+}
+
+static apop_data* text_to_resident_impl(const char* path, int has_row_names, int has_col_names, const char* delimiters,
+                                        const int* field_ends, int n_ends, int outcome_col0) {
     LOCK;
     if (!path) { set_error("apop_b200_text_to_resident: NULL path"); return nullptr; }
     if (!require_ready()) return nullptr;
@@ -332,7 +383,7 @@ extern "C" apop_data* apop_b200_text_to_resident(const char* path, int has_row_n
     if (!M.open(path)) { set_error("trouble opening %s", path); return nullptr; }
     Plan P;
     const size_t seg_bytes = (size_t)4 << 20;
-    if (!make_plan(M, has_row_names, has_col_names, delimiters, seg_bytes, P)) return nullptr;
+    if (!make_plan(M, has_row_names, has_col_names, delimiters, field_ends, n_ends, seg_bytes, P)) return nullptr;
     const int k = (int)P.k;
     const bool col0 = outcome_col0 != 0 && k >= 1;
     const size_t n = P.n_rows;
@@ -407,4 +458,14 @@ extern "C" apop_data* apop_b200_text_to_resident(const char* path, int has_row_n
     }
     R.reg[d] = r;
     return d;
+}
+
+extern "C" apop_data* apop_b200_text_to_resident(const char* path, int has_row_names, int has_col_names,
+                                                 const char* delimiters, int outcome_col0) {
+    return text_to_resident_impl(path, has_row_names, has_col_names, delimiters, nullptr, 0, outcome_col0);
+}
+extern "C" apop_data* apop_b200_text_to_resident_fixed(const char* path, int has_row_names, int has_col_names,
+                                                       const int* field_ends, int n_field_ends, int outcome_col0) {
+    if (!field_ends || n_field_ends <= 0) { set_error("apop_b200_text_to_resident_fixed: no field ends"); return nullptr; }
+    return text_to_resident_impl(path, has_row_names, has_col_names, nullptr, field_ends, n_field_ends, outcome_col0);
 }

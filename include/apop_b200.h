@@ -279,8 +279,9 @@ int apop_b200_logit_expected(apop_data *d, apop_model *m, double *probs, double 
  * (apop_conversions.m4.c:339-403) that are honoured: delimiter set (NULL = "|,\t"), '#' comments, blank
  * lines, white space around fields, has_col_names (1/'y': the first non-blank line is skipped),
  * has_row_names (1/'y': the first field of every row is skipped), an empty field = NaN unless the
- * delimiter closing it is a space or tab, text fields = 0, strtod number syntax, quoted fields ("..." read
- * verbatim with the marks stripped) and backslash escapes.  Fixed-width fields (.field_ends) are refused.  outcome_col0 != 0: column 0 is the outcome
+ * delimiter closing it is a space or tab, strtod number syntax, NaN for a field strtod cannot convert (what the
+ * reference's code does, :659-666; its format page says zeros, :363), quoted fields ("..." read verbatim with the
+ * marks stripped) and backslash escapes.  Fixed-width layouts: the _fixed forms below.  outcome_col0 != 0: column 0 is the outcome
  * (ols_shuffle while tiling).  Returns a device-only header (sizes set, data pointers NULL) that is
  * resident; free it with apop_b200_synth_free.  NULL on error. */
 apop_data *apop_b200_text_to_resident(const char *path, int has_row_names, int has_col_names,
@@ -289,6 +290,14 @@ apop_data *apop_b200_text_to_resident(const char *path, int has_row_names, int h
  * row-major n x k buffer owned by the caller.  Needs no device. */
 int apop_b200_text_to_host(const char *path, int has_row_names, int has_col_names, const char *delimiters,
                            double **out, size_t *n_rows, size_t *k);
+/* Fixed-width files: apop_text_to_data(.field_ends = ...), parse_a_fixed_line (apop_conversions.m4.c:434-464).
+ * field_ends[i] is the 1-based position of the last character of field i; characters after the last given end form
+ * one more field; no comments, quotes or delimiters; a line without characters is blank; each field converts like
+ * any other (strtod skips leading white space; empty or unconvertible = NaN). */
+apop_data *apop_b200_text_to_resident_fixed(const char *path, int has_row_names, int has_col_names,
+                                            const int *field_ends, int n_field_ends, int outcome_col0);
+int apop_b200_text_to_host_fixed(const char *path, int has_row_names, int has_col_names, const int *field_ends,
+                                 int n_field_ends, double **out, size_t *n_rows, size_t *k);
 
 /* Row reductions the models are built from (apop_map_sum / apop_matrix_sum,
  * apop_mapply.m4.c:485, apop_stats.m4.c:15,310) over a resident data set:
